@@ -1,0 +1,132 @@
+// Shared device/host helpers for libesr (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "esr.h"
+
+namespace esr {
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing: no exception crosses the C ABI; the CUDA error string is kept per thread.
+// ---------------------------------------------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+
+#define ESR_CUDA(call)                                              \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) {                                       \
+      ::esr::set_cuda_error(e__, #call, __FILE__, __LINE__);        \
+      return ESR_ECUDA;                                             \
+    }                                                               \
+  } while (0)
+
+#define ESR_LAUNCH_CHECK() ESR_CUDA(cudaPeekAtLastError())
+
+#define ESR_REQUIRE(cond) \
+  do {                    \
+    if (!(cond)) return ESR_EINVAL; \
+  } while (0)
+
+int sm_count();  // cached per process (device of first call)
+
+#ifdef __CUDACC__
+#define ESR_HD __host__ __device__
+#else
+#define ESR_HD
+#endif
+ESR_HD static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+ESR_HD static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Carves a caller-provided workspace into 256-byte aligned pieces.
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T), 256);
+    return p;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Sum over a power-of-two group of G lanes (xor butterfly: every lane gets the total, and the
+// summation tree is fixed, so the result is bit-reproducible).
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+// Block-wide sum of NV values for blockDim.x <= 1024 (fixed tree => deterministic). Result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* [32*NV] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) smem[wid * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float x = lane < nw ? smem[lane * NV + k] : 0.f;
+      v[k] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+// 128-bit loads/stores with cache policy.
+//  ld_keep   : table rows that other work items of the same step will re-read (default caching).
+//  ld_stream : read-once data (accumulator rows, partials): evict-first in L2, not kept in L1.
+//  st_stream : written-once data (new rows, accumulator): evict-first.
+__device__ __forceinline__ float4 ld_keep(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void f4_fma(float4& acc, float s, float4 v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ void f4_add(float4& acc, float4 v) {
+  acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+}
+
+// optax.adagrad: a += g^2 ; p -= lr * g * rsqrt(a + eps)   (0 where a == 0)
+__device__ __forceinline__ void adagrad1(float& p, float& a, float g, float lr, float eps) {
+  a = fmaf(g, g, a);
+  const float inv = a > 0.f ? rsqrtf(a + eps) : 0.f;
+  p = fmaf(-lr * g, inv, p);
+}
+__device__ __forceinline__ void adagrad4(float4& p, float4& a, float4 g, float lr, float eps) {
+  adagrad1(p.x, a.x, g.x, lr, eps);
+  adagrad1(p.y, a.y, g.y, lr, eps);
+  adagrad1(p.z, a.z, g.z, lr, eps);
+  adagrad1(p.w, a.w, g.w, lr, eps);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace esr

@@ -1,0 +1,299 @@
+// Embedding-table row operations and the optimizer rules (HBM-bound, 128-bit accesses).
+//
+//  esr_table_gather_f32   <- jnp.take behind nn.Embed.__call__ (wikipedia/models.py:31-34,
+//                            spotify/models.py:43-44)
+//  esr_table_export_f32   <- reading state.params[...]['embedding'] (wikipedia/train_cooccurence.py:133)
+//  esr_sparse_adagrad_f32 <- optax.adagrad applied to the touched rows only (north-star rule)
+//  esr_scatter_rows_f32   <- the dense gradient pytree of jax.value_and_grad
+//                            (wikipedia/train_cooccurence.py:86-87): zero except the touched rows
+//  esr_dense_adam_f32     <- optax.adam via TrainState.apply_gradients (wikipedia/train_cooccurence.py:101,171)
+//  esr_dense_sgdm_f32     <- optax.sgd(momentum) (spotify/train_spotify.py:238-241)
+//
+// Row kernels: a group of TPR lanes (TPR = min(32, pow2ceil(D/4))) owns a row and every group
+// keeps kRowsPerGroup independent rows in flight, so each lane has several 16-byte loads
+// outstanding before the first use (the gather is latency-bound otherwise).
+#include "esr_common.cuh"
+
+namespace esr {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerGroup = 4;
+
+__device__ __forceinline__ const float4* cur_row(const float* r0, const float* r1, const uint8_t* ver, int64_t row,
+                                                 int D4) {
+  const float* base = (ver != nullptr && ver[row]) ? r1 : r0;
+  return reinterpret_cast<const float4*>(base) + row * D4;
+}
+
+// out[k,:] = table[ids[k],:]   (ids == nullptr: identity, i.e. export)
+template <int TPR>
+__global__ void __launch_bounds__(kThreads) k_gather(const float* __restrict__ r0, const float* __restrict__ r1,
+                                                     const uint8_t* __restrict__ ver, const int32_t* __restrict__ ids,
+                                                     int64_t n, int D4, float4* __restrict__ out) {
+  const int lane = threadIdx.x % TPR;
+  const int64_t group = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
+  const int64_t first = group * kRowsPerGroup;
+  const float4* src[kRowsPerGroup];
+#pragma unroll
+  for (int r = 0; r < kRowsPerGroup; ++r) {
+    const int64_t k = first + r;
+    src[r] = nullptr;
+    if (k < n) {
+      const int64_t row = ids ? (int64_t)ids[k] : k;
+      src[r] = cur_row(r0, r1, ver, row, D4);
+    }
+  }
+  for (int c = lane; c < D4; c += TPR) {
+    float4 v[kRowsPerGroup];
+#pragma unroll
+    for (int r = 0; r < kRowsPerGroup; ++r)
+      if (src[r]) v[r] = __ldg(src[r] + c);
+#pragma unroll
+    for (int r = 0; r < kRowsPerGroup; ++r)
+      if (src[r]) st_stream(out + (first + r) * D4 + c, v[r]);
+  }
+}
+
+// In-place Adagrad on the CURRENT buffer of each listed row (no concurrent readers).
+template <int TPR>
+__global__ void __launch_bounds__(kThreads) k_sparse_adagrad(float* __restrict__ r0, float* __restrict__ r1,
+                                                             const uint8_t* __restrict__ ver, float* __restrict__ acc,
+                                                             const int32_t* __restrict__ uniq,
+                                                             const int32_t* __restrict__ n_uniq, int D4,
+                                                             const float4* __restrict__ g, float lr, float eps) {
+  const int lane = threadIdx.x % TPR;
+  const int64_t group = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
+  const int64_t first = group * kRowsPerGroup;
+  const int64_t n = *n_uniq;
+#pragma unroll
+  for (int r = 0; r < kRowsPerGroup; ++r) {
+    const int64_t u = first + r;
+    if (u >= n) continue;
+    const int64_t row = uniq[u];
+    float4* p = const_cast<float4*>(cur_row(r0, r1, ver, row, D4));
+    float4* a = reinterpret_cast<float4*>(acc) + row * D4;
+    for (int c = lane; c < D4; c += TPR) {
+      float4 pv = p[c], av = ld_stream(a + c);
+      const float4 gv = ld_stream(g + u * D4 + c);
+      adagrad4(pv, av, gv, lr, eps);
+      p[c] = pv;
+      st_stream(a + c, av);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sparse_adagrad_bias(float* __restrict__ bias, float* __restrict__ bacc,
+                                                                  const int32_t* __restrict__ uniq,
+                                                                  const int32_t* __restrict__ n_uniq,
+                                                                  const float* __restrict__ gb, float lr, float eps) {
+  const int64_t u = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (u >= *n_uniq) return;
+  const int64_t row = uniq[u];
+  float p = bias[row], a = bacc[row];
+  adagrad1(p, a, gb[u], lr, eps);
+  bias[row] = p;
+  bacc[row] = a;
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(kThreads) k_scatter_rows(float4* __restrict__ dst, int D4,
+                                                           const int32_t* __restrict__ uniq,
+                                                           const int32_t* __restrict__ n_uniq,
+                                                           const float4* __restrict__ g, int accumulate) {
+  const int lane = threadIdx.x % TPR;
+  const int64_t group = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
+  const int64_t first = group * kRowsPerGroup;
+  const int64_t n = *n_uniq;
+#pragma unroll
+  for (int r = 0; r < kRowsPerGroup; ++r) {
+    const int64_t u = first + r;
+    if (u >= n) continue;
+    float4* d = dst + (int64_t)uniq[u] * D4;
+    for (int c = lane; c < D4; c += TPR) {
+      float4 v = ld_stream(g + u * D4 + c);
+      if (accumulate) f4_add(v, d[c]);
+      d[c] = v;
+    }
+  }
+}
+
+// optax.adam: mu = b1 mu + (1-b1) g ; nu = b2 nu + (1-b2) g^2 ; p -= lr (mu/c1) / (sqrt(nu/c2) + eps)
+__device__ __forceinline__ void adam1(float& p, float g, float& mu, float& nu, float lr, float b1, float b2, float eps,
+                                      float c1, float c2) {
+  mu = b1 * mu + (1.f - b1) * g;
+  nu = b2 * nu + (1.f - b2) * (g * g);
+  const float mhat = mu / c1;
+  const float vhat = nu / c2;
+  p = p - lr * mhat / (sqrtf(vhat) + eps);
+}
+
+__global__ void __launch_bounds__(kThreads) k_dense_adam(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ mu, float* __restrict__ nu, int64_t n,
+                                                         float lr, float b1, float b2, float eps, float c1,
+                                                         float c2) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    float4 m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
+    adam1(pv.x, gv.x, m.x, v.x, lr, b1, b2, eps, c1, c2);
+    adam1(pv.y, gv.y, m.y, v.y, lr, b1, b2, eps, c1, c2);
+    adam1(pv.z, gv.z, m.z, v.z, lr, b1, b2, eps, c1, c2);
+    adam1(pv.w, gv.w, m.w, v.w, lr, b1, b2, eps, c1, c2);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(mu)[i] = m;
+    reinterpret_cast<float4*>(nu)[i] = v;
+  }
+  // tail (n % 4) by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    adam1(p[i], g[i], mu[i], nu[i], lr, b1, b2, eps, c1, c2);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_dense_sgdm(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ tr, int64_t n, float lr, float mom) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    float4 t = reinterpret_cast<float4*>(tr)[i];
+    t.x = gv.x + mom * t.x; t.y = gv.y + mom * t.y; t.z = gv.z + mom * t.z; t.w = gv.w + mom * t.w;
+    pv.x -= lr * t.x; pv.y -= lr * t.y; pv.z -= lr * t.z; pv.w -= lr * t.w;
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(tr)[i] = t;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float t = g[i] + mom * tr[i];
+    tr[i] = t;
+    p[i] -= lr * t;
+  }
+}
+
+int tpr_for(int D4) {
+  int t = 1;
+  while (t < D4 && t < 32) t <<= 1;
+  return t;
+}
+
+bool table_ok(const EsrTable* t) {
+  return t != nullptr && t->struct_size >= sizeof(EsrTable) && t->D > 0 && (t->D % 4) == 0 && t->V >= 0 &&
+         t->rows[0] != nullptr && (reinterpret_cast<uintptr_t>(t->rows[0]) % 16) == 0 &&
+         (t->rows[1] == nullptr || (reinterpret_cast<uintptr_t>(t->rows[1]) % 16) == 0) &&
+         ((t->ver == nullptr) || (t->rows[1] != nullptr));
+}
+
+#define ESR_DISPATCH_TPR(tpr, CALL) \
+  switch (tpr) {                    \
+    case 1: { constexpr int TPR = 1; CALL; } break;   \
+    case 2: { constexpr int TPR = 2; CALL; } break;   \
+    case 4: { constexpr int TPR = 4; CALL; } break;   \
+    case 8: { constexpr int TPR = 8; CALL; } break;   \
+    case 16: { constexpr int TPR = 16; CALL; } break; \
+    default: { constexpr int TPR = 32; CALL; } break; \
+  }
+
+unsigned row_grid(int64_t rows, int tpr) {
+  const int64_t groups = ceil_div(rows, kRowsPerGroup);
+  return (unsigned)ceil_div(groups * tpr, kThreads);
+}
+
+int gather_impl(const EsrTable* t, const int32_t* ids, int64_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return ESR_OK;
+  const int D4 = t->D / 4;
+  const int tpr = tpr_for(D4);
+  ESR_DISPATCH_TPR(tpr, (k_gather<TPR><<<row_grid(n, tpr), kThreads, 0, stream>>>(
+                            t->rows[0], t->rows[1], t->ver, ids, n, D4, reinterpret_cast<float4*>(out))));
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+}  // namespace
+}  // namespace esr
+
+using namespace esr;
+
+extern "C" int esr_table_gather_f32(const EsrTable* t, const int32_t* ids, int64_t n, float* out, esr_stream_t stream) {
+  ESR_REQUIRE(table_ok(t) && n >= 0 && (n == 0 || (ids != nullptr && out != nullptr)));
+  ESR_REQUIRE((reinterpret_cast<uintptr_t>(out) % 16) == 0);
+  return gather_impl(t, ids, n, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_table_export_f32(const EsrTable* t, float* out, esr_stream_t stream) {
+  ESR_REQUIRE(table_ok(t) && (t->V == 0 || out != nullptr) && (reinterpret_cast<uintptr_t>(out) % 16) == 0);
+  return gather_impl(t, nullptr, t->V, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_sparse_adagrad_f32(EsrTable* t, const int32_t* uniq, const int32_t* n_uniq, int64_t cap,
+                                      const float* g, const float* gb, float lr, float eps, esr_stream_t stream_) {
+  ESR_REQUIRE(table_ok(t) && cap >= 0 && uniq != nullptr && n_uniq != nullptr);
+  ESR_REQUIRE(g == nullptr || (t->acc != nullptr && (reinterpret_cast<uintptr_t>(g) % 16) == 0));
+  ESR_REQUIRE(gb == nullptr || (t->bias != nullptr && t->bias_acc != nullptr));
+  if (cap == 0) return ESR_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int D4 = t->D / 4;
+  const int tpr = tpr_for(D4);
+  if (g != nullptr) {
+    ESR_DISPATCH_TPR(tpr, (k_sparse_adagrad<TPR><<<row_grid(cap, tpr), kThreads, 0, stream>>>(
+                              t->rows[0], t->rows[1], t->ver, t->acc, uniq, n_uniq, D4,
+                              reinterpret_cast<const float4*>(g), lr, eps)));
+    ESR_LAUNCH_CHECK();
+  }
+  if (gb != nullptr) {
+    k_sparse_adagrad_bias<<<(unsigned)ceil_div(cap, kThreads), kThreads, 0, stream>>>(t->bias, t->bias_acc, uniq, n_uniq,
+                                                                                      gb, lr, eps);
+    ESR_LAUNCH_CHECK();
+  }
+  return ESR_OK;
+}
+
+extern "C" int esr_scatter_rows_f32(float* dst, int32_t D, const int32_t* uniq, const int32_t* n_uniq, int64_t cap,
+                                    const float* g, int32_t accumulate, esr_stream_t stream_) {
+  ESR_REQUIRE(dst != nullptr && D > 0 && (D % 4) == 0 && uniq != nullptr && n_uniq != nullptr && g != nullptr && cap >= 0);
+  ESR_REQUIRE((reinterpret_cast<uintptr_t>(dst) % 16) == 0 && (reinterpret_cast<uintptr_t>(g) % 16) == 0);
+  if (cap == 0) return ESR_OK;
+  const int D4 = D / 4;
+  const int tpr = tpr_for(D4);
+  ESR_DISPATCH_TPR(tpr, (k_scatter_rows<TPR><<<row_grid(cap, tpr), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+                            reinterpret_cast<float4*>(dst), D4, uniq, n_uniq, reinterpret_cast<const float4*>(g),
+                            accumulate)));
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+static unsigned dense_grid(int64_t n) {
+  const int64_t want = ceil_div(ceil_div(n, 4), kThreads);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+extern "C" int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, float lr, float b1, float b2,
+                                  float eps, int64_t count, esr_stream_t stream_) {
+  ESR_REQUIRE(n >= 0 && count >= 1);
+  if (n == 0) return ESR_OK;
+  ESR_REQUIRE(p && g && mu && nu);
+  ESR_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mu) |
+                reinterpret_cast<uintptr_t>(nu)) % 16) == 0);
+  // bias corrections in double on the host, like optax evaluates 1 - b^count in python floats / f32
+  const float c1 = (float)(1.0 - pow((double)b1, (double)count));
+  const float c2 = (float)(1.0 - pow((double)b2, (double)count));
+  k_dense_adam<<<dense_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p, g, mu, nu, n, lr, b1, b2, eps,
+                                                                                   c1, c2);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+extern "C" int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float lr, float momentum,
+                                  esr_stream_t stream_) {
+  ESR_REQUIRE(n >= 0);
+  if (n == 0) return ESR_OK;
+  ESR_REQUIRE(p && g && trace);
+  ESR_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(trace)) % 16) == 0);
+  k_dense_sgdm<<<dense_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p, g, trace, n, lr, momentum);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}

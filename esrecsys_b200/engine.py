@@ -1,0 +1,228 @@
+"""Host-side objects around the C ABI: the versioned embedding table, the per-batch index plan
+and the fused GloVe step.  torch owns every device buffer and stream; all arithmetic happens in
+``libesr.so`` (see include/esr.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _dev(device):
+    L.require_cuda()
+    return torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+
+
+class EmbeddingTable:
+    """``nn.Embed`` parameter ``{'embedding': f32[V, D]}`` (wikipedia/models.py:16-19,
+    spotify/models.py:30-31) plus its Adagrad slot, laid out for the batch-synchronous sparse update:
+    two row buffers + a per-row version byte (include/esr.h, EsrTable).
+
+    ``sparse=False`` keeps a single buffer (dense Adam / SGD-momentum parity modes, or the compact
+    fetched-row table of the row-sharded path).
+    """
+
+    def __init__(self, V, D, device=None, sparse=True, with_bias=True, init_acc=0.1):
+        self.device = _dev(device)
+        if D % 4:
+            raise ValueError("D must be a multiple of 4 (16-byte rows)")
+        self.V, self.D, self.sparse = int(V), int(D), bool(sparse)
+        dev = self.device
+        self.rows0 = torch.zeros(V, D, dtype=torch.float32, device=dev)
+        self.rows1 = torch.zeros(V, D, dtype=torch.float32, device=dev) if sparse else None
+        self.ver = torch.zeros(V, dtype=torch.uint8, device=dev) if sparse else None
+        self.acc = torch.full((V, D), float(init_acc), dtype=torch.float32, device=dev) if sparse else None
+        self.bias = torch.zeros(V, dtype=torch.float32, device=dev) if with_bias else None
+        self.bias_acc = (torch.full((V,), float(init_acc), dtype=torch.float32, device=dev)
+                         if (with_bias and sparse) else None)
+        self._struct = None
+
+    # -- construction ----------------------------------------------------------------------
+    @classmethod
+    def from_dense(cls, E, bias=None, device=None, sparse=True, init_acc=0.1):
+        E = torch.as_tensor(E)
+        t = cls(E.shape[0], E.shape[1], device, sparse, bias is not None, init_acc)
+        t.rows0.copy_(E.to(torch.float32))
+        if bias is not None:
+            t.bias.copy_(torch.as_tensor(bias).to(torch.float32).reshape(-1))
+        return t
+
+    def struct(self) -> L.EsrTable:
+        if self._struct is None:
+            s = L.EsrTable()
+            s.struct_size = C.sizeof(L.EsrTable)
+            s.D, s.V = self.D, self.V
+            s.rows[0] = L.ptr(self.rows0)
+            s.rows[1] = L.ptr(self.rows1)
+            s.ver = L.ptr(self.ver)
+            s.acc = L.ptr(self.acc)
+            s.bias = L.ptr(self.bias)
+            s.bias_acc = L.ptr(self.bias_acc)
+            self._struct = s
+        return self._struct
+
+    # -- reads -----------------------------------------------------------------------------
+    def gather(self, ids, out=None):
+        """``jnp.take(embedding, ids, axis=0)`` (nn.Embed.__call__)."""
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        n = ids.numel()
+        if out is None:
+            out = torch.empty(n, self.D, dtype=torch.float32, device=self.device)
+        L.check(L.lib().esr_table_gather_f32(C.byref(self.struct()), L.ptr(ids), n, L.ptr(out), L.stream_ptr()),
+                "esr_table_gather_f32")
+        return out.view(*ids.shape, self.D)
+
+    def dense(self):
+        """The dense ``f32[V, D]`` array ``state.params[..]['embedding']`` holds in the reference."""
+        if not self.sparse:
+            return self.rows0
+        out = torch.empty(self.V, self.D, dtype=torch.float32, device=self.device)
+        L.check(L.lib().esr_table_export_f32(C.byref(self.struct()), L.ptr(out), L.stream_ptr()), "esr_table_export_f32")
+        return out
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in
+                   (self.rows0, self.rows1, self.ver, self.acc, self.bias, self.bias_acc) if t is not None)
+
+
+class IndexPlan:
+    """Device buffers + descriptor of one batch's index plan (EsrPlan)."""
+
+    def __init__(self, n_slots, V, device=None, with_partner=True):
+        self.device = _dev(device)
+        n = int(n_slots)
+        self.n_slots = n
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        cap = max(n, 1)
+        self.sorted_keys = torch.empty(cap, **i32)
+        self.perm = torch.empty(cap, **i32)
+        self.partner = torch.empty(cap, **i32) if with_partner else None
+        self.useg = torch.empty(cap, **i32)
+        self.uniq = torch.empty(cap, **i32)
+        self.seg_off = torch.empty(cap + 1, **i32)
+        self.n_uniq = torch.zeros(1, **i32)
+        self.ws_bytes = int(L.lib().esr_plan_workspace_bytes(n))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.key_bits = max(1, int(math.ceil(math.log2(max(int(V), 2)))))
+        s = L.EsrPlan()
+        s.struct_size = C.sizeof(L.EsrPlan)
+        s.key_bits = self.key_bits
+        s.n_slots = n
+        s.keys = None
+        s.sorted_keys, s.perm = L.ptr(self.sorted_keys), L.ptr(self.perm)
+        s.partner = L.ptr(self.partner)
+        s.useg, s.uniq, s.seg_off, s.n_uniq = (L.ptr(self.useg), L.ptr(self.uniq), L.ptr(self.seg_off),
+                                               L.ptr(self.n_uniq))
+        self.s = s
+        self._keys = None
+
+    def build(self, keys, stream=None):
+        """keys: int32 device tensor with n_slots elements (for GloVe the flat (2,B) batch)."""
+        assert keys.dtype == torch.int32 and keys.is_cuda and keys.is_contiguous() and keys.numel() == self.n_slots
+        self._keys = keys  # keep alive until the next build
+        self.s.keys = L.ptr(keys)
+        L.check(L.lib().esr_plan_build_i32(C.byref(self.s), L.ptr(self.ws), self.ws_bytes, L.stream_ptr(stream)),
+                "esr_plan_build_i32")
+        return self
+
+    def remap_ids(self, out=None, stream=None):
+        if out is None:
+            out = torch.empty(self.n_slots, dtype=torch.int32, device=self.device)
+        L.check(L.lib().esr_plan_remap_ids_i32(C.byref(self.s), L.ptr(out), L.stream_ptr(stream)), "esr_plan_remap_ids_i32")
+        return out
+
+    def host_view(self):
+        """(sorted_keys, perm, uniq, seg_off) as NumPy, trimmed to n_uniq (synchronises)."""
+        U = int(self.n_uniq.item())
+        n = self.n_slots
+        return (self.sorted_keys[:n].cpu().numpy(), self.perm[:n].cpu().numpy(), self.uniq[:U].cpu().numpy(),
+                self.seg_off[:U + 1].cpu().numpy())
+
+
+class GloveStep:
+    """apply_model + update_model of wikipedia/train_cooccurence.py:71-101 as three stream-ordered
+    phases over an IndexPlan (include/esr.h: esr_glove_prep/rows/finish)."""
+
+    def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", eps=1e-7,
+                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None):
+        self.table = table
+        self.B = int(B)
+        dev = table.device
+        cfg = L.EsrGloveCfg()
+        cfg.struct_size = C.sizeof(L.EsrGloveCfg)
+        cfg.bias_mode = L.BIAS_MODES[bias_mode]
+        cfg.rows_mode = L.ROWS_EMIT_GRADS if emit_grads else L.ROWS_UPDATE
+        cfg.impl = L.IMPL_AUTO
+        cfg.B = self.B
+        cfg.B_global = int(B_global if B_global is not None else B)
+        cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
+        cfg.chunk = chunk
+        self.cfg = cfg
+        self.emit = bool(emit_grads)
+        self.ws_bytes = int(L.lib().esr_glove_workspace_bytes(self.B, table.D, chunk))
+        self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
+        self.scalars = torch.zeros(L.GLOVE_NSCAL, dtype=torch.float32, device=dev)
+        n = max(2 * self.B, 1)
+        self.dE = torch.empty(n, table.D, dtype=torch.float32, device=dev) if emit_grads else None
+        self.db = torch.empty(n, dtype=torch.float32, device=dev) if emit_grads else None
+
+    def _args(self, plan):
+        return C.byref(self.table.struct()), C.byref(plan.s), C.byref(self.cfg)
+
+    def prep(self, plan, counts, stream=None):
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_prep_f32(t, p, L.ptr(counts), c, L.ptr(self.scalars), L.ptr(self.ws), self.ws_bytes,
+                                           L.stream_ptr(stream)), "esr_glove_prep_f32")
+
+    def rows(self, plan, stream=None):
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_rows_f32(t, p, c, L.ptr(self.scalars), L.ptr(self.dE), L.ptr(self.ws), self.ws_bytes,
+                                           L.stream_ptr(stream)), "esr_glove_rows_f32")
+
+    def finish(self, plan, stream=None):
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_finish_f32(t, p, c, L.ptr(self.scalars), L.ptr(self.db), L.ptr(self.ws), self.ws_bytes,
+                                             L.stream_ptr(stream)), "esr_glove_finish_f32")
+
+    def run(self, plan, counts, stream=None):
+        """All three phases.  Returns the device scalars block (loss at index SC_LOSS)."""
+        assert counts.dtype == torch.float32 and counts.is_cuda and counts.numel() == self.B
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_step_f32(t, p, L.ptr(counts), c, L.ptr(self.scalars), L.ptr(self.dE), L.ptr(self.db),
+                                           L.ptr(self.ws), self.ws_bytes, L.stream_ptr(stream)), "esr_glove_step_f32")
+        return self.scalars
+
+
+def sparse_adagrad(table: EmbeddingTable, uniq, n_uniq, g, gb, lr, eps=1e-7, stream=None):
+    cap = uniq.numel()
+    L.check(L.lib().esr_sparse_adagrad_f32(C.byref(table.struct()), L.ptr(uniq), L.ptr(n_uniq), cap, L.ptr(g), L.ptr(gb),
+                                           lr, eps, L.stream_ptr(stream)), "esr_sparse_adagrad_f32")
+
+
+def scatter_rows(dst, uniq, n_uniq, g, accumulate=False, stream=None):
+    D = dst.shape[1] if dst.dim() == 2 else 1
+    L.check(L.lib().esr_scatter_rows_f32(L.ptr(dst), D, L.ptr(uniq), L.ptr(n_uniq), uniq.numel(), L.ptr(g),
+                                         1 if accumulate else 0, L.stream_ptr(stream)), "esr_scatter_rows_f32")
+
+
+def dense_adam(p, g, mu, nu, lr, count, b1=0.9, b2=0.999, eps=1e-8, stream=None):
+    L.check(L.lib().esr_dense_adam_f32(L.ptr(p), L.ptr(g), L.ptr(mu), L.ptr(nu), p.numel(), lr, b1, b2, eps, int(count),
+                                       L.stream_ptr(stream)), "esr_dense_adam_f32")
+
+
+def dense_sgdm(p, g, trace, lr, momentum, stream=None):
+    L.check(L.lib().esr_dense_sgdm_f32(L.ptr(p), L.ptr(g), L.ptr(trace), p.numel(), lr, momentum, L.stream_ptr(stream)),
+            "esr_dense_sgdm_f32")
+
+
+def check_ids(ids, V):
+    """Debug validator: number of ids outside [0, V) (synchronises)."""
+    ids = ids.contiguous()
+    n_bad = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    L.check(L.lib().esr_check_ids_i32(L.ptr(ids), ids.numel(), int(V), L.ptr(n_bad), L.stream_ptr()), "esr_check_ids_i32")
+    return int(n_bad.item())

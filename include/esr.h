@@ -1,0 +1,197 @@
+/*
+ * esr.h -- C ABI of libesr.so, the B200 (sm_100a) embedding-training hot path for the
+ * ESRecsys trainers.
+ *
+ * The reference (BBischof/ESRecsys) is pure Python: it has NO FFI/plugin boundary.  Its hot path
+ * runs through jax/flax/optax calls, so each entry point below cites the reference call it
+ * replaces (paths relative to the reference root).  The reference-side binding a maintainer
+ * would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; POD config structs start with `struct_size` so the
+ *    struct can grow without breaking old callers.
+ *  - Every pointer is DEVICE memory owned by the caller unless stated otherwise.  The library
+ *    never allocates device memory, never keeps a pointer after return and never synchronises:
+ *    all work is enqueued on the `stream` argument (a cudaStream_t passed as void*).
+ *  - Return value: 0 (ESR_OK) or a negative ESR_E* code; esr_strerror() names it and
+ *    esr_last_cuda_error() returns the CUDA error string behind the last ESR_ECUDA of the
+ *    calling thread.  No C++ exception crosses this boundary.
+ *  - Ids are NOT range-checked on the hot path (XLA clamps silently in the reference; we
+ *    document "validated by the caller").  esr_check_ids_i32() is the debug validator.
+ *  - Thread-compatible: no global mutable state besides the thread-local error string.
+ */
+#ifndef ESR_H_
+#define ESR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESR_VERSION 100 /* 0.1.0 */
+
+typedef void* esr_stream_t; /* cudaStream_t */
+
+enum {
+  ESR_OK = 0,
+  ESR_EINVAL = -1,     /* bad shape / alignment / null pointer / unknown enum */
+  ESR_EWORKSPACE = -2, /* workspace smaller than esr_*_workspace_bytes() */
+  ESR_ECUDA = -3,      /* a CUDA call or launch failed; see esr_last_cuda_error() */
+  ESR_ENOTSUP = -4     /* valid request this build does not implement */
+};
+
+enum { ESR_OPT_ADAGRAD = 0, ESR_OPT_ADAM = 1, ESR_OPT_SGDM = 2 };
+enum { ESR_BIAS_REFERENCE_BROADCAST = 0, ESR_BIAS_PER_PAIR = 1 };
+enum { ESR_ROWS_UPDATE = 0, ESR_ROWS_EMIT_GRADS = 1 };
+enum { ESR_IMPL_AUTO = 0, ESR_IMPL_LDG = 1, ESR_IMPL_TMA = 2 };
+enum { ESR_LOSS_HINGE = 0, ESR_LOSS_SOFTMAX = 1 };
+
+int esr_version(void);
+const char* esr_strerror(int rc);
+const char* esr_last_cuda_error(void);
+/* sm count and compute capability of the current device. */
+int esr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding table.  Replaces the flax param `{'embedding': f32[V,D]}` of nn.Embed
+ * (wikipedia/models.py:16-19, spotify/models.py:30-31) plus its optimizer slot.
+ *
+ * Sparse (Adagrad) training keeps TWO row buffers and a per-row version byte: a step reads row r
+ * from rows[ver[r]] and writes the updated row to rows[1-ver[r]]; versions of the touched rows
+ * flip at the end of the step.  That makes the batch-synchronous update (every gradient taken at
+ * the OLD parameters, exactly what XLA's scatter-add gives the reference) race-free without ever
+ * materialising a gradient buffer: each touched row is read once and written once.
+ * rows[1] == NULL and ver == NULL describe a plain dense table (dense Adam / SGD-momentum modes).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsrTable {
+  uint32_t struct_size;
+  int32_t D;        /* row width in floats; D % 4 == 0, rows 16-byte aligned */
+  int64_t V;        /* rows */
+  float* rows[2];   /* [V*D] each */
+  uint8_t* ver;     /* [V] or NULL */
+  float* acc;       /* [V*D] Adagrad accumulator, or NULL */
+  float* bias;      /* [V] GloVe bias (wikipedia/models.py:18-19), updated in place, or NULL */
+  float* bias_acc;  /* [V] or NULL */
+} EsrTable;
+
+/* out[k, :] = current row ids[k].  Replaces jnp.take behind nn.Embed.__call__
+ * (wikipedia/models.py:31-34, spotify/models.py:43-44). */
+int esr_table_gather_f32(const EsrTable* t, const int32_t* ids, int64_t n, float* out,
+                         esr_stream_t stream);
+/* out[V*D] = dense current table (what state.params['..']['embedding'] holds in the reference). */
+int esr_table_export_f32(const EsrTable* t, float* out, esr_stream_t stream);
+/* Debug validator: *n_bad (device int32) = number of ids outside [0, V). */
+int esr_check_ids_i32(const int32_t* ids, int64_t n, int64_t V, int32_t* n_bad, esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Index plan of one batch (integer bookkeeping only; depends on the ids, never on the table, so
+ * it can be built for batch t+1 while batch t trains).  Slots: s in [0, 2B), key[s] = ids[s]
+ * with ids the (2,B) int32 batch of wikipedia/cooccurrence_matrix.py:103-114 laid out flat
+ * ([i ; j]: both roles index the same table, wikipedia/models.py:31-34).
+ * Bit-exact contract: oracle/index.py (stable sort by row, unique rows, segment offsets).
+ * Replaces the gather/scatter index handling XLA performs inside jnp.take and its VJP.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsrPlan {
+  uint32_t struct_size;
+  int32_t key_bits;      /* number of significant key bits (ceil(log2 V)); 0 => 32 */
+  int64_t n_slots;       /* 2B for GloVe */
+  const int32_t* keys;   /* [n_slots] input */
+  int32_t* sorted_keys;  /* [n_slots] */
+  int32_t* perm;         /* [n_slots] sorted position -> slot, stable */
+  int32_t* partner;      /* [n_slots] row id of the other role of the slot's pair, or NULL */
+  int32_t* useg;         /* [n_slots] sorted position -> index into uniq */
+  int32_t* uniq;         /* [n_slots] capacity; first *n_uniq valid */
+  int32_t* seg_off;      /* [n_slots+1] capacity; first *n_uniq+1 valid */
+  int32_t* n_uniq;       /* device scalar */
+} EsrPlan;
+
+size_t esr_plan_workspace_bytes(int64_t n_slots);
+int esr_plan_build_i32(const EsrPlan* plan, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* ids_out[perm[p]] = useg[p]: rewrites a batch's row ids as indices into its own unique-row list
+ * (used by the row-sharded path, where the "table" of a step is the compact buffer of fetched rows). */
+int esr_plan_remap_ids_i32(const EsrPlan* plan, int32_t* ids_out, esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GloVe step.  Replaces apply_model + update_model (wikipedia/train_cooccurence.py:71-101):
+ * Glove.__call__ (wikipedia/models.py:21-38), glove_loss (:76-84), jax.value_and_grad (:86-87),
+ * TrainState.apply_gradients (:101).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsrGloveCfg {
+  uint32_t struct_size;
+  int32_t bias_mode;   /* ESR_BIAS_* ; REFERENCE_BROADCAST reproduces wikipedia/models.py:37 */
+  int32_t rows_mode;   /* ESR_ROWS_UPDATE (fused sparse Adagrad) or ESR_ROWS_EMIT_GRADS */
+  int32_t impl;        /* ESR_IMPL_* kernel variant of the row pass */
+  int64_t B;           /* pairs in this (local) batch */
+  int64_t B_global;    /* divisor of the loss (== B on one GPU; sum over ranks when sharded) */
+  float lr;
+  float eps;           /* Adagrad eps (optax default 1e-7) */
+  float x_max;         /* 100.0  wikipedia/train_cooccurence.py:80 */
+  float alpha;         /* 0.75   wikipedia/train_cooccurence.py:81 */
+  int32_t chunk;       /* sorted slots per work item; 0 => default */
+  int32_t reserved;
+} EsrGloveCfg;
+
+/* Scalars block (device float[ESR_GLOVE_NSCAL]) shared by the three phases.  After
+ * esr_glove_prep it holds LOCAL sums; a multi-GPU caller all-reduces [0..2] before
+ * esr_glove_rows and [3..4] before esr_glove_finish. */
+enum {
+  ESR_SC_SUM_BS = 0,  /* sum_r bs_r,  bs_r = b[i_r] + b[j_r] */
+  ESR_SC_SUM_BS2 = 1, /* sum_r bs_r^2 */
+  ESR_SC_S0 = 2,      /* sum_c w_c */
+  ESR_SC_S1 = 3,      /* sum_c w_c res_c */
+  ESR_SC_S2 = 4,      /* sum_c w_c res_c^2   (per_pair: sum_c w_c (res_c - bs_c)^2) */
+  ESR_SC_LOSS = 5,    /* written by esr_glove_finish */
+  ESR_GLOVE_NSCAL = 8
+};
+
+size_t esr_glove_workspace_bytes(int64_t B, int32_t D, int32_t chunk);
+/* Phase 1: per-slot w, t, bs, buffer versions; sums [0..2]. */
+int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const float* counts,
+                       const EsrGloveCfg* cfg, float* scalars, void* ws, size_t ws_bytes,
+                       esr_stream_t stream);
+/* Phase 2: fused gather -> dot -> loss coefficient -> per-row segment sum -> (Adagrad row write |
+ * emit dE[U,D]); sums [3..4].  dE may be NULL in UPDATE mode. */
+int esr_glove_rows_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                       float* dE, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* Phase 3: bias gradient (-> Adagrad in place | emit db[U]), version flip, loss -> scalars[5]. */
+int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                         float* db, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* All three phases back to back (single GPU). */
+int esr_glove_step_f32(EsrTable* t, const EsrPlan* plan, const float* counts, const EsrGloveCfg* cfg,
+                       float* scalars, float* dE, float* db, void* ws, size_t ws_bytes,
+                       esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer rules (optax semantics).
+ * ------------------------------------------------------------------------------------------ */
+/* Sparse Adagrad on the current rows, in place: rows uniq[0..*n_uniq) get gradient g[u,:].
+ * North-star rule (BASELINE.json); also the owner-side update of the row-sharded path. */
+int esr_sparse_adagrad_f32(EsrTable* t, const int32_t* uniq, const int32_t* n_uniq, int64_t cap,
+                           const float* g, const float* gb, float lr, float eps, esr_stream_t stream);
+/* dst[uniq[u], :] += / = g[u, :]  (dense gradient pytree of jax.value_and_grad, zero elsewhere). */
+int esr_scatter_rows_f32(float* dst, int32_t D, const int32_t* uniq, const int32_t* n_uniq,
+                         int64_t cap, const float* g, int32_t accumulate, esr_stream_t stream);
+/* optax.adam(lr) over n elements -- wikipedia/train_cooccurence.py:171, :101;
+ * pinterest/train_shop_the_look.py:175.  `count` is the step count AFTER this update (>=1). */
+int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, float lr, float b1,
+                       float b2, float eps, int64_t count, esr_stream_t stream);
+/* optax.sgd(lr, momentum) over n elements -- spotify/train_spotify.py:238-241, :110. */
+int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float lr, float momentum,
+                       esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Retrieval: Glove.score_all + find_knn (wikipedia/models.py:40-55,
+ * wikipedia/train_cooccurence.py:91-97,121-125), find_top_k (pinterest/make_recommendations.py:49-65).
+ * top_idx/top_val are [T,k]; best first; ties: larger row id first when tie_high != 0 (the order
+ * dump_knn reads from the tail of a stable ascending argsort), else smaller id first (lax.top_k).
+ * ------------------------------------------------------------------------------------------ */
+size_t esr_score_topk_workspace_bytes(int64_t V, int32_t T, int32_t k);
+int esr_score_topk_f32(const EsrTable* t, const float* queries, int32_t T, int32_t k, int32_t tie_high,
+                       int32_t* top_idx, float* top_val, void* ws, size_t ws_bytes, esr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_H_ */

@@ -1,0 +1,261 @@
+"""GPU parity: the CUDA GloVe path (through the C ABI) vs the NumPy oracle on the same seeded batches.
+
+Integer bookkeeping (sort permutation, unique rows, segment offsets) is bit-exact; floating point is
+compared at 1e-5 (abs + rel, fp32) as BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from esrecsys_b200 import synth
+from oracle import glove as og
+from oracle import index as oidx
+from oracle import optim as oopt
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ATOL = 1e-5
+
+
+def _engine():
+    from esrecsys_b200 import engine
+    return engine
+
+
+def _batch(V, B, seed, uniform=False, n=1):
+    ids, counts = synth.glove_batches(V, B, n, seed, uniform)
+    return ids, counts
+
+
+def _tables(V, D, seed, bias_scale=0.05):
+    E, b = synth.init_glove_tables(V, D, seed)
+    rng = np.random.default_rng(seed + 5)
+    b = (rng.standard_normal(V) * bias_scale).astype(np.float32)   # non-zero biases exercise the broadcast terms
+    return E, b
+
+
+@pytest.mark.parametrize("V,B", [(50, 64), (1000, 2048), (10000, 2048), (200000, 4096)])
+def test_plan_bit_exact(V, B):
+    eng = _engine()
+    ids, _ = _batch(V, B, seed=V + B)
+    keys = torch.from_numpy(ids[0].reshape(-1)).cuda()
+    plan = eng.IndexPlan(2 * B, V).build(keys)
+    sk, perm, uniq, seg_off = plan.host_view()
+    osk, operm = oidx.sort_slots(oidx.slot_keys(ids[0, 0], ids[0, 1]))
+    ouniq, ooff = oidx.segments(osk)
+    assert np.array_equal(sk, osk)
+    assert np.array_equal(perm, operm)
+    assert np.array_equal(uniq, ouniq)
+    assert np.array_equal(seg_off, ooff)
+    assert np.array_equal(plan.useg[:2 * B].cpu().numpy(), oidx.slot_segment_index(osk))
+    i, j = ids[0]
+    pair = operm % B
+    partner = np.where(operm >= B, i[pair], j[pair])
+    assert np.array_equal(plan.partner[:2 * B].cpu().numpy(), partner)
+    # remap: ids rewritten as indices into uniq
+    remap = plan.remap_ids().cpu().numpy()
+    assert np.array_equal(ouniq[remap], oidx.slot_keys(i, j))
+
+
+def test_plan_empty_and_all_same():
+    eng = _engine()
+    plan = eng.IndexPlan(0, 10).build(torch.zeros(0, dtype=torch.int32, device="cuda"))
+    assert int(plan.n_uniq.item()) == 0 and int(plan.seg_off[0].item()) == 0
+    keys = torch.full((64,), 7, dtype=torch.int32, device="cuda")
+    plan = eng.IndexPlan(64, 10).build(keys)
+    sk, perm, uniq, seg_off = plan.host_view()
+    assert uniq.tolist() == [7] and seg_off.tolist() == [0, 64] and perm.tolist() == list(range(64))
+
+
+def test_check_ids():
+    eng = _engine()
+    ids = torch.tensor([0, 5, 9, 10, -1], dtype=torch.int32, device="cuda")
+    assert eng.check_ids(ids, 10) == 2
+    assert eng.check_ids(ids[:3], 10) == 0
+
+
+@pytest.mark.parametrize("D", [4, 32, 64, 100, 128, 256, 512])
+def test_gather_and_export_bit_exact(D):
+    eng = _engine()
+    V = 3000
+    E, b = _tables(V, D, seed=D)
+    t = eng.EmbeddingTable.from_dense(E, b)
+    rng = np.random.default_rng(D)
+    ids = rng.integers(0, V, size=4097).astype(np.int32)
+    out = t.gather(torch.from_numpy(ids)).cpu().numpy()
+    assert np.array_equal(out, E[ids])
+    assert np.array_equal(t.dense().cpu().numpy(), E)
+    assert t.gather(torch.zeros(0, dtype=torch.int32)).shape == (0, D)
+
+
+def _emit(E, b, ids, counts, bias_mode, chunk=0):
+    eng = _engine()
+    V, D = E.shape
+    B = ids.shape[1]
+    t = eng.EmbeddingTable.from_dense(E, b, sparse=False)
+    keys = torch.from_numpy(ids.reshape(-1)).cuda()
+    plan = eng.IndexPlan(2 * B, V).build(keys)
+    step = eng.GloveStep(t, B, bias_mode=bias_mode, emit_grads=True, chunk=chunk)
+    sc = step.run(plan, torch.from_numpy(counts).cuda()).cpu().numpy()
+    U = int(plan.n_uniq.item())
+    return sc, step.dE[:U].cpu().numpy(), step.db[:U].cpu().numpy(), plan
+
+
+@pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
+@pytest.mark.parametrize("V,D,B,chunk", [
+    (10000, 64, 2048, 0),      # BASELINE config 1 shape
+    (10000, 64, 2048, 8),
+    (50, 64, 512, 0),          # duplicate-heavy: every row straddles many chunks
+    (50, 128, 512, 4),
+    (100000, 128, 4096, 16),
+    (2000, 256, 1000, 0),
+    (2000, 100, 777, 12),      # D not a multiple of 32, ragged B
+    (2000, 512, 300, 0),
+    (3, 8, 1, 0),              # single pair
+])
+def test_grads_match_oracle(V, D, B, chunk, bias_mode):
+    E, b = _tables(V, D, seed=V + D)
+    ids, counts = _batch(V, B, seed=B + D)
+    sc, dE, db, plan = _emit(E, b, ids[0], counts[0], bias_mode, chunk)
+    gr = og.loss_and_grads(E, b, ids[0, 0], ids[0, 1], counts[0], bias_mode)
+    assert np.array_equal(plan.uniq[:len(gr.uniq)].cpu().numpy(), gr.uniq)
+    np.testing.assert_allclose(sc[5], gr.loss, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(sc[2], gr.S0, rtol=RTOL)
+    np.testing.assert_allclose(sc[3], gr.S1, rtol=1e-4, atol=1e-3)   # a large cancelling sum
+    np.testing.assert_allclose(dE, gr.dE, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(db, gr.db, rtol=RTOL, atol=ATOL)
+
+
+def test_grads_i_equals_j_and_literal_loss():
+    """i == j cannot occur in real data (make_cooccurrence.py:48) but both terms must then apply;
+    the loss is also checked against the literal (B,B) evaluation of the reference forward."""
+    V, D, B = 40, 64, 96
+    E, b = _tables(V, D, seed=1)
+    ids, counts = _batch(V, B, seed=2)
+    ids = ids[0].copy()
+    ids[1, :10] = ids[0, :10]
+    sc, dE, db, _ = _emit(E, b, ids, counts[0], "reference_broadcast")
+    gr = og.loss_and_grads(E, b, ids[0], ids[1], counts[0])
+    np.testing.assert_allclose(dE, gr.dE, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(db, gr.db, rtol=RTOL, atol=ATOL)
+    lit = og.loss_literal(E.astype(np.float64), b.astype(np.float64), ids[0], ids[1], counts[0].astype(np.float64))
+    np.testing.assert_allclose(sc[5], lit, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
+@pytest.mark.parametrize("V,D,B,uniform", [(10000, 64, 2048, False), (300, 128, 1024, False), (50000, 128, 8192, True)])
+def test_adagrad_steps_match_oracle(V, D, B, uniform, bias_mode):
+    """Several fused sparse-Adagrad steps (north-star rule) vs oracle.glove.step_adagrad."""
+    eng = _engine()
+    n_steps = 5
+    lr = 0.05
+    E, b = _tables(V, D, seed=V)
+    ids, counts = _batch(V, B, seed=V + 1, uniform=uniform, n=n_steps)
+    t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
+    step = eng.GloveStep(t, B, lr=lr, bias_mode=bias_mode)
+    plan = eng.IndexPlan(2 * B, V)
+    Eo, bo = E.copy(), b.copy()
+    accE = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC)
+    accb = np.full_like(bo, oopt.ADAGRAD_INIT_ACC)
+    for k in range(n_steps):
+        keys = torch.from_numpy(ids[k].reshape(-1)).cuda()
+        plan.build(keys)
+        sc = step.run(plan, torch.from_numpy(counts[k]).cuda())
+        loss = float(sc[5].item())
+        oloss = og.step_adagrad(Eo, bo, accE, accb, ids[k, 0], ids[k, 1], counts[k], lr, bias_mode)
+        np.testing.assert_allclose(loss, oloss, rtol=2e-5, atol=ATOL)
+    np.testing.assert_allclose(t.dense().cpu().numpy(), Eo, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(t.bias.cpu().numpy(), bo, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(t.acc.cpu().numpy(), accE, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(t.bias_acc.cpu().numpy(), accb, rtol=RTOL, atol=ATOL)
+    # untouched rows are bit-identical to the initial table
+    touched = np.zeros(V, bool)
+    touched[ids.reshape(-1)] = True
+    assert np.array_equal(t.dense().cpu().numpy()[~touched], E[~touched])
+
+
+def test_step_is_deterministic():
+    """Sorted segment sums + fixed-order partial combine: two runs give identical bits."""
+    eng = _engine()
+    V, D, B = 500, 128, 4096
+    E, b = _tables(V, D, seed=3)
+    ids, counts = _batch(V, B, seed=4)
+    outs = []
+    for _ in range(2):
+        t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
+        plan = eng.IndexPlan(2 * B, V).build(torch.from_numpy(ids[0].reshape(-1)).cuda())
+        eng.GloveStep(t, B).run(plan, torch.from_numpy(counts[0]).cuda())
+        outs.append(t.dense().cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_empty_batch():
+    eng = _engine()
+    E, b = _tables(16, 64, seed=0)
+    t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
+    plan = eng.IndexPlan(0, 16).build(torch.zeros(0, dtype=torch.int32, device="cuda"))
+    sc = eng.GloveStep(t, 0).run(plan, torch.zeros(0, dtype=torch.float32, device="cuda"))
+    assert float(sc[5].item()) == 0.0
+    assert np.array_equal(t.dense().cpu().numpy(), E)
+
+
+def test_optimizer_kernels_match_oracle():
+    eng = _engine()
+    rng = np.random.default_rng(0)
+    n = 100003
+    p = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    mu = np.zeros(n, np.float32)
+    nu = np.zeros(n, np.float32)
+    tp, tmu, tnu = (torch.from_numpy(x.copy()).cuda() for x in (p, mu, nu))
+    count = 0
+    for k in range(3):
+        gk = (g * (k + 1)).astype(np.float32)
+        p, mu, nu, count = oopt.adam_update(p, gk, mu, nu, count, 1e-3)
+        eng.dense_adam(tp, torch.from_numpy(gk).cuda(), tmu, tnu, 1e-3, count)
+    np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(tnu.cpu().numpy(), nu, rtol=RTOL, atol=1e-9)
+    p2 = rng.standard_normal(n).astype(np.float32)
+    tr = np.zeros(n, np.float32)
+    tp2, ttr = torch.from_numpy(p2.copy()).cuda(), torch.from_numpy(tr.copy()).cuda()
+    for k in range(3):
+        p2, tr = oopt.sgdm_update(p2, g, tr, 1e-3, 0.98)
+        eng.dense_sgdm(tp2, torch.from_numpy(g).cuda(), ttr, 1e-3, 0.98)
+    np.testing.assert_allclose(tp2.cpu().numpy(), p2, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(ttr.cpu().numpy(), tr, rtol=RTOL, atol=1e-6)
+
+
+def test_sparse_adagrad_and_scatter_rows():
+    eng = _engine()
+    V, D = 1000, 128
+    E, b = _tables(V, D, seed=9)
+    t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
+    rng = np.random.default_rng(1)
+    uniq = np.sort(rng.choice(V, 300, replace=False)).astype(np.int32)
+    g = rng.standard_normal((300, D)).astype(np.float32)
+    gb = rng.standard_normal(300).astype(np.float32)
+    cap = 512
+    tu = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    tu[:300] = torch.from_numpy(uniq).cuda()
+    tg = torch.zeros(cap, D, device="cuda")
+    tg[:300] = torch.from_numpy(g).cuda()
+    tgb = torch.zeros(cap, device="cuda")
+    tgb[:300] = torch.from_numpy(gb).cuda()
+    nu = torch.tensor([300], dtype=torch.int32, device="cuda")
+    eng.sparse_adagrad(t, tu, nu, tg, tgb, 0.05)
+    Eo, bo = E.copy(), b.copy()
+    acc = np.full_like(Eo, 0.1)
+    accb = np.full_like(bo, 0.1)
+    Eo[uniq], acc[uniq] = oopt.adagrad_update(Eo[uniq], g, acc[uniq], 0.05)
+    bo[uniq], accb[uniq] = oopt.adagrad_update(bo[uniq], gb, accb[uniq], 0.05)
+    np.testing.assert_allclose(t.dense().cpu().numpy(), Eo, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(t.bias.cpu().numpy(), bo, rtol=RTOL, atol=ATOL)
+    dense = torch.zeros(V, D, device="cuda")
+    eng.scatter_rows(dense, tu, nu, tg)
+    ref = np.zeros((V, D), np.float32)
+    ref[uniq] = g
+    assert np.array_equal(dense.cpu().numpy(), ref)
+    eng.scatter_rows(dense, tu, nu, tg, accumulate=True)
+    assert np.array_equal(dense.cpu().numpy(), ref * 2)
