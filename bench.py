@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config[1].
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Workload (N = 1): wikipedia GloVe, 1M-vocab x 128-dim table, synthetic Zipf(1) (i, j, count)
+triples (esrecsys_b200/synth.py), fused gather -> dot -> loss -> sparse Adagrad scatter, one
+"step" = one batch of --batch pairs through the whole hot path (index plan + prep + rows +
+combine + finish).  Prints ONE JSON line (rank 0).
+
+* value      : pairs/s, batches resident in HBM before the timed region.
+* e2e        : pairs/s through GloveTrainer.submit() from PINNED HOST batches (H2D every step)
+               plus a device->host read of the step's loss.
+* roofline   : the row-pass kernel's ALGORITHMIC bytes (U*R*4 + U*16 + B*12)
+               / its CUDA-event duration, on the timed (Zipf) stream; roofline_uniform is the same
+               kernel on the uniform no-reuse control stream, where the >=70 % target is judged.
+* cpu_baseline: oracle/glove_torch.py (a port of the reference's dense-Adam step) on the host.
+* --impl reference: only that CPU leg, as its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairs/sec"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=262144)
+    ap.add_argument("--nbatch", type=int, default=8, help="distinct pre-generated batches cycled through")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--lr", type=float, default=0.05)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-uniform", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "wikipedia GloVe: %dk-vocab x %d-dim, synthetic Zipf triples, B=%d, fused gather->dot->scatter (BASELINE configs[1])" % (
+        a.vocab // 1000, a.dim, a.batch)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the reference's own step (dense gradient + dense Adam), ported in oracle/glove_torch.py
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(a, steps, warmup):
+    import torch
+    from esrecsys_b200 import synth
+    from oracle import glove_torch as ogt
+    torch.manual_seed(a.seed)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    V, D, B = a.vocab, a.dim, a.batch
+    n = max(1, min(a.nbatch, steps + warmup))
+    ids, counts = synth.glove_batches(V, B, n, a.seed)
+    E = torch.randn(V, D) / np.sqrt(D)
+    b = torch.zeros(V)
+    st = dict(count=0, muE=torch.zeros_like(E), nuE=torch.zeros_like(E), mub=torch.zeros_like(b), nub=torch.zeros_like(b))
+    ti = [torch.from_numpy(ids[k, 0].astype(np.int64)) for k in range(n)]
+    tj = [torch.from_numpy(ids[k, 1].astype(np.int64)) for k in range(n)]
+    tx = [torch.from_numpy(counts[k]) for k in range(n)]
+    for k in range(warmup):
+        ogt.step_adam_dense(E, b, st, ti[k % n], tj[k % n], tx[k % n], 1e-3)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ogt.step_adam_dense(E, b, st, ti[k % n], tj[k % n], tx[k % n], 1e-3)
+    dt = time.perf_counter() - t0
+    return dict(value=B * steps / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d steps of B=%d on the %dx%d table: oracle/glove_torch.step_adam_dense (dense grad + optax.adam "
+                       "over all rows, as wikipedia/train_cooccurence.py:71-101), torch CPU ops, %d threads"
+                       % (steps, B, V, D, cores)), dt / steps * 1e3
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 5))
+    warm = max(0, min(a.warmup, 1))
+    cb, ms = cpu_reference(a, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "batch": a.batch,
+                                                         "note": "reference is CPU-only (jax/flax absent): oracle port, "
+                                                                 "steps clamped to <=5 so the run stays bounded"},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled with NVML during the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # pragma: no cover
+            self.nv = None
+        self.active = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop:
+            if self.active:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                        nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # pragma: no cover
+                    pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self.th.start()
+
+    def summary(self):
+        self.stop = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------
+def alg_bytes(ids_np, D, B):
+    """bytes_step = U*R*(2+2S) + U_b*4*(2+2S) + B*12 with S = 1 (Adagrad)."""
+    U = float(np.mean([np.unique(ids_np[k]).size for k in range(ids_np.shape[0])]))
+    R = D * 4
+    return U * R * 4 + U * 16 + B * 12, U
+
+
+def timed_region(tr, batches, steps, warmup, read_loss, world):
+    import torch
+    import torch.distributed as dist
+    n = len(batches)
+    for k in range(warmup):
+        tr.submit(*batches[k % n])
+    tr.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tr.s_side.wait_stream(tr.s_main)
+    e0.record(tr.s_main)
+    tr.s_side.wait_event(e0)
+    for k in range(steps):
+        s = tr.submit(*batches[(warmup + k) % n])
+        if read_loss:
+            tr.read_loss(s)
+    e1.record(tr.s_main)
+    tr.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def rows_kernel_time(table, a, ids_dev, cnt_dev, steps):
+    """Average CUDA-event duration of the row-pass kernel alone (eager launches, same batches)."""
+    import torch
+    from esrecsys_b200 import engine
+    step = engine.GloveStep(table, a.batch, lr=a.lr, impl=a.kernel)
+    plan = engine.IndexPlan(2 * a.batch, a.vocab)
+    n = len(ids_dev)
+    tot = 0.0
+    for k in range(steps + 3):
+        plan.build(ids_dev[k % n])
+        step.prep(plan, cnt_dev[k % n])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.rows_main(plan)
+        e1.record()
+        step.rows_combine(plan)
+        step.finish(plan)
+        torch.cuda.synchronize()
+        if k >= 3:
+            tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from esrecsys_b200 import _lib, engine, synth
+    from esrecsys_b200.trainer import GloveTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()
+    _lib.lib()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    V, D, B = a.vocab, a.dim, a.batch
+    torch.manual_seed(a.seed + rank)
+    table = engine.EmbeddingTable(V, D)
+    table.rows0.normal_(0.0, 1.0 / np.sqrt(D))        # flax nn.Embed default init (wikipedia/models.py:16-17)
+    ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
+    ids_dev = [torch.from_numpy(ids[k].reshape(-1)).cuda() for k in range(a.nbatch)]
+    cnt_dev = [torch.from_numpy(counts[k]).cuda() for k in range(a.nbatch)]
+    ids_pin = [torch.from_numpy(ids[k]).pin_memory() for k in range(a.nbatch)]
+    cnt_pin = [torch.from_numpy(counts[k]).pin_memory() for k in range(a.nbatch)]
+    tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    clocks.active = True
+    # --- value: device-resident batches ---
+    ms = timed_region(tr, list(zip(ids_dev, cnt_dev)), a.steps, a.warmup, False, world)
+    # --- e2e: pinned host batches, H2D + loss D2H every step ---
+    ms_e2e = timed_region(tr, list(zip(ids_pin, cnt_pin)), a.steps, max(3, a.warmup // 4), True, world)
+    loss = float(tr.losses(tr.t - 1, tr.t)[0])
+    clocks.active = False
+    value = world * B * a.steps / (ms * 1e-3)
+    e2e = world * B * a.steps / (ms_e2e * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "vocab": V, "dim": D, "batch": B, "optimizer": "sparse adagrad (north star)",
+                   "bias_mode": "reference_broadcast", "kernel": a.kernel, "stream": "zipf(1)",
+                   "l2": "no flush: table + state = %.2f GB per GPU >> 126 MB L2, fresh random rows every step" % (table.nbytes() / 1e9),
+                   "parallelism": "replicas" if world > 1 else "single"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": a.steps * tr.launches_per_step,
+        "final_loss": loss,
+    }
+    if rank == 0:
+        # --- roofline of the dominant kernel, Zipf (timed stream) and uniform control ---
+        clocks.active = True
+        ksteps = max(5, min(a.steps, 50))
+        t_rows = rows_kernel_time(table, a, ids_dev, cnt_dev, ksteps)
+        ab, U = alg_bytes(ids, D, B)
+        ach = ab / (t_rows * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                            "traffic": None, "kernel": "k_glove_rows", "kernel_ms": t_rows, "alg_bytes_per_launch": ab,
+                            "unique_rows_per_step": U, "peak_source": peak_src, "stream": "zipf(1)"}
+        if not a.no_uniform:
+            uids, ucnt = synth.glove_batches(V, B, 4, a.seed + 99, uniform=True)
+            u_dev = [torch.from_numpy(uids[k].reshape(-1)).cuda() for k in range(4)]
+            uc_dev = [torch.from_numpy(ucnt[k]).cuda() for k in range(4)]
+            t_u = rows_kernel_time(table, a, u_dev, uc_dev, ksteps)
+            abu, Uu = alg_bytes(uids, D, B)
+            achu = abu / (t_u * 1e-3) / 1e9
+            line["roofline_uniform"] = {"bound": "hbm", "achieved": achu, "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": achu / hbm_peak, "traffic": None, "kernel": "k_glove_rows", "kernel_ms": t_u,
+                                        "alg_bytes_per_launch": abu, "unique_rows_per_step": Uu, "stream": "uniform"}
+        clocks.active = False
+    line["clocks"] = clocks.summary()
+    if rank == 0:
+        if world == 1 and not a.no_cpu:
+            del tr, table
+            torch.cuda.empty_cache()
+            cb, _ = cpu_reference(a, a.cpu_steps, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,13 +65,17 @@ _SIGNATURES = {
                                      C.c_size_t, _P]),
     "esr_glove_rows_f32": (C.c_int, [C.POINTER(EsrTable), C.POINTER(EsrPlan), C.POINTER(EsrGloveCfg), _P, _P, _P,
                                      C.c_size_t, _P]),
+    "esr_glove_rows_main_f32": (C.c_int, [C.POINTER(EsrTable), C.POINTER(EsrPlan), C.POINTER(EsrGloveCfg), _P, _P, _P,
+                                          C.c_size_t, _P]),
+    "esr_glove_rows_combine_f32": (C.c_int, [C.POINTER(EsrTable), C.POINTER(EsrPlan), C.POINTER(EsrGloveCfg), _P, _P, _P,
+                                             C.c_size_t, _P]),
     "esr_glove_finish_f32": (C.c_int, [C.POINTER(EsrTable), C.POINTER(EsrPlan), C.POINTER(EsrGloveCfg), _P, _P, _P,
                                        C.c_size_t, _P]),
     "esr_glove_step_f32": (C.c_int, [C.POINTER(EsrTable), C.POINTER(EsrPlan), _P, C.POINTER(EsrGloveCfg), _P, _P, _P,
                                      _P, C.c_size_t, _P]),
     "esr_sparse_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int64, _P, _P, C.c_float, C.c_float, _P]),
     "esr_scatter_rows_f32": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64, _P, C.c_int32, _P]),
-    "esr_dense_adam_f32": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+    "esr_dense_adam_f32": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_int64, _P]),
     "esr_dense_sgdm_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, _P]),
 }

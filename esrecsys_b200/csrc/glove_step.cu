@@ -20,6 +20,8 @@
 //   lane in flight) to cover HBM latency.
 //   Segments that straddle a chunk boundary (Zipf head rows) leave per-chunk partial sums that
 //   k_glove_combine adds in a fixed order, so the result is bit-reproducible run to run.
+#include <algorithm>
+
 #include "esr_common.cuh"
 
 namespace esr {
@@ -27,7 +29,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCombineThreads = 128;
+constexpr int kCombineThreads = 512;
 constexpr int kCombineWarps = kCombineThreads / 32;
 constexpr int32_t kRowMask = 0x3fffffff;
 constexpr int32_t kRoleBit = 0x40000000;  // slot is the i role: its pair counts towards the batch sums
@@ -48,6 +50,9 @@ struct GloveWs {
   float* parts;     // [nchunks][2]    partial scalar sums
   float* prep_blk;  // [prep_blocks][3]
   float* rows_blk;  // [row_blocks][2]
+  int32_t* wl_count;  // [2]
+  int32_t* wl_light;  // [nchunks]
+  int32_t* wl_heavy;  // [nchunks]
   int64_t nchunks;
   int32_t prep_blocks;
   int32_t row_blocks;
@@ -76,6 +81,9 @@ size_t carve_ws(void* base, int64_t B, int32_t D, int32_t chunk_in, GloveWs* w) 
   t.parts = c.take<float>(t.nchunks * 2);
   t.prep_blk = c.take<float>((size_t)t.prep_blocks * 3);
   t.rows_blk = c.take<float>((size_t)t.row_blocks * 2);
+  t.wl_count = c.take<int32_t>(2);
+  t.wl_light = c.take<int32_t>(t.nchunks);
+  t.wl_heavy = c.take<int32_t>(t.nchunks);
   if (w) *w = t;
   return c.off;
 }
@@ -187,6 +195,12 @@ __device__ __forceinline__ void row_store(const Row<NK>& r, float4* __restrict__
   }
 }
 
+template <int NK>
+__device__ __forceinline__ void row_add(Row<NK>& acc, const Row<NK>& x) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) f4_add(acc.v[k], x.v[k]);
+}
+
 struct RowsArgs {
   const float* rows[2];
   float* wrows[2];
@@ -194,13 +208,18 @@ struct RowsArgs {
   const int32_t* skv;
   const SlotRec* rec;
   const int32_t* useg;
+  const int32_t* seg_off;
   const float* scalars;  // [0..2] already global
   float* bsum;
   float* part;
   float* parts;
   float* rows_blk;
+  int32_t* wl_count;  // [0] light, [1] heavy work-list lengths
+  int32_t* wl_light;  // head chunks of straddling segments with <= kHeavyParts partials
+  int32_t* wl_heavy;
   float* dE;
   int64_t n;
+  int64_t nchunks;
   int32_t D4;
   int32_t chunk;
   int32_t per_pair;
@@ -209,6 +228,8 @@ struct RowsArgs {
   float inv_B;    // 1 / B_global
   float lr, eps;
 };
+
+constexpr int kHeavyParts = 64;
 
 // Close a finished segment: Adagrad row write (UPDATE) or gradient emit (EMIT).
 template <int NK>
@@ -228,118 +249,99 @@ __device__ __forceinline__ void close_segment(const RowsArgs& a, int32_t key, in
   if (lane == 0) a.bsum[u] = bacc;
 }
 
-template <int NK, int S>
-__global__ void __launch_bounds__(kThreads) k_glove_rows(const RowsArgs a) {
-  __shared__ float red[32 * 2];
-  const int lane = threadIdx.x & 31;
-  const int64_t c = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+// Per-chunk bookkeeping shared by both kernel variants.
+struct ChunkMeta {
+  int cnt;
+  int32_t kl;          // lane's own skv (kNoKey beyond cnt)
+  unsigned head_mask;  // slot is the first of its segment (true head)
+  unsigned end_mask;   // slot is the last of its segment
+  SlotRec r;           // lane's own record
+  int64_t u_first;     // unique-row index of slot 0
+};
+
+__device__ __forceinline__ ChunkMeta load_chunk(const RowsArgs& a, int64_t c, int lane) {
+  ChunkMeta m;
   const int64_t p0 = c * a.chunk;
-  float sums[2] = {0.f, 0.f};  // S1, S2 contributions (lane-uniform)
+  m.cnt = (int)min((int64_t)a.chunk, a.n - p0);
+  m.kl = lane < m.cnt ? a.skv[p0 + lane] : kNoKey;
+  const int32_t kprev0 = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
+  const int32_t knextN = p0 + m.cnt < a.n ? a.skv[p0 + m.cnt] : kNoKey;
+  int32_t kp = __shfl_up_sync(FULL, m.kl, 1);
+  if (lane == 0) kp = kprev0;
+  int32_t kn = __shfl_down_sync(FULL, m.kl, 1);
+  if (lane == m.cnt - 1) kn = knextN;
+  m.head_mask = __ballot_sync(FULL, lane < m.cnt && m.kl != kp);
+  m.end_mask = __ballot_sync(FULL, lane < m.cnt && m.kl != kn);
+  m.r.code = 0; m.r.w = 0.f; m.r.t = 0.f; m.r.bs = 0.f;
+  if (lane < m.cnt) m.r = a.rec[p0 + lane];
+  m.u_first = a.useg[p0];
+  return m;
+}
 
-  if (p0 < a.n) {
-    const int cnt = (int)min((int64_t)a.chunk, a.n - p0);
-    // keys of the chunk (+ one on each side) -> head / end masks
-    const int32_t kl = lane < cnt ? a.skv[p0 + lane] : kNoKey;
-    const int32_t kprev0 = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-    const int32_t knextN = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
-    int32_t kp = __shfl_up_sync(FULL, kl, 1);
-    if (lane == 0) kp = kprev0;
-    int32_t kn = __shfl_down_sync(FULL, kl, 1);
-    if (lane == cnt - 1) kn = knextN;
-    const unsigned head_mask = __ballot_sync(FULL, lane < cnt && kl != kp);
-    const unsigned end_mask = __ballot_sync(FULL, lane < cnt && kl != kn);
-    SlotRec r;
-    r.code = 0; r.w = 0.f; r.t = 0.f; r.bs = 0.f;
-    if (lane < cnt) r = a.rec[p0 + lane];
-    const int64_t u_first = a.useg[p0];
-    const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+template <int NK>
+struct SegState {
+  Row<NK> cur, grad;
+  float bacc;
+  bool started_here;
+  int32_t cur_key;
+};
 
-    Row<NK> cur, grad;
-    row_zero(cur);
-    row_zero(grad);
-    float bacc = 0.f;
-    bool started_here = false;
-    int32_t cur_key = kNoKey;
-
-    for (int sb = 0; sb < cnt; sb += S) {
-      Row<NK> P[S], Sf[S], A[S];
-      int32_t code[S], key[S];
-      float w[S], t[S], bs[S];
-      // ---- issue every load of the sub-batch before the first use ----
+// One slot: dot with the segment's self row, loss coefficient, gradient accumulate, and -- at
+// the end of a segment or of the chunk -- the row update or the partial-sum hand-off.
+template <int NK>
+__device__ __forceinline__ void consume_slot(const RowsArgs& a, const ChunkMeta& m, int64_t c, int s, SegState<NK>& st,
+                                             const Row<NK>& P, const Row<NK>& Sf, const Row<NK>& A, int32_t code,
+                                             int32_t key, float w, float t, float bs, float mbs, float (&sums)[2],
+                                             int lane) {
+  const bool is_head = (m.head_mask >> s) & 1u;
+  if (s == 0 || is_head) {
+    st.cur = Sf;
+    st.cur_key = key;
+    row_zero(st.grad);
+    st.bacc = 0.f;
+    st.started_here = is_head;
+  }
+  float d = 0.f;
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        const int s = sb + j;
-        const int src = s < 32 ? s : 31;
-        code[j] = __shfl_sync(FULL, r.code, src);
-        w[j] = __shfl_sync(FULL, r.w, src);
-        t[j] = __shfl_sync(FULL, r.t, src);
-        bs[j] = __shfl_sync(FULL, r.bs, src);
-        key[j] = __shfl_sync(FULL, kl, src);
-        if (s < cnt) {
-          const int64_t q = code[j] & kRowMask;
-          const int qv = (code[j] >> 31) & 1;
-          row_load<NK, false>(P[j], reinterpret_cast<const float4*>(a.rows[qv]) + q * a.D4, lane, a.D4);
-          const bool need_self = (s == 0) || ((head_mask >> s) & 1u);
-          if (need_self) {
-            const int64_t row = key[j] & kRowMask;
-            const int v = (key[j] >> 31) & 1;
-            row_load<NK, false>(Sf[j], reinterpret_cast<const float4*>(a.rows[v]) + row * a.D4, lane, a.D4);
-          }
-          if (!a.emit && ((end_mask >> s) & 1u)) {
-            // the accumulator is only used if the segment also started in this chunk; a segment
-            // that closes here but started earlier is rare (one per straddling row), so the
-            // unconditional prefetch costs nothing measurable
-            const int64_t row = key[j] & kRowMask;
-            row_load<NK, true>(A[j], reinterpret_cast<const float4*>(a.acc) + row * a.D4, lane, a.D4);
-          }
-        }
-      }
-      // ---- consume in slot order ----
+  for (int k = 0; k < NK; ++k) d += f4_dot(st.cur.v[k], P.v[k]);
+  const float dot = warp_sum(d);
+  const float res = t - dot;
+  const float rr = a.per_pair ? res - bs : res;
+  const float g = a.c2B * w * (a.per_pair ? rr : res - mbs);
+  if (code & kRoleBit) {
+    sums[0] = fmaf(w, res, sums[0]);
+    sums[1] = fmaf(w * rr, rr, sums[1]);
+  }
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        const int s = sb + j;
-        if (s < cnt) {
-          const bool is_head = (head_mask >> s) & 1u;
-          if (s == 0 || is_head) {
-            cur = Sf[j];
-            cur_key = key[j];
-            row_zero(grad);
-            bacc = 0.f;
-            started_here = is_head;
-          }
-          float d = 0.f;
-#pragma unroll
-          for (int k = 0; k < NK; ++k) d += f4_dot(cur.v[k], P[j].v[k]);
-          const float dot = warp_sum(d);
-          const float res = t[j] - dot;
-          const float rr = a.per_pair ? res - bs[j] : res;
-          const float g = a.c2B * w[j] * (a.per_pair ? rr : res - mbs);
-          if (code[j] & kRoleBit) {
-            sums[0] = fmaf(w[j], res, sums[0]);
-            sums[1] = fmaf(w[j] * rr, rr, sums[1]);
-          }
-#pragma unroll
-          for (int k = 0; k < NK; ++k) f4_fma(grad.v[k], g, P[j].v[k]);
-          bacc += a.per_pair ? g : bs[j];
-          const bool is_end = (end_mask >> s) & 1u;
-          if (is_end) {
-            if (started_here) {
-              const int64_t u = u_first + __popc(head_mask & ((2u << s) - 1u) & ~1u);
-              close_segment<NK>(a, cur_key, u, cur, A[j], grad, bacc, lane);
-            } else {  // leading partial: the segment started in an earlier chunk
-              row_store<NK, false>(grad, reinterpret_cast<float4*>(a.part) + (c * 2 + 0) * a.D4, lane, a.D4);
-              if (lane == 0) a.parts[c * 2 + 0] = bacc;
-            }
-          } else if (s == cnt - 1) {  // the chunk ends inside a segment
-            const int slot = started_here ? 1 : 0;
-            row_store<NK, false>(grad, reinterpret_cast<float4*>(a.part) + (c * 2 + slot) * a.D4, lane, a.D4);
-            if (lane == 0) a.parts[c * 2 + slot] = bacc;
-          }
-        }
+  for (int k = 0; k < NK; ++k) f4_fma(st.grad.v[k], g, P.v[k]);
+  st.bacc += a.per_pair ? g : bs;
+  const bool is_end = (m.end_mask >> s) & 1u;
+  if (is_end) {
+    if (st.started_here) {
+      const int64_t u = m.u_first + __popc(m.head_mask & ((2u << s) - 1u) & ~1u);
+      close_segment<NK>(a, st.cur_key, u, st.cur, A, st.grad, st.bacc, lane);
+    } else {  // leading partial: the segment started in an earlier chunk
+      row_store<NK, false>(st.grad, reinterpret_cast<float4*>(a.part) + (c * 2 + 0) * a.D4, lane, a.D4);
+      if (lane == 0) a.parts[c * 2 + 0] = st.bacc;
+    }
+  } else if (s == m.cnt - 1) {  // the chunk ends inside a segment
+    const int slot = st.started_here ? 1 : 0;
+    row_store<NK, false>(st.grad, reinterpret_cast<float4*>(a.part) + (c * 2 + slot) * a.D4, lane, a.D4);
+    if (lane == 0) {
+      a.parts[c * 2 + slot] = st.bacc;
+      if (slot == 1) {  // this chunk holds the head of a straddling segment: queue its combine
+        const int64_t u = m.u_first + __popc(m.head_mask & ~1u);
+        const int64_t np = (a.seg_off[u + 1] - 1) / a.chunk - c + 1;
+        const int heavy = np > kHeavyParts;
+        const int e = atomicAdd(a.wl_count + heavy, 1);
+        (heavy ? a.wl_heavy : a.wl_light)[e] = (int32_t)c;
       }
     }
   }
-  // per-block S1 / S2 partials (lane 0 of each warp carries the warp's value)
+}
+
+__device__ __forceinline__ void store_block_sums(const RowsArgs& a, float (&sums)[2], float* red, int lane) {
+  // per-block S1 / S2 partials (lane 0 of each warp carries the warp's lane-uniform value)
   float v[2] = {lane == 0 ? sums[0] : 0.f, lane == 0 ? sums[1] : 0.f};
   block_sum<2>(v, red);
   if (threadIdx.x == 0) {
@@ -348,67 +350,441 @@ __global__ void __launch_bounds__(kThreads) k_glove_rows(const RowsArgs a) {
   }
 }
 
-// One block per chunk; the block whose chunk holds the HEAD of a straddling segment adds the
-// segment's partials in chunk order (fixed tree => deterministic) and closes the segment.
-// The extra last block reduces the S1/S2 block partials into scalars[3..4].
+// LDG variant: one chunk per warp, S slots' rows held in registers between issue and use.
+template <int NK, int S, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_glove_rows(const RowsArgs a) {
+  __shared__ float red[32 * 2];
+  const int lane = threadIdx.x & 31;
+  const int64_t c = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  float sums[2] = {0.f, 0.f};  // S1, S2 contributions (lane-uniform)
+
+  if (c < a.nchunks) {
+    const ChunkMeta m = load_chunk(a, c, lane);
+    const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+    SegState<NK> st;
+    row_zero(st.cur);
+    row_zero(st.grad);
+    st.bacc = 0.f;
+    st.started_here = false;
+    st.cur_key = kNoKey;
+
+    for (int sb = 0; sb < m.cnt; sb += S) {
+      Row<NK> P[S], Sf[S], A[S];
+      int32_t code[S], key[S];
+      float w[S], t[S], bs[S];
+      // ---- issue every load of the sub-batch before the first use ----
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const int s = sb + j;
+        const int src = s < 32 ? s : 31;
+        code[j] = __shfl_sync(FULL, m.r.code, src);
+        w[j] = __shfl_sync(FULL, m.r.w, src);
+        t[j] = __shfl_sync(FULL, m.r.t, src);
+        bs[j] = __shfl_sync(FULL, m.r.bs, src);
+        key[j] = __shfl_sync(FULL, m.kl, src);
+        if (s < m.cnt) {
+          const int64_t q = code[j] & kRowMask;
+          const int qv = (code[j] >> 31) & 1;
+          row_load<NK, false>(P[j], reinterpret_cast<const float4*>(a.rows[qv]) + q * a.D4, lane, a.D4);
+          const int64_t row = key[j] & kRowMask;
+          if ((s == 0) || ((m.head_mask >> s) & 1u)) {
+            const int v = (key[j] >> 31) & 1;
+            row_load<NK, false>(Sf[j], reinterpret_cast<const float4*>(a.rows[v]) + row * a.D4, lane, a.D4);
+          }
+          // The accumulator is only used when the segment also started in this chunk; a segment that
+          // closes here but started earlier is rare (one per straddling row).
+          if (!a.emit && ((m.end_mask >> s) & 1u))
+            row_load<NK, true>(A[j], reinterpret_cast<const float4*>(a.acc) + row * a.D4, lane, a.D4);
+        }
+      }
+      // ---- consume in slot order ----
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const int s = sb + j;
+        if (s < m.cnt)
+          consume_slot<NK>(a, m, c, s, st, P[j], Sf[j], A[j], code[j], key[j], w[j], t[j], bs[j], mbs, sums, lane);
+      }
+    }
+  }
+  store_block_sums(a, sums, red, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2, group variant (default): a row is owned by a GROUP of G lanes (NV float4 per lane,
+// D <= 16*G*NV... i.e. D4 <= G*NV), and the 32/G groups of a warp walk 32/G consecutive chunks in
+// lock step, so every warp instruction advances 32/G slots.  The LDG-per-warp variant above spends
+// ~230 warp instructions per slot and is issue-bound (ncu: 58-78 % issue-active at 4.7-5.1 TB/s);
+// here the per-slot bookkeeping (keys, record, addresses, flags) is shared by 32/G slots.
+// Lane gl of a group owns float4 columns gl, gl+G, gl+2G, ... so each load instruction of a group
+// covers G*16 contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+template <int G, int NV>
+__device__ __forceinline__ void grow_load(Row<NV>& r, const float4* __restrict__ p, int gl, int D4, bool stream) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    if (c < D4) r.v[k] = stream ? ld_stream(p + c) : ld_keep(p + c);
+    else r.v[k] = f4_zero();
+  }
+}
+template <int G, int NV>
+__device__ __forceinline__ void grow_store(const Row<NV>& r, float4* __restrict__ p, int gl, int D4, bool stream) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    if (c < D4) {
+      if (stream) st_stream(p + c, r.v[k]);
+      else p[c] = r.v[k];
+    }
+  }
+}
+
+template <int G, int NV, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArgs a) {
+  __shared__ float red[32 * 2];
+  constexpr int GP = 32 / G;  // chunks per warp
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, grp = lane / G;
+  const int64_t c = (blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * GP + grp;
+  const uint32_t D4 = (uint32_t)a.D4;
+  const int64_t p0 = c * a.chunk;
+  const int cnt = c < a.nchunks ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+  const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+  const float4* const rows0 = reinterpret_cast<const float4*>(a.rows[0]);
+  const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
+  const float4* const accp = reinterpret_cast<const float4*>(a.acc);
+  float sums[2] = {0.f, 0.f};  // group-uniform
+
+  Row<NV> cur, grad;
+  row_zero(cur);
+  row_zero(grad);
+  float bacc = 0.f;
+  bool started_here = false;
+  int64_t u = 0;
+  // metadata runs one slot ahead of the row loads
+  int32_t key_prev = kNoKey, key_cur = kNoKey, key_next = kNoKey;
+  SlotRec rec;
+  rec.code = 0; rec.w = 0.f; rec.t = 0.f; rec.bs = 0.f;
+  if (cnt > 0) {
+    key_prev = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
+    key_cur = a.skv[p0];
+    rec = a.rec[p0];
+    u = a.useg[p0];
+  }
+  for (int s = 0; s < a.chunk; ++s) {
+    const bool active = s < cnt;
+    SlotRec rec_next = rec;
+    Row<NV> P, A;
+    row_zero(P);
+    bool is_head = false, is_end = false;
+    if (active) {
+      key_next = p0 + s + 1 < a.n ? a.skv[p0 + s + 1] : kNoKey;
+      if (s + 1 < cnt) rec_next = a.rec[p0 + s + 1];
+      is_head = key_cur != key_prev;
+      is_end = key_cur != key_next;
+      const uint32_t q = (uint32_t)(rec.code & kRowMask);
+      grow_load<G, NV>(P, ((rec.code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl, a.D4, false);
+      const uint32_t row = (uint32_t)(key_cur & kRowMask);
+      if (s == 0 || is_head) {
+        grow_load<G, NV>(cur, ((key_cur >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, false);
+        row_zero(grad);
+        bacc = 0.f;
+        started_here = is_head;
+        if (is_head && s > 0) ++u;
+      }
+      if (!a.emit && is_end && started_here) grow_load<G, NV>(A, accp + (uint64_t)row * D4, gl, a.D4, true);
+    }
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d += f4_dot(cur.v[k], P.v[k]);
+    const float dot = group_sum<G>(d);
+    if (active) {
+      const float res = rec.t - dot;
+      const float rr = a.per_pair ? res - rec.bs : res;
+      const float g = a.c2B * rec.w * (a.per_pair ? rr : res - mbs);
+      if (rec.code & kRoleBit) {
+        sums[0] = fmaf(rec.w, res, sums[0]);
+        sums[1] = fmaf(rec.w * rr, rr, sums[1]);
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) f4_fma(grad.v[k], g, P.v[k]);
+      bacc += a.per_pair ? g : rec.bs;
+      if (is_end && started_here) {
+        if (a.emit) {
+          grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.dE) + (uint64_t)u * D4, gl, a.D4, true);
+        } else {
+          const uint32_t row = (uint32_t)(key_cur & kRowMask);
+          const int v = (key_cur >> 31) & 1;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+          grow_store<G, NV>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
+          grow_store<G, NV>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
+        }
+        if (gl == 0) a.bsum[u] = bacc;
+      } else if (is_end || s == cnt - 1) {
+        // leading partial (segment started in an earlier chunk) or the chunk ends inside a segment
+        const int slot = (!is_end && started_here) ? 1 : 0;
+        grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.part) + (uint64_t)(c * 2 + slot) * D4, gl, a.D4, false);
+        if (gl == 0) {
+          a.parts[c * 2 + slot] = bacc;
+          if (slot == 1) {  // this chunk holds the head of a straddling segment: queue its combine
+            const int64_t np = (a.seg_off[u + 1] - 1) / a.chunk - c + 1;
+            const int heavy = np > kHeavyParts;
+            const int e = atomicAdd(a.wl_count + heavy, 1);
+            (heavy ? a.wl_heavy : a.wl_light)[e] = (int32_t)c;
+          }
+        }
+      }
+    }
+    key_prev = key_cur;
+    key_cur = key_next;
+    rec = rec_next;
+  }
+  // per-block S1 / S2 partials: lane 0 of every group carries its group's value
+  float v[2] = {gl == 0 ? sums[0] : 0.f, gl == 0 ? sums[1] : 0.f};
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) {
+    a.rows_blk[blockIdx.x * 2 + 0] = v[0];
+    a.rows_blk[blockIdx.x * 2 + 1] = v[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2, TMA variant: rows are staged into shared memory by the bulk-copy engine
+// (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP).  Every warp owns a
+// private ring of NS stages; a stage holds the three rows one slot can need (partner, self,
+// accumulator).  The in-flight data lives in shared memory instead of registers, so a warp keeps
+// NS slots (up to 3*NS rows) outstanding while it consumes, and the low register count lets
+// 32 warps per SM stay resident.  The kernel is persistent: warps stride over the chunks.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
 template <int NK>
-__global__ void __launch_bounds__(kCombineThreads) k_glove_combine(const RowsArgs a, const int32_t* __restrict__ seg_off,
-                                                                   int64_t nchunks, int row_blocks,
-                                                                   float* __restrict__ scalars) {
-  if (blockIdx.x == nchunks) {
-    reduce_partials<2>(a.rows_blk, row_blocks, scalars + ESR_SC_S1);
-    return;
+__device__ __forceinline__ void row_from_smem(Row<NK>& r, const float4* sp, int lane, int D4) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int c = k * 32 + lane;
+    r.v[k] = c < D4 ? sp[c] : f4_zero();
   }
-  const int64_t c = blockIdx.x;
-  const int64_t pl = min((c + 1) * (int64_t)a.chunk, a.n) - 1;
-  if (pl >= a.n - 1) return;
-  const int32_t key = a.skv[pl];
-  if (key != a.skv[pl + 1]) return;
-  const int64_t u = a.useg[pl];
-  const int64_t s0 = seg_off[u];
-  if (s0 < c * (int64_t)a.chunk) return;  // an earlier chunk holds the head
-  const int64_t s1 = seg_off[u + 1];
-  const int64_t c1 = (s1 - 1) / a.chunk;
-  // partial list: index 0 = part[c][1]; index m >= 1 = part[c+m][0]; total np = c1 - c + 1
-  const int64_t np = c1 - c + 1;
+}
+
+constexpr int kTmaStages = 4;
+constexpr int tma_min_blocks(int nk) { return nk == 1 ? 4 : (nk == 2 ? 2 : 1); }
+
+template <int NK>
+__global__ void __launch_bounds__(kThreads, tma_min_blocks(NK)) k_glove_rows_tma(const RowsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[kWarps][kTmaStages];
+  __shared__ float red[32 * 2];
+  constexpr int NS = kTmaStages;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t per = ceil_div(np, (int64_t)kCombineWarps);
-  const int64_t m0 = wid * per, m1 = min(np, m0 + per);
-  Row<NK> sum;
-  row_zero(sum);
-  float ssum = 0.f;
-  for (int64_t m = m0; m < m1; ++m) {
-    const int64_t idx = m == 0 ? c * 2 + 1 : (c + m) * 2;
-    Row<NK> x;
-    row_load<NK, true>(x, reinterpret_cast<const float4*>(a.part) + idx * a.D4, lane, a.D4);
+  const uint32_t RB = (uint32_t)a.D4 * 16u;  // row bytes
+  const uint32_t stage_bytes = 3u * RB;
+  unsigned char* my = smem_raw + (size_t)wid * NS * stage_bytes;
+  const uint32_t my_u32 = smem_u32(my);
+  const uint32_t bar0 = smem_u32(&bars[wid][0]);
+  if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NK; ++k) f4_add(sum.v[k], x.v[k]);
-    ssum += a.parts[idx];
+    for (int i = 0; i < NS; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __shared__ float4 sh[kCombineWarps][NK * 32];
-  __shared__ float shs[kCombineWarps];
+  __syncwarp();
+  uint64_t pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  uint32_t phase = 0;  // bit i = parity the next wait on stage i expects
+  float sums[2] = {0.f, 0.f};
+  const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+
+  for (int64_t c = blockIdx.x * (int64_t)kWarps + wid; c < a.nchunks; c += stride) {
+    const ChunkMeta m = load_chunk(a, c, lane);
+    // lane s issues the copies of slot s (it holds the slot's key and record)
+    auto issue = [&](int s) {
+      if (lane == s) {
+        const int stg = s % NS;
+        const uint32_t bar = bar0 + 8u * stg;
+        const uint32_t dst = my_u32 + (uint32_t)stg * stage_bytes;
+        const bool need_self = (s == 0) || ((m.head_mask >> s) & 1u);
+        const bool need_acc = !a.emit && ((m.end_mask >> s) & 1u);
+        mbar_expect_tx(bar, RB * (1u + (need_self ? 1u : 0u) + (need_acc ? 1u : 0u)));
+        const int64_t q = m.r.code & kRowMask;
+        const int qv = (m.r.code >> 31) & 1;
+        bulk_g2s(dst, a.rows[qv] + q * (int64_t)a.D4 * 4, RB, bar);
+        const int64_t row = m.kl & kRowMask;
+        if (need_self) bulk_g2s(dst + RB, a.rows[(m.kl >> 31) & 1] + row * (int64_t)a.D4 * 4, RB, bar);
+        if (need_acc) bulk_g2s_hint(dst + 2u * RB, a.acc + row * (int64_t)a.D4 * 4, RB, bar, pol_stream);
+      }
+    };
 #pragma unroll
-  for (int k = 0; k < NK; ++k) sh[wid][k * 32 + lane] = sum.v[k];
-  if (lane == 0) shs[wid] = ssum;
-  __syncthreads();
-  if (wid != 0) return;
-  float bacc = shs[0];
-#pragma unroll
-  for (int w = 1; w < kCombineWarps; ++w) {
-#pragma unroll
-    for (int k = 0; k < NK; ++k) f4_add(sum.v[k], sh[w][k * 32 + lane]);
-    bacc += shs[w];
+    for (int s = 0; s < NS; ++s)
+      if (s < m.cnt) issue(s);
+
+    SegState<NK> st;
+    row_zero(st.cur);
+    row_zero(st.grad);
+    st.bacc = 0.f;
+    st.started_here = false;
+    st.cur_key = kNoKey;
+
+    for (int s = 0; s < m.cnt; ++s) {
+      const int stg = s % NS;
+      const int32_t code = __shfl_sync(FULL, m.r.code, s);
+      const float w = __shfl_sync(FULL, m.r.w, s);
+      const float t = __shfl_sync(FULL, m.r.t, s);
+      const float bs = __shfl_sync(FULL, m.r.bs, s);
+      const int32_t key = __shfl_sync(FULL, m.kl, s);
+      mbar_wait(bar0 + 8u * stg, (phase >> stg) & 1u);
+      phase ^= 1u << stg;
+      const float4* sp = reinterpret_cast<const float4*>(my + (size_t)stg * stage_bytes);
+      Row<NK> P, Sf, A;
+      row_from_smem<NK>(P, sp, lane, a.D4);
+      if (s == 0 || ((m.head_mask >> s) & 1u)) row_from_smem<NK>(Sf, sp + a.D4, lane, a.D4);
+      if (!a.emit && ((m.end_mask >> s) & 1u)) row_from_smem<NK>(A, sp + 2 * a.D4, lane, a.D4);
+      __syncwarp();  // every lane has read the stage: it can be refilled
+      if (s + NS < m.cnt) issue(s + NS);
+      consume_slot<NK>(a, m, c, s, st, P, Sf, A, code, key, w, t, bs, mbs, sums, lane);
+    }
   }
+  store_block_sums(a, sums, red, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Combine: adds the per-chunk partial sums of every segment that straddles chunk boundaries, in
+// chunk order with a fixed tree (deterministic), and closes the segment.  The row pass queued the
+// head chunk of each such segment: short ones (<= kHeavyParts partials) are taken one per warp,
+// the Zipf-head rows (thousands of partials) one per block.  Block 0 first reduces the S1/S2
+// block partials into scalars[3..4].
+// ---------------------------------------------------------------------------------------------
+struct Straddler {
+  int32_t key;
+  int64_t u, np;
+};
+
+__device__ __forceinline__ Straddler straddler_of(const RowsArgs& a, int64_t c) {
+  Straddler s;
+  const int64_t pl = min((c + 1) * (int64_t)a.chunk, a.n) - 1;
+  s.key = a.skv[pl];
+  s.u = a.useg[pl];
+  s.np = (a.seg_off[s.u + 1] - 1) / a.chunk - c + 1;
+  return s;
+}
+
+// partial m of the segment whose head chunk is c: m == 0 -> part[c][1]; m >= 1 -> part[c+m][0]
+__device__ __forceinline__ int64_t part_index(int64_t c, int64_t m) { return m == 0 ? c * 2 + 1 : (c + m) * 2; }
+
+template <int NK, int UN>
+__device__ __forceinline__ void sum_parts(const RowsArgs& a, int64_t c, int64_t m0, int64_t m1, Row<NK>& sum,
+                                          float& ssum, int lane) {
+  for (int64_t m = m0; m < m1; m += UN) {
+    Row<NK> x[UN];
+    float xs[UN];
+#pragma unroll
+    for (int j = 0; j < UN; ++j) {
+      if (m + j < m1) {
+        const int64_t idx = part_index(c, m + j);
+        row_load<NK, true>(x[j], reinterpret_cast<const float4*>(a.part) + idx * a.D4, lane, a.D4);
+        xs[j] = a.parts[idx];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UN; ++j) {
+      if (m + j < m1) {
+        row_add<NK>(sum, x[j]);
+        ssum += xs[j];
+      }
+    }
+  }
+}
+
+template <int NK>
+__device__ __forceinline__ void close_straddler(const RowsArgs& a, const Straddler& s, const Row<NK>& sum, float bacc,
+                                                int lane) {
   Row<NK> self, accrow;
   row_zero(self);
   row_zero(accrow);
   if (!a.emit) {
-    const int64_t row = key & kRowMask;
-    const int v = (key >> 31) & 1;
+    const int64_t row = s.key & kRowMask;
+    const int v = (s.key >> 31) & 1;
     row_load<NK, false>(self, reinterpret_cast<const float4*>(a.rows[v]) + row * a.D4, lane, a.D4);
     row_load<NK, true>(accrow, reinterpret_cast<const float4*>(a.acc) + row * a.D4, lane, a.D4);
   }
-  close_segment<NK>(a, key, u, self, accrow, sum, bacc, lane);
+  close_segment<NK>(a, s.key, s.u, self, accrow, sum, bacc, lane);
+}
+
+template <int NK>
+__global__ void __launch_bounds__(kCombineThreads) k_glove_combine(const RowsArgs a, int row_blocks,
+                                                                   float* __restrict__ scalars) {
+  constexpr int UN = NK == 1 ? 8 : 4;
+  __shared__ float4 sh[kCombineWarps][NK * 32];
+  __shared__ float shs[kCombineWarps];
+  if (blockIdx.x == 0) reduce_partials<2>(a.rows_blk, row_blocks, scalars + ESR_SC_S1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // light work list: one warp per straddling segment
+  const int nl = a.wl_count[0];
+  for (int e = blockIdx.x * kCombineWarps + wid; e < nl; e += gridDim.x * kCombineWarps) {
+    const int64_t c = a.wl_light[e];
+    const Straddler s = straddler_of(a, c);
+    Row<NK> sum;
+    row_zero(sum);
+    float bacc = 0.f;
+    sum_parts<NK, UN>(a, c, 0, s.np, sum, bacc, lane);
+    close_straddler<NK>(a, s, sum, bacc, lane);
+  }
+  // heavy work list: one block per segment, warps take contiguous ranges of partials
+  const int nh = a.wl_count[1];
+  for (int e = blockIdx.x; e < nh; e += gridDim.x) {
+    const int64_t c = a.wl_heavy[e];
+    const Straddler s = straddler_of(a, c);
+    const int64_t per = ceil_div(s.np, (int64_t)kCombineWarps);
+    const int64_t m0 = wid * per, m1 = min(s.np, m0 + per);
+    Row<NK> sum;
+    row_zero(sum);
+    float ssum = 0.f;
+    sum_parts<NK, UN>(a, c, m0, m1, sum, ssum, lane);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) sh[wid][k * 32 + lane] = sum.v[k];
+    if (lane == 0) shs[wid] = ssum;
+    __syncthreads();
+    if (wid == 0) {
+      float bacc = shs[0];
+      for (int w = 1; w < kCombineWarps; ++w) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) f4_add(sum.v[k], sh[w][k * 32 + lane]);
+        bacc += shs[w];
+      }
+      close_straddler<NK>(a, s, sum, bacc, lane);
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,6 +869,11 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.skv = w.skv;
   a.rec = w.rec;
   a.useg = plan->useg;
+  a.seg_off = plan->seg_off;
+  a.wl_count = w.wl_count;
+  a.wl_light = w.wl_light;
+  a.wl_heavy = w.wl_heavy;
+  a.nchunks = w.nchunks;
   a.scalars = scalars;
   a.bsum = w.bsum;
   a.part = w.part;
@@ -540,37 +921,94 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
   return ESR_OK;
 }
 
-template <int NK, int S>
-static int launch_rows(const RowsArgs& a, const GloveWs& w, const EsrPlan* plan, float* scalars, cudaStream_t stream) {
-  k_glove_rows<NK, S><<<w.row_blocks, kThreads, 0, stream>>>(a);
-  ESR_LAUNCH_CHECK();
-  k_glove_combine<NK><<<(unsigned)(w.nchunks + 1), kCombineThreads, 0, stream>>>(a, plan->seg_off, w.nchunks, w.row_blocks,
-                                                                               scalars);
-  ESR_LAUNCH_CHECK();
+template <int G, int NV, int NKC>
+static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream) {
+  constexpr int GP = 32 / G;
+  const int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
+  if (phases & 1) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 2 * sizeof(int32_t), stream));
+    k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)><<<row_blocks, kThreads, 0, stream>>>(a);
+    ESR_LAUNCH_CHECK();
+  }
+  if (phases & 2) {
+    k_glove_combine<NKC><<<2 * sm_count(), kCombineThreads, 0, stream>>>(a, row_blocks, scalars);
+    ESR_LAUNCH_CHECK();
+  }
   return ESR_OK;
 }
 
-extern "C" int esr_glove_rows_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* dE,
-                                  void* ws, size_t ws_bytes, esr_stream_t stream_) {
+template <int NK, int S, int MINB>
+static int launch_rows(const RowsArgs& a, const GloveWs& w, float* scalars, bool tma, int phases, cudaStream_t stream) {
+  int row_blocks = w.row_blocks;
+  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 2 * sizeof(int32_t), stream));
+  if (tma) {
+    const size_t smem = (size_t)kWarps * kTmaStages * 3 * a.D4 * 16;
+    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per NK: largest dynamic smem opted in
+    if (smem > configured[NK]) {
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_tma<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[NK] = smem;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(tma_min_blocks(NK), (size_t)(220 * 1024) / (smem + 1024)));
+    row_blocks = (int)std::min<int64_t>(w.row_blocks, (int64_t)sm_count() * per_sm);
+    if (phases & 1) k_glove_rows_tma<NK><<<row_blocks, kThreads, smem, stream>>>(a);
+  } else {
+    if (phases & 1) k_glove_rows<NK, S, MINB><<<row_blocks, kThreads, 0, stream>>>(a);
+  }
+  ESR_LAUNCH_CHECK();
+  if (phases & 2) {
+    k_glove_combine<NK><<<2 * sm_count(), kCombineThreads, 0, stream>>>(a, row_blocks, scalars);
+    ESR_LAUNCH_CHECK();
+  }
+  return ESR_OK;
+}
+
+static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* dE, void* ws,
+                           size_t ws_bytes, int phases, esr_stream_t stream_) {
   ESR_REQUIRE(cfg_ok(cfg, plan) && glove_table_ok(t, cfg->rows_mode == ESR_ROWS_UPDATE) && scalars != nullptr);
   if (cfg->B == 0) return ESR_OK;
   const bool emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
   ESR_REQUIRE(ws && plan->useg && plan->seg_off);
   ESR_REQUIRE(!emit || (dE != nullptr && (reinterpret_cast<uintptr_t>(dE) % 16) == 0));
-  if (cfg->impl != ESR_IMPL_AUTO && cfg->impl != ESR_IMPL_LDG) return ESR_ENOTSUP;
+  if (cfg->impl != ESR_IMPL_AUTO && cfg->impl != ESR_IMPL_LDG && cfg->impl != ESR_IMPL_TMA) return ESR_EINVAL;
+  const bool tma = cfg->impl == ESR_IMPL_TMA;
   if (ws_bytes < esr_glove_workspace_bytes(cfg->B, t->D, cfg->chunk)) return ESR_EWORKSPACE;
   GloveWs w;
   carve_ws(ws, cfg->B, t->D, cfg->chunk, &w);
   const RowsArgs a = make_rows_args(t, plan, cfg, w, scalars, dE);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int nk = (a.D4 + 31) / 32;
+  if (cfg->impl == ESR_IMPL_AUTO) {
+    // group variant: G lanes x 4 float4 per row (G = D/16 rounded up to a power of two)
+    const int d4 = a.D4;
+    if (d4 <= 4) return launch_rows_grp<1, 4, 1>(a, w, scalars, phases, stream);
+    if (d4 <= 8) return launch_rows_grp<2, 4, 1>(a, w, scalars, phases, stream);
+    if (d4 <= 16) return launch_rows_grp<4, 4, 1>(a, w, scalars, phases, stream);
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream);
+  }
   switch (nk) {
-    case 1: return launch_rows<1, 4>(a, w, plan, scalars, stream);
-    case 2: return launch_rows<2, 2>(a, w, plan, scalars, stream);
-    case 3: return launch_rows<3, 1>(a, w, plan, scalars, stream);
-    case 4: return launch_rows<4, 1>(a, w, plan, scalars, stream);
+    case 1:
+      return launch_rows<1, 2, 4>(a, w, scalars, tma, phases, stream);
+    case 2: return launch_rows<2, 2, 1>(a, w, scalars, tma, phases, stream);
+    case 3: return launch_rows<3, 1, 1>(a, w, scalars, tma, phases, stream);
+    case 4: return launch_rows<4, 1, 1>(a, w, scalars, tma, phases, stream);
     default: return ESR_EINVAL;
   }
+}
+
+extern "C" int esr_glove_rows_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* dE,
+                                  void* ws, size_t ws_bytes, esr_stream_t stream) {
+  return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 3, stream);
+}
+extern "C" int esr_glove_rows_main_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                                       float* dE, void* ws, size_t ws_bytes, esr_stream_t stream) {
+  return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 1, stream);
+}
+extern "C" int esr_glove_rows_combine_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                                          float* dE, void* ws, size_t ws_bytes, esr_stream_t stream) {
+  return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 2, stream);
 }
 
 extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* db,

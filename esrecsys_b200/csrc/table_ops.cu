@@ -119,10 +119,14 @@ __global__ void __launch_bounds__(kThreads) k_scatter_rows(float4* __restrict__ 
 }
 
 // optax.adam: mu = b1 mu + (1-b1) g ; nu = b2 nu + (1-b2) g^2 ; p -= lr (mu/c1) / (sqrt(nu/c2) + eps)
-__device__ __forceinline__ void adam1(float& p, float g, float& mu, float& nu, float lr, float b1, float b2, float eps,
-                                      float c1, float c2) {
-  mu = b1 * mu + (1.f - b1) * g;
-  nu = b2 * nu + (1.f - b2) * (g * g);
+struct AdamK {
+  float lr, b1, b2, omb1, omb2, eps, c1, c2;  // omb = 1 - b, c = 1 - b^count: evaluated in double on the host
+};
+
+__device__ __forceinline__ void adam1(float& p, float g, float& mu, float& nu, const AdamK& k) {
+  const float lr = k.lr, eps = k.eps, c1 = k.c1, c2 = k.c2;
+  mu = k.b1 * mu + k.omb1 * g;
+  nu = k.b2 * nu + k.omb2 * (g * g);
   const float mhat = mu / c1;
   const float vhat = nu / c2;
   p = p - lr * mhat / (sqrtf(vhat) + eps);
@@ -130,18 +134,17 @@ __device__ __forceinline__ void adam1(float& p, float g, float& mu, float& nu, f
 
 __global__ void __launch_bounds__(kThreads) k_dense_adam(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ mu, float* __restrict__ nu, int64_t n,
-                                                         float lr, float b1, float b2, float eps, float c1,
-                                                         float c2) {
+                                                         const AdamK k) {
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
     float4 m = reinterpret_cast<float4*>(mu)[i], v = reinterpret_cast<float4*>(nu)[i];
-    adam1(pv.x, gv.x, m.x, v.x, lr, b1, b2, eps, c1, c2);
-    adam1(pv.y, gv.y, m.y, v.y, lr, b1, b2, eps, c1, c2);
-    adam1(pv.z, gv.z, m.z, v.z, lr, b1, b2, eps, c1, c2);
-    adam1(pv.w, gv.w, m.w, v.w, lr, b1, b2, eps, c1, c2);
+    adam1(pv.x, gv.x, m.x, v.x, k);
+    adam1(pv.y, gv.y, m.y, v.y, k);
+    adam1(pv.z, gv.z, m.z, v.z, k);
+    adam1(pv.w, gv.w, m.w, v.w, k);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(mu)[i] = m;
     reinterpret_cast<float4*>(nu)[i] = v;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_adam(float* __restrict__ p, 
   // tail (n % 4) by the first threads of block 0
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    adam1(p[i], g[i], mu[i], nu[i], lr, b1, b2, eps, c1, c2);
+    adam1(p[i], g[i], mu[i], nu[i], k);
   }
 }
 
@@ -271,18 +274,20 @@ static unsigned dense_grid(int64_t n) {
   return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
-extern "C" int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, float lr, float b1, float b2,
-                                  float eps, int64_t count, esr_stream_t stream_) {
+extern "C" int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, double lr, double b1,
+                                  double b2, double eps, int64_t count, esr_stream_t stream_) {
   ESR_REQUIRE(n >= 0 && count >= 1);
   if (n == 0) return ESR_OK;
   ESR_REQUIRE(p && g && mu && nu);
   ESR_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mu) |
                 reinterpret_cast<uintptr_t>(nu)) % 16) == 0);
   // bias corrections in double on the host, like optax evaluates 1 - b^count in python floats / f32
-  const float c1 = (float)(1.0 - pow((double)b1, (double)count));
-  const float c2 = (float)(1.0 - pow((double)b2, (double)count));
-  k_dense_adam<<<dense_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p, g, mu, nu, n, lr, b1, b2, eps,
-                                                                                   c1, c2);
+  AdamK k;
+  k.lr = (float)lr; k.b1 = (float)b1; k.b2 = (float)b2; k.omb1 = (float)(1.0 - b1); k.omb2 = (float)(1.0 - b2);
+  k.eps = (float)eps;
+  k.c1 = (float)(1.0 - pow(b1, (double)count));
+  k.c2 = (float)(1.0 - pow(b2, (double)count));
+  k_dense_adam<<<dense_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p, g, mu, nu, n, k);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

@@ -149,7 +149,7 @@ class GloveStep:
     phases over an IndexPlan (include/esr.h: esr_glove_prep/rows/finish)."""
 
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", eps=1e-7,
-                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None):
+                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto"):
         self.table = table
         self.B = int(B)
         dev = table.device
@@ -157,7 +157,7 @@ class GloveStep:
         cfg.struct_size = C.sizeof(L.EsrGloveCfg)
         cfg.bias_mode = L.BIAS_MODES[bias_mode]
         cfg.rows_mode = L.ROWS_EMIT_GRADS if emit_grads else L.ROWS_UPDATE
-        cfg.impl = L.IMPL_AUTO
+        cfg.impl = impl if isinstance(impl, int) else {"auto": L.IMPL_AUTO, "ldg": L.IMPL_LDG, "tma": L.IMPL_TMA}[impl]
         cfg.B = self.B
         cfg.B_global = int(B_global if B_global is not None else B)
         cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
@@ -183,6 +183,16 @@ class GloveStep:
         t, p, c = self._args(plan)
         L.check(L.lib().esr_glove_rows_f32(t, p, c, L.ptr(self.scalars), L.ptr(self.dE), L.ptr(self.ws), self.ws_bytes,
                                            L.stream_ptr(stream)), "esr_glove_rows_f32")
+
+    def rows_main(self, plan, stream=None):
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_rows_main_f32(t, p, c, L.ptr(self.scalars), L.ptr(self.dE), L.ptr(self.ws),
+                                                self.ws_bytes, L.stream_ptr(stream)), "esr_glove_rows_main_f32")
+
+    def rows_combine(self, plan, stream=None):
+        t, p, c = self._args(plan)
+        L.check(L.lib().esr_glove_rows_combine_f32(t, p, c, L.ptr(self.scalars), L.ptr(self.dE), L.ptr(self.ws),
+                                                   self.ws_bytes, L.stream_ptr(stream)), "esr_glove_rows_combine_f32")
 
     def finish(self, plan, stream=None):
         t, p, c = self._args(plan)

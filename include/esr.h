@@ -155,6 +155,12 @@ int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const float* coun
  * emit dE[U,D]); sums [3..4].  dE may be NULL in UPDATE mode. */
 int esr_glove_rows_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
                        float* dE, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* The two kernels of phase 2 separately (esr_glove_rows_f32 == main then combine): the row pass
+ * proper, and the fixed-order combine of the partial sums of segments that straddle chunks. */
+int esr_glove_rows_main_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                            float* dE, void* ws, size_t ws_bytes, esr_stream_t stream);
+int esr_glove_rows_combine_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
+                               float* dE, void* ws, size_t ws_bytes, esr_stream_t stream);
 /* Phase 3: bias gradient (-> Adagrad in place | emit db[U]), version flip, loss -> scalars[5]. */
 int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
                          float* db, void* ws, size_t ws_bytes, esr_stream_t stream);
@@ -174,9 +180,11 @@ int esr_sparse_adagrad_f32(EsrTable* t, const int32_t* uniq, const int32_t* n_un
 int esr_scatter_rows_f32(float* dst, int32_t D, const int32_t* uniq, const int32_t* n_uniq,
                          int64_t cap, const float* g, int32_t accumulate, esr_stream_t stream);
 /* optax.adam(lr) over n elements -- wikipedia/train_cooccurence.py:171, :101;
- * pinterest/train_shop_the_look.py:175.  `count` is the step count AFTER this update (>=1). */
-int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, float lr, float b1,
-                       float b2, float eps, int64_t count, esr_stream_t stream);
+ * pinterest/train_shop_the_look.py:175.  `count` is the step count AFTER this update (>=1).
+ * Hyper-parameters are doubles because optax evaluates 1-b and 1-b^count in Python floats before the
+ * f32 cast (1.f - 0.999f is off by 5e-5 relative). */
+int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, double lr, double b1,
+                       double b2, double eps, int64_t count, esr_stream_t stream);
 /* optax.sgd(lr, momentum) over n elements -- spotify/train_spotify.py:238-241, :110. */
 int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float lr, float momentum,
                        esr_stream_t stream);

@@ -90,19 +90,20 @@ def test_gather_and_export_bit_exact(D):
     assert t.gather(torch.zeros(0, dtype=torch.int32)).shape == (0, D)
 
 
-def _emit(E, b, ids, counts, bias_mode, chunk=0):
+def _emit(E, b, ids, counts, bias_mode, chunk=0, impl="auto"):
     eng = _engine()
     V, D = E.shape
     B = ids.shape[1]
     t = eng.EmbeddingTable.from_dense(E, b, sparse=False)
     keys = torch.from_numpy(ids.reshape(-1)).cuda()
     plan = eng.IndexPlan(2 * B, V).build(keys)
-    step = eng.GloveStep(t, B, bias_mode=bias_mode, emit_grads=True, chunk=chunk)
+    step = eng.GloveStep(t, B, bias_mode=bias_mode, emit_grads=True, chunk=chunk, impl=impl)
     sc = step.run(plan, torch.from_numpy(counts).cuda()).cpu().numpy()
     U = int(plan.n_uniq.item())
     return sc, step.dE[:U].cpu().numpy(), step.db[:U].cpu().numpy(), plan
 
 
+@pytest.mark.parametrize("impl", ["auto", "ldg", "tma"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B,chunk", [
     (10000, 64, 2048, 0),      # BASELINE config 1 shape
@@ -115,10 +116,10 @@ def _emit(E, b, ids, counts, bias_mode, chunk=0):
     (2000, 512, 300, 0),
     (3, 8, 1, 0),              # single pair
 ])
-def test_grads_match_oracle(V, D, B, chunk, bias_mode):
+def test_grads_match_oracle(V, D, B, chunk, bias_mode, impl):
     E, b = _tables(V, D, seed=V + D)
     ids, counts = _batch(V, B, seed=B + D)
-    sc, dE, db, plan = _emit(E, b, ids[0], counts[0], bias_mode, chunk)
+    sc, dE, db, plan = _emit(E, b, ids[0], counts[0], bias_mode, chunk, impl)
     gr = og.loss_and_grads(E, b, ids[0, 0], ids[0, 1], counts[0], bias_mode)
     assert np.array_equal(plan.uniq[:len(gr.uniq)].cpu().numpy(), gr.uniq)
     np.testing.assert_allclose(sc[5], gr.loss, rtol=RTOL, atol=ATOL)
@@ -144,9 +145,11 @@ def test_grads_i_equals_j_and_literal_loss():
     np.testing.assert_allclose(sc[5], lit, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("impl", ["auto", "ldg", "tma"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
-@pytest.mark.parametrize("V,D,B,uniform", [(10000, 64, 2048, False), (300, 128, 1024, False), (50000, 128, 8192, True)])
-def test_adagrad_steps_match_oracle(V, D, B, uniform, bias_mode):
+@pytest.mark.parametrize("V,D,B,uniform", [(10000, 64, 2048, False), (300, 128, 1024, False), (50000, 128, 8192, True),
+                                           (20, 256, 4096, False)])
+def test_adagrad_steps_match_oracle(V, D, B, uniform, bias_mode, impl):
     """Several fused sparse-Adagrad steps (north-star rule) vs oracle.glove.step_adagrad."""
     eng = _engine()
     n_steps = 5
@@ -154,7 +157,7 @@ def test_adagrad_steps_match_oracle(V, D, B, uniform, bias_mode):
     E, b = _tables(V, D, seed=V)
     ids, counts = _batch(V, B, seed=V + 1, uniform=uniform, n=n_steps)
     t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
-    step = eng.GloveStep(t, B, lr=lr, bias_mode=bias_mode)
+    step = eng.GloveStep(t, B, lr=lr, bias_mode=bias_mode, impl=impl)
     plan = eng.IndexPlan(2 * B, V)
     Eo, bo = E.copy(), b.copy()
     accE = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC)
