@@ -21,6 +21,8 @@
 //   Segments that straddle a chunk boundary (Zipf head rows) leave per-chunk partial sums that
 //   k_glove_combine adds in a fixed order, so the result is bit-reproducible run to run.
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 
 #include "esr_common.cuh"
 
@@ -59,31 +61,60 @@ struct GloveWs {
   int32_t chunk;
 };
 
-int norm_chunk(int32_t chunk) {
-  if (chunk <= 0) return 32;
+// lanes that own one row in the group variant: 4 float4 per lane, rounded up to a power of two
+int group_lanes(int D4) {
+  int g = 1;
+  while (g * 4 < D4 && g < 32) g <<= 1;
+  return g;
+}
+
+constexpr int kMinAutoChunk = 16;
+
+// chunk == 0: pick the chunk length that wastes the least of the last wave.  All resident groups
+// advance in lock step through `rounds` chunks, so the pass costs rounds * (chunk + start-up).
+int auto_chunk(int64_t n, int D4) {
+  const int64_t resident = (int64_t)sm_count() * 2 * kWarps * (32 / group_lanes(D4));
+  int best = 32;
+  int64_t best_cost = INT64_MAX;
+  for (int c = 32; c >= kMinAutoChunk; c -= 4) {
+    const int64_t rounds = ceil_div(ceil_div(n, c), resident);
+    const int64_t cost = rounds * (c + 2);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+int norm_chunk(int32_t chunk, int64_t n, int D4) {
+  if (chunk <= 0) return auto_chunk(n, D4);
   if (chunk > 32) return 32;
   return (chunk + 3) / 4 * 4;
 }
 
 size_t carve_ws(void* base, int64_t B, int32_t D, int32_t chunk_in, GloveWs* w) {
   const int64_t n = 2 * (B > 0 ? B : 1);
-  const int chunk = norm_chunk(chunk_in);
+  const int chunk = norm_chunk(chunk_in, n, D / 4);
   Carver c(base);
   GloveWs t;
   t.chunk = chunk;
   t.nchunks = ceil_div(n, chunk);
+  // capacity: with chunk == 0 the chunk length is chosen per device, so size for the smallest one
+  const int64_t cap_chunks = chunk_in <= 0 ? ceil_div(n, kMinAutoChunk) : t.nchunks;
   t.prep_blocks = (int32_t)ceil_div(n, kThreads);
   t.row_blocks = (int32_t)ceil_div(t.nchunks, kWarps);
+  const int64_t cap_row_blocks = ceil_div(cap_chunks, kWarps);
   t.skv = c.take<int32_t>(n);
   t.rec = c.take<SlotRec>(n);
   t.bsum = c.take<float>(n);
-  t.part = c.take<float>(t.nchunks * 2 * D);
-  t.parts = c.take<float>(t.nchunks * 2);
+  t.part = c.take<float>(cap_chunks * 2 * D);
+  t.parts = c.take<float>(cap_chunks * 2);
   t.prep_blk = c.take<float>((size_t)t.prep_blocks * 3);
-  t.rows_blk = c.take<float>((size_t)t.row_blocks * 2);
+  t.rows_blk = c.take<float>((size_t)cap_row_blocks * 2);
   t.wl_count = c.take<int32_t>(2);
-  t.wl_light = c.take<int32_t>(t.nchunks);
-  t.wl_heavy = c.take<int32_t>(t.nchunks);
+  t.wl_light = c.take<int32_t>(cap_chunks);
+  t.wl_heavy = c.take<int32_t>(cap_chunks);
   if (w) *w = t;
   return c.off;
 }
@@ -461,29 +492,34 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
   float bacc = 0.f;
   bool started_here = false;
   int64_t u = 0;
-  // metadata runs one slot ahead of the row loads
+  // The record runs two slots ahead and the PARTNER row one slot ahead of the consumer, so a
+  // group always has the next partner row in flight while it works on the current slot (on the
+  // Zipf stream most slots need nothing else).
   int32_t key_prev = kNoKey, key_cur = kNoKey, key_next = kNoKey;
-  SlotRec rec;
+  SlotRec rec, rec1;  // slots s and s+1
   rec.code = 0; rec.w = 0.f; rec.t = 0.f; rec.bs = 0.f;
+  rec1 = rec;
+  Row<NV> Pn;  // partner row of slot s (prefetched during slot s-1)
+  row_zero(Pn);
   if (cnt > 0) {
     key_prev = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
     key_cur = a.skv[p0];
     rec = a.rec[p0];
+    if (cnt > 1) rec1 = a.rec[p0 + 1];
     u = a.useg[p0];
+    const uint32_t q = (uint32_t)(rec.code & kRowMask);
+    grow_load<G, NV>(Pn, ((rec.code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl, a.D4, false);
   }
   for (int s = 0; s < a.chunk; ++s) {
     const bool active = s < cnt;
-    SlotRec rec_next = rec;
-    Row<NV> P, A;
-    row_zero(P);
+    SlotRec rec2 = rec1;
+    Row<NV> P = Pn, A;
     bool is_head = false, is_end = false;
     if (active) {
       key_next = p0 + s + 1 < a.n ? a.skv[p0 + s + 1] : kNoKey;
-      if (s + 1 < cnt) rec_next = a.rec[p0 + s + 1];
+      if (s + 2 < cnt) rec2 = a.rec[p0 + s + 2];
       is_head = key_cur != key_prev;
       is_end = key_cur != key_next;
-      const uint32_t q = (uint32_t)(rec.code & kRowMask);
-      grow_load<G, NV>(P, ((rec.code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl, a.D4, false);
       const uint32_t row = (uint32_t)(key_cur & kRowMask);
       if (s == 0 || is_head) {
         grow_load<G, NV>(cur, ((key_cur >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, false);
@@ -493,6 +529,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
         if (is_head && s > 0) ++u;
       }
       if (!a.emit && is_end && started_here) grow_load<G, NV>(A, accp + (uint64_t)row * D4, gl, a.D4, true);
+      if (s + 1 < cnt) {
+        const uint32_t q = (uint32_t)(rec1.code & kRowMask);
+        grow_load<G, NV>(Pn, ((rec1.code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl, a.D4, false);
+      }
     }
     float d = 0.f;
 #pragma unroll
@@ -538,7 +578,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
     }
     key_prev = key_cur;
     key_cur = key_next;
-    rec = rec_next;
+    rec = rec1;
+    rec1 = rec2;
   }
   // per-block S1 / S2 partials: lane 0 of every group carries its group's value
   float v[2] = {gl == 0 ? sums[0] : 0.f, gl == 0 ? sums[1] : 0.f};

@@ -189,16 +189,6 @@ int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n
 int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float lr, float momentum,
                        esr_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------
- * Retrieval: Glove.score_all + find_knn (wikipedia/models.py:40-55,
- * wikipedia/train_cooccurence.py:91-97,121-125), find_top_k (pinterest/make_recommendations.py:49-65).
- * top_idx/top_val are [T,k]; best first; ties: larger row id first when tie_high != 0 (the order
- * dump_knn reads from the tail of a stable ascending argsort), else smaller id first (lax.top_k).
- * ------------------------------------------------------------------------------------------ */
-size_t esr_score_topk_workspace_bytes(int64_t V, int32_t T, int32_t k);
-int esr_score_topk_f32(const EsrTable* t, const float* queries, int32_t T, int32_t k, int32_t tie_high,
-                       int32_t* top_idx, float* top_val, void* ws, size_t ws_bytes, esr_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

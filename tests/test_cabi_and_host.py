@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/esr.h declares, the
+ctypes structs match the header's layout, the host never computes without CUDA, and the torch-CPU
+baseline port agrees with the NumPy oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "esr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(esr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from esrecsys_b200 import _lib, build
+    build.build()
+    h = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(h, n), "libesr.so does not export %s" % n
+    # the ctypes binding covers the header exactly
+    assert sorted(_lib.declared_symbols()) == names
+    assert h.esr_version() == 100
+    assert b"workspace" in h.esr_strerror(-2)
+
+
+def test_struct_layouts_match_header():
+    from esrecsys_b200 import _lib
+    # EsrTable: u32, i32, i64, 2 ptr, 4 ptr ; EsrPlan: u32, i32, i64, 8 ptr ; EsrGloveCfg: 4x4, 2x8, 4 floats, 2 ints
+    assert C.sizeof(_lib.EsrTable) == 16 + 6 * 8
+    assert C.sizeof(_lib.EsrPlan) == 16 + 8 * 8
+    assert C.sizeof(_lib.EsrGloveCfg) == 16 + 16 + 16 + 8
+    assert _lib.EsrGloveCfg.B.offset == 16 and _lib.EsrGloveCfg.lr.offset == 32
+
+
+def test_pure_queries_work_without_gpu():
+    from esrecsys_b200 import _lib
+    h = _lib.lib()
+    assert h.esr_plan_workspace_bytes(0) > 0
+    a, b = h.esr_plan_workspace_bytes(2048), h.esr_plan_workspace_bytes(1 << 21)
+    assert 0 < a < b
+    assert h.esr_glove_workspace_bytes(65536, 128, 0) > 2 * 65536 * 20
+    assert h.esr_glove_workspace_bytes(-1, 128, 0) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from esrecsys_b200 import _lib, engine
+    with pytest.raises(_lib.EsrError):
+        engine.EmbeddingTable(16, 64)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "esrecsys_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+@pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
+def test_torch_port_matches_numpy_oracle(bias_mode):
+    import torch
+    from esrecsys_b200 import synth
+    from oracle import glove as og
+    from oracle import glove_torch as ogt
+    from oracle import optim as oopt
+    V, D, B = 500, 32, 256
+    E, b = synth.init_glove_tables(V, D, 0)
+    b = (np.random.default_rng(3).standard_normal(V) * 0.05).astype(np.float32)
+    ids, counts = synth.glove_batches(V, B, 2, 1)
+    # dense Adam (the reference's rule)
+    En, bn = E.copy(), b.copy()
+    st = dict(count=0, muE=np.zeros_like(E), nuE=np.zeros_like(E), mub=np.zeros_like(b), nub=np.zeros_like(b))
+    Et, bt = torch.from_numpy(E.copy()), torch.from_numpy(b.copy())
+    stt = dict(count=0, muE=torch.zeros_like(Et), nuE=torch.zeros_like(Et), mub=torch.zeros_like(bt), nub=torch.zeros_like(bt))
+    for k in range(2):
+        ln = og.step_adam(En, bn, st, ids[k, 0], ids[k, 1], counts[k], 1e-3, bias_mode)
+        lt = ogt.step_adam_dense(Et, bt, stt, torch.from_numpy(ids[k, 0].astype(np.int64)),
+                                 torch.from_numpy(ids[k, 1].astype(np.int64)), torch.from_numpy(counts[k]), 1e-3, bias_mode)
+        np.testing.assert_allclose(lt, ln, rtol=1e-5)
+    np.testing.assert_allclose(Et.numpy(), En, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(bt.numpy(), bn, rtol=1e-5, atol=2e-6)
+    # sparse Adagrad (north star)
+    En, bn = E.copy(), b.copy()
+    aE, ab = np.full_like(E, 0.1), np.full_like(b, 0.1)
+    Et, bt = torch.from_numpy(E.copy()), torch.from_numpy(b.copy())
+    aEt, abt = torch.full_like(Et, 0.1), torch.full_like(bt, 0.1)
+    for k in range(2):
+        og.step_adagrad(En, bn, aE, ab, ids[k, 0], ids[k, 1], counts[k], 0.05, bias_mode)
+        ogt.step_adagrad_sparse(Et, bt, aEt, abt, torch.from_numpy(ids[k, 0].astype(np.int64)),
+                                torch.from_numpy(ids[k, 1].astype(np.int64)), torch.from_numpy(counts[k]), 0.05, bias_mode)
+    np.testing.assert_allclose(Et.numpy(), En, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(aEt.numpy(), aE, rtol=1e-5, atol=1e-7)
+    assert oopt.ADAGRAD_EPS == ogt.ADAGRAD_EPS
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--vocab", "20000", "--dim", "64", "--batch", "4096"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
