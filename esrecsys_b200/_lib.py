@@ -78,6 +78,12 @@ _SIGNATURES = {
     "esr_dense_adam_f32": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_int64, _P]),
     "esr_dense_sgdm_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, _P]),
+    "esr_route_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "esr_route_plan_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "esr_plan_compact_i32": (C.c_int, [C.POINTER(EsrPlan), _P, _P, _P, _P, _P]),
+    "esr_gather_scalar_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "esr_permute_rows_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "esr_segment_sum_rows_f32": (C.c_int, [C.POINTER(EsrPlan), C.c_int32, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -26,7 +26,7 @@ class EmbeddingTable:
     fetched-row table of the row-sharded path).
     """
 
-    def __init__(self, V, D, device=None, sparse=True, with_bias=True, init_acc=0.1):
+    def __init__(self, V, D, device=None, sparse=True, with_bias=True, init_acc=0.1, adagrad=None):
         self.device = _dev(device)
         if D % 4:
             raise ValueError("D must be a multiple of 4 (16-byte rows)")
@@ -35,17 +35,18 @@ class EmbeddingTable:
         self.rows0 = torch.zeros(V, D, dtype=torch.float32, device=dev)
         self.rows1 = torch.zeros(V, D, dtype=torch.float32, device=dev) if sparse else None
         self.ver = torch.zeros(V, dtype=torch.uint8, device=dev) if sparse else None
-        self.acc = torch.full((V, D), float(init_acc), dtype=torch.float32, device=dev) if sparse else None
+        adagrad = sparse if adagrad is None else bool(adagrad)   # single-buffer shards still carry the Adagrad slot
+        self.acc = torch.full((V, D), float(init_acc), dtype=torch.float32, device=dev) if adagrad else None
         self.bias = torch.zeros(V, dtype=torch.float32, device=dev) if with_bias else None
         self.bias_acc = (torch.full((V,), float(init_acc), dtype=torch.float32, device=dev)
-                         if (with_bias and sparse) else None)
+                         if (with_bias and adagrad) else None)
         self._struct = None
 
     # -- construction ----------------------------------------------------------------------
     @classmethod
-    def from_dense(cls, E, bias=None, device=None, sparse=True, init_acc=0.1):
+    def from_dense(cls, E, bias=None, device=None, sparse=True, init_acc=0.1, adagrad=None):
         E = torch.as_tensor(E)
-        t = cls(E.shape[0], E.shape[1], device, sparse, bias is not None, init_acc)
+        t = cls(E.shape[0], E.shape[1], device, sparse, bias is not None, init_acc, adagrad)
         t.rows0.copy_(E.to(torch.float32))
         if bias is not None:
             t.bias.copy_(torch.as_tensor(bias).to(torch.float32).reshape(-1))
@@ -96,6 +97,7 @@ class IndexPlan:
         self.device = _dev(device)
         n = int(n_slots)
         self.n_slots = n
+        self.capacity = n
         dev = self.device
         i32 = dict(dtype=torch.int32, device=dev)
         cap = max(n, 1)
@@ -122,9 +124,13 @@ class IndexPlan:
         self._keys = None
 
     def build(self, keys, stream=None):
-        """keys: int32 device tensor with n_slots elements (for GloVe the flat (2,B) batch)."""
-        assert keys.dtype == torch.int32 and keys.is_cuda and keys.is_contiguous() and keys.numel() == self.n_slots
+        """keys: int32 device tensor (for GloVe the flat (2,B) batch).  Fewer keys than the capacity
+        the plan was created with are allowed (owner-side plans of the sharded path vary per step)."""
+        assert keys.dtype == torch.int32 and keys.is_cuda and keys.is_contiguous()
+        assert keys.numel() <= self.capacity
         self._keys = keys  # keep alive until the next build
+        self.n_slots = keys.numel()
+        self.s.n_slots = self.n_slots
         self.s.keys = L.ptr(keys)
         L.check(L.lib().esr_plan_build_i32(C.byref(self.s), L.ptr(self.ws), self.ws_bytes, L.stream_ptr(stream)),
                 "esr_plan_build_i32")

@@ -1,0 +1,209 @@
+"""Row-sharded GloVe training across the GPUs of one box (BASELINE.json north star; the reference
+itself is single-device -- SURVEY.md 0, 8(e)).
+
+One process per GPU.  The table is sharded CYCLICALLY (owner = row % n, local = row // n; rows are
+frequency ranks, wikipedia/make_dictionary.py:113-116).  A step on rank r, for its B_local pairs:
+
+  1. index plan of the local batch (sort / unique / segments)             libesr
+  2. bucket the unique rows by owner                                      libesr  esr_route_plan_i32
+  3. count all-to-all, id all-to-all                                      NCCL
+  4. owners gather the requested rows (+ biases)                          libesr
+  5. row all-to-all back; scatter into the compact table in unique order  NCCL + libesr
+  6. the GloVe step on the compact table in EMIT_GRADS mode, with the batch sums all-reduced
+     (3 floats before the row pass, 2 after) so every rank uses the GLOBAL mean(bs), S0, S1
+  7. gradient all-to-all to the owners                                    NCCL
+  8. owners merge duplicates across source ranks (sorted, deterministic) and apply sparse Adagrad
+
+The exchange choreography (``RowExchange``) is device-agnostic given an ``ops`` object; the product
+uses ``LibesrOps`` (CUDA only -- it raises without a GPU).  tests/ drives the same choreography on CPU
+with gloo and NumPy ops to pin the routing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .engine import EmbeddingTable, GloveStep, IndexPlan
+
+
+def shard_rows(V, rank, n):
+    return (V - rank + n - 1) // n
+
+
+class LibesrOps:
+    """The CUDA implementation of the per-rank pieces (every method enqueues on the current stream)."""
+
+    def __init__(self, device):
+        L.require_cuda()
+        self.dev = device
+        self._route_ws = None
+        self._plans = {}
+
+    def route_plan(self, uniq, n_uniq, n_ranks):
+        cap = uniq.numel()
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        order = torch.empty(cap, **i32)
+        send_local = torch.empty(cap, **i32)
+        send_counts = torch.zeros(n_ranks, **i32)
+        need = int(L.lib().esr_route_workspace_bytes(cap))
+        if self._route_ws is None or self._route_ws.numel() < need:
+            self._route_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        L.check(L.lib().esr_route_plan_i32(L.ptr(uniq), L.ptr(n_uniq), cap, n_ranks, L.ptr(order), L.ptr(send_local),
+                                           L.ptr(send_counts), L.ptr(self._route_ws), self._route_ws.numel(),
+                                           L.stream_ptr()), "esr_route_plan_i32")
+        return order, send_local, send_counts
+
+    def gather_rows(self, table: EmbeddingTable, ids):
+        return table.gather(ids)
+
+    def gather_scalar(self, src, ids):
+        out = torch.empty(ids.numel(), dtype=torch.float32, device=self.dev)
+        L.check(L.lib().esr_gather_scalar_f32(L.ptr(src), L.ptr(ids), ids.numel(), L.ptr(out), L.stream_ptr()),
+                "esr_gather_scalar_f32")
+        return out
+
+    def permute_rows(self, src, idx, n, scatter, out):
+        """scatter: out[idx[k]] = src[k]; else out[k] = src[idx[k]]; k < n."""
+        D = src.shape[1]
+        L.check(L.lib().esr_permute_rows_f32(L.ptr(src), L.ptr(idx), None, int(n), D, 1 if scatter else 0, L.ptr(out),
+                                             L.stream_ptr()), "esr_permute_rows_f32")
+        return out
+
+    def owner_update(self, shard: EmbeddingTable, recv_ids, recv_g, recv_gb, lr, eps):
+        """Merge the gradients received for owner-local rows (duplicates across source ranks) and apply
+        optax.adagrad to the shard (App. A.5)."""
+        R = recv_ids.numel()
+        if R == 0:
+            return
+        cap = 1 << max(10, (R - 1).bit_length())
+        plan = self._plans.get(cap)
+        if plan is None:
+            plan = IndexPlan(cap, shard.V, self.dev, with_partner=False)
+            self._plans[cap] = plan
+        plan.build(recv_ids)
+        D = shard.D
+        gsum = torch.empty(R, D, dtype=torch.float32, device=self.dev)
+        gbsum = torch.empty(R, dtype=torch.float32, device=self.dev)
+        L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), D, L.ptr(recv_g), L.ptr(recv_gb), L.ptr(gsum),
+                                                 L.ptr(gbsum), L.stream_ptr()), "esr_segment_sum_rows_f32")
+        L.check(L.lib().esr_sparse_adagrad_f32(C.byref(shard.struct()), L.ptr(plan.uniq), L.ptr(plan.n_uniq), R,
+                                               L.ptr(gsum), L.ptr(gbsum), lr, eps, L.stream_ptr()), "esr_sparse_adagrad_f32")
+
+
+class RowExchange:
+    """fetch(): unique global rows -> their current values from the owners; push(): per-row gradients
+    -> owners, merged and applied.  ``ops`` supplies the per-rank compute; ``shard`` is this rank's table."""
+
+    def __init__(self, ops, shard, group=None):
+        self.ops, self.shard, self.group = ops, shard, group
+        self.n = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.state = None
+
+    def _a2a(self, send, out_splits, in_splits, trailing=()):
+        out = send.new_empty((sum(out_splits),) + tuple(trailing))
+        dist.all_to_all_single(out, send, out_splits, in_splits, group=self.group)
+        return out
+
+    def fetch(self, uniq, n_uniq_dev):
+        """uniq: sorted unique global rows (capacity-sized; first U valid).  Returns (rows[U,D], bias[U])
+        in the order of ``uniq``."""
+        ops = self.ops
+        order, send_local, send_counts = ops.route_plan(uniq, n_uniq_dev, self.n)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc = [int(x) for x in send_counts.cpu().tolist()]       # host split sizes (synchronises)
+        rc = [int(x) for x in recv_counts.cpu().tolist()]
+        U = sum(sc)
+        recv_ids = self._a2a(send_local[:U].contiguous(), rc, sc)
+        rows_out = ops.gather_rows(self.shard, recv_ids)
+        bias_out = ops.gather_scalar(self.shard.bias, recv_ids)
+        D = self.shard.D
+        got_rows = self._a2a(rows_out.reshape(-1, D), sc, rc, (D,))
+        got_bias = self._a2a(bias_out, sc, rc)
+        rows = got_rows.new_empty(max(U, 1), D)
+        ops.permute_rows(got_rows, order, U, True, rows)           # rows[order[k]] = got_rows[k]
+        bias = got_bias.new_zeros(max(U, 1))
+        bias[order[:U].long()] = got_bias
+        self.state = (order, sc, rc, recv_ids, U)
+        return rows, bias
+
+    def push(self, dE, db, lr, eps=1e-7):
+        """dE[U,D], db[U] in the order of ``uniq`` -> owners."""
+        order, sc, rc, recv_ids, U = self.state
+        ops = self.ops
+        D = self.shard.D
+        send_g = dE.new_empty(max(U, 1), D)
+        ops.permute_rows(dE, order, U, False, send_g)              # send_g[k] = dE[order[k]]
+        send_gb = db[order[:U].long()]
+        recv_g = self._a2a(send_g[:U], rc, sc, (D,))
+        recv_gb = self._a2a(send_gb.contiguous(), rc, sc)
+        ops.owner_update(self.shard, recv_ids, recv_g, recv_gb, lr, eps)
+
+
+class ShardedGloveTrainer:
+    def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0):
+        L.require_cuda()
+        self.group = group
+        self.n = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.V, self.D, self.B, self.lr = int(V), int(D), int(B_local), float(lr)
+        self.shard = EmbeddingTable(shard_rows(V, self.rank, self.n), D, self.dev, sparse=False, adagrad=True)
+        self.ops = LibesrOps(self.dev)
+        self.xchg = RowExchange(self.ops, self.shard, group)
+        n_slots = 2 * self.B
+        self.plan = IndexPlan(n_slots, V, self.dev)
+        # compact table of fetched rows + the plan re-expressed in unique-row indices
+        self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
+        self.cplan = IndexPlan(n_slots, n_slots, self.dev)
+        self.scratch = torch.empty(n_slots, dtype=torch.int32, device=self.dev)
+        self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
+                                 B_global=self.B * self.n)
+        self.loss = None
+
+    def load_dense(self, E, b):
+        """Scatter a dense (V,D) table / (V,) bias (host or device) into the shards."""
+        idx = torch.arange(self.rank, self.V, self.n)
+        self.shard.rows0.copy_(torch.as_tensor(E)[idx].to(self.dev))
+        self.shard.bias.copy_(torch.as_tensor(b).reshape(-1)[idx].to(self.dev))
+
+    def step(self, ids, counts):
+        """ids: int32 (2, B_local) global rows; counts: f32 (B_local,).  Returns the GLOBAL loss (device scalar)."""
+        ids = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
+        counts = counts.to(self.dev, non_blocking=True)
+        plan, cplan = self.plan, self.cplan
+        plan.build(ids)
+        rows, bias = self.xchg.fetch(plan.uniq, plan.n_uniq)
+        U = rows.shape[0]
+        self.compact.rows0[:U].copy_(rows)
+        self.compact.bias[:U].copy_(bias)
+        L.check(L.lib().esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner),
+                                             L.ptr(cplan.uniq), L.ptr(self.scratch), L.stream_ptr()), "esr_plan_compact_i32")
+        # the compact plan shares perm / useg / seg_off / n_uniq with the original
+        cs = cplan.s
+        cs.n_slots = plan.n_slots
+        cs.perm, cs.useg, cs.seg_off, cs.n_uniq = plan.s.perm, plan.s.useg, plan.s.seg_off, plan.s.n_uniq
+        st = self.step_fn
+        st.prep(cplan, counts)
+        dist.all_reduce(st.scalars[0:3], group=self.group)
+        st.rows(cplan)
+        dist.all_reduce(st.scalars[3:5], group=self.group)
+        st.finish(cplan)
+        self.xchg.push(st.dE, st.db, self.lr)
+        self.loss = st.scalars[L.SC_LOSS].clone()
+        return self.loss
+
+    def gather_dense(self):
+        """All shards -> dense (V,D) table and (V,) bias on every rank (test / checkpoint helper)."""
+        E = torch.zeros(self.V, self.D, device=self.dev)
+        b = torch.zeros(self.V, device=self.dev)
+        idx = torch.arange(self.rank, self.V, self.n, device=self.dev)
+        E[idx] = self.shard.rows0
+        b[idx] = self.shard.bias
+        dist.all_reduce(E, group=self.group)
+        dist.all_reduce(b, group=self.group)
+        return E, b

@@ -189,6 +189,34 @@ int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n
 int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float lr, float momentum,
                        esr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded table (north star; the reference has no distributed code -- SURVEY.md 0, 8(e)).
+ * Ownership is cyclic: owner = row % n_ranks, local row = row / n_ranks (ids are frequency ranks,
+ * wikipedia/make_dictionary.py:113-116).  Integer contract: oracle/index.py route_plan.
+ * The exchanges themselves (NCCL all-to-all) are issued by the caller on the same stream.
+ * ------------------------------------------------------------------------------------------ */
+size_t esr_route_workspace_bytes(int64_t cap);
+/* uniq[0..*n_uniq) sorted unique global rows of this rank's batch (EsrPlan.uniq).  Outputs:
+ * order[k] = index into uniq of the k-th row in owner-bucket order (stable), send_local[k] = its
+ * owner-local row id (payload of the id all-to-all), send_counts[r] = rows owned by rank r. */
+int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks, int32_t* order,
+                       int32_t* send_local, int32_t* send_counts, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* Re-express a plan in unique-row indices (sorted_keys := useg, partner := unique index of the
+ * partner row, uniq := 0..U-1) so a step can run on the compact table of fetched rows without a
+ * second sort.  perm / useg / seg_off / n_uniq of the original plan stay valid.  scratch: [n_slots]. */
+int esr_plan_compact_i32(const EsrPlan* plan, int32_t* sorted_keys, int32_t* partner, int32_t* uniq,
+                         int32_t* scratch, esr_stream_t stream);
+/* out[k] = src[ids[k]]  (bias lookups: jnp.take on the (V,1) bias table, wikipedia/models.py:32,34). */
+int esr_gather_scalar_f32(const float* src, const int32_t* ids, int64_t n, float* out, esr_stream_t stream);
+/* scatter == 0: out[k,:] = src[idx[k],:]; scatter != 0: out[idx[k],:] = src[k,:]; k < min(cap, *n_valid)
+ * (n_valid may be NULL). */
+int esr_permute_rows_f32(const float* src, const int32_t* idx, const int32_t* n_valid, int64_t cap, int32_t D,
+                         int32_t scatter, float* out, esr_stream_t stream);
+/* Owner side: plan built over the received owner-local ids; g_out[u,:] = sum of g_in[slot,:] over the
+ * slots of unique row u in stable sorted order (deterministic); same for the optional bias grads. */
+int esr_segment_sum_rows_f32(const EsrPlan* plan, int32_t D, const float* g_in, const float* gb_in, float* g_out,
+                             float* gb_out, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""World-size-2 gloo test (CPU) of the row-sharded exchange choreography in esrecsys_b200/sharded.py.
+
+The per-rank compute is supplied by NumPy ops that follow oracle/index.py, so what is pinned here is
+the HOST logic: owner bucketing order, count/id/row all-to-alls, split sizes, reassembly in unique
+order, and the gradient return + cross-rank duplicate merge."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Shard:
+    def __init__(self, rows, bias):
+        self.rows0, self.bias = rows, bias
+        self.V, self.D = rows.shape
+        self.acc = torch.full_like(rows, 0.1)
+        self.bias_acc = torch.full_like(bias, 0.1)
+
+
+class NumpyOps:
+    """Same interface as sharded.LibesrOps, on CPU tensors, via oracle.index / oracle.optim."""
+
+    def route_plan(self, uniq, n_uniq, n_ranks):
+        from oracle import index as oidx
+        U = int(n_uniq.item())
+        counts, _, send_local, order = oidx.route_plan(uniq[:U].numpy(), n_ranks)
+        cap = uniq.numel()
+        o = torch.zeros(cap, dtype=torch.int32)
+        s = torch.zeros(cap, dtype=torch.int32)
+        o[:U] = torch.from_numpy(order)
+        s[:U] = torch.from_numpy(send_local)
+        return o, s, torch.from_numpy(counts.astype(np.int32))
+
+    def gather_rows(self, shard, ids):
+        return shard.rows0[ids.long()]
+
+    def gather_scalar(self, src, ids):
+        return src[ids.long()]
+
+    def permute_rows(self, src, idx, n, scatter, out):
+        i = idx[:n].long()
+        if scatter:
+            out[i] = src[:n]
+        else:
+            out[:n] = src[i]
+        return out
+
+    def owner_update(self, shard, recv_ids, recv_g, recv_gb, lr, eps):
+        from oracle import index as oidx
+        from oracle import optim as oopt
+        ids = recv_ids.numpy()
+        sk, perm = oidx.sort_slots(ids)
+        uniq, off = oidx.segments(sk)
+        g = np.add.reduceat(recv_g.numpy()[perm], off[:-1], axis=0) if len(uniq) else np.zeros((0, shard.D), np.float32)
+        gb = np.add.reduceat(recv_gb.numpy()[perm], off[:-1]) if len(uniq) else np.zeros(0, np.float32)
+        E, a = oopt.adagrad_update(shard.rows0.numpy()[uniq], g.astype(np.float32), shard.acc.numpy()[uniq], lr, eps)
+        shard.rows0[uniq] = torch.from_numpy(E)
+        shard.acc[uniq] = torch.from_numpy(a)
+        bb, ab = oopt.adagrad_update(shard.bias.numpy()[uniq], gb.astype(np.float32), shard.bias_acc.numpy()[uniq], lr, eps)
+        shard.bias[uniq] = torch.from_numpy(bb)
+        shard.bias_acc[uniq] = torch.from_numpy(ab)
+
+
+def _worker(rank, world, port, V, D, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from esrecsys_b200.sharded import RowExchange, shard_rows
+        from oracle import optim as oopt
+        rng = np.random.default_rng(0)                       # same table on every rank
+        E = rng.standard_normal((V, D)).astype(np.float32)
+        b = rng.standard_normal(V).astype(np.float32)
+        mine = np.arange(rank, V, world)
+        assert len(mine) == shard_rows(V, rank, world)
+        shard = _Shard(torch.from_numpy(E[mine].copy()), torch.from_numpy(b[mine].copy()))
+        xchg = RowExchange(NumpyOps(), shard)
+        # each rank asks for its own sorted unique rows (overlapping between ranks; rank 1 asks for few)
+        r2 = np.random.default_rng(100 + rank)
+        uniq = np.unique(r2.integers(0, V, size=40 if rank == 0 else 7)).astype(np.int32)
+        U = len(uniq)
+        cap = 64
+        u_t = torch.zeros(cap, dtype=torch.int32)
+        u_t[:U] = torch.from_numpy(uniq)
+        rows, bias = xchg.fetch(u_t, torch.tensor([U], dtype=torch.int32))
+        assert np.array_equal(rows[:U].numpy(), E[uniq]), "fetched rows are not table[uniq]"
+        assert np.array_equal(bias[:U].numpy(), b[uniq])
+        # gradients: g = row id + 1000*rank in every column (so the merge is checkable exactly)
+        dE = torch.zeros(cap, D)
+        db = torch.zeros(cap)
+        dE[:U] = torch.from_numpy((uniq[:, None] * 0.001 + rank).astype(np.float32)).expand(U, D)
+        db[:U] = torch.from_numpy((uniq * 0.01 + rank).astype(np.float32))
+        xchg.push(dE, db, lr=0.05)
+        # expected: every rank's request list is known to everyone (deterministic seeds)
+        gsum = np.zeros((V, D), np.float32)
+        gbsum = np.zeros(V, np.float32)
+        for r in range(world):
+            rr = np.random.default_rng(100 + r)
+            uq = np.unique(rr.integers(0, V, size=40 if r == 0 else 7)).astype(np.int32)
+            gsum[uq] += (uq[:, None] * 0.001 + r).astype(np.float32)
+            gbsum[uq] += (uq * 0.01 + r).astype(np.float32)
+        touched = np.flatnonzero(gbsum != 0) if False else np.unique(np.concatenate(
+            [np.unique(np.random.default_rng(100 + r).integers(0, V, size=40 if r == 0 else 7)) for r in range(world)]))
+        Eexp, bexp = E.copy(), b.copy()
+        Eexp[touched], _ = oopt.adagrad_update(E[touched], gsum[touched], np.full((len(touched), D), 0.1, np.float32), 0.05)
+        bexp[touched], _ = oopt.adagrad_update(b[touched], gbsum[touched], np.full(len(touched), 0.1, np.float32), 0.05)
+        np.testing.assert_allclose(shard.rows0.numpy(), Eexp[mine], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(shard.bias.numpy(), bexp[mine], rtol=1e-6, atol=1e-6)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 101, 8, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
