@@ -197,6 +197,70 @@ def timed_region(tr, batches, steps, warmup, read_loss, world):
     return ms
 
 
+def timed_region_sharded(tr, batches, steps, warmup, pinned_loss, world):
+    """N > 1: ShardedGloveTrainer.step on the current stream (NCCL all-to-alls inside)."""
+    import torch
+    import torch.distributed as dist
+    n = len(batches)
+    for k in range(warmup):
+        tr.step(*batches[k % n])
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        loss = tr.step(*batches[(warmup + k) % n])
+        if pinned_loss is not None:
+            pinned_loss[k % pinned_loss.numel(): k % pinned_loss.numel() + 1].copy_(loss.reshape(1), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    return float(t.item())
+
+
+def run_sharded(a, rank, world, local):
+    """N > 1: the table row-shards cyclically over the ranks (weak scaling: --batch pairs per GPU)."""
+    import torch
+    import torch.distributed as dist
+    from esrecsys_b200 import synth
+    from esrecsys_b200.sharded import ShardedGloveTrainer
+    V, D, B = a.vocab, a.dim, a.batch
+    torch.manual_seed(a.seed)
+    tr = ShardedGloveTrainer(V, D, B, lr=a.lr)
+    tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
+    ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
+    dev_b = [(torch.from_numpy(ids[k]).cuda(), torch.from_numpy(counts[k]).cuda()) for k in range(a.nbatch)]
+    pin_b = [(torch.from_numpy(ids[k]).pin_memory(), torch.from_numpy(counts[k]).pin_memory()) for k in range(a.nbatch)]
+    clocks = ClockSampler(local)
+    clocks.start()
+    clocks.active = True
+    ms = timed_region_sharded(tr, dev_b, a.steps, a.warmup, None, world)
+    pinned_loss = torch.zeros(64).pin_memory()
+    ms_e2e = timed_region_sharded(tr, pin_b, a.steps, max(3, a.warmup // 4), pinned_loss, world)
+    clocks.active = False
+    line = {
+        "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a) + "; table row-sharded (cyclic) over %d GPUs, B per GPU" % world, "vocab": V,
+                   "dim": D, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "sparse adagrad (north star)",
+                   "bias_mode": "reference_broadcast", "stream": "zipf(1)",
+                   "l2": "no flush: per-step working set (fetched rows + shard rows + state) >> 126 MB L2",
+                   "parallelism": "row-sharded table, NCCL all-to-all ids/rows/grads, dp%d over pairs" % world},
+        "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * B,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": a.steps * 40, "final_loss": float(tr.loss.item()),
+        "clocks": clocks.summary(),
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def rows_kernel_time(table, a, ids_dev, cnt_dev, steps):
     """Average CUDA-event duration of the row-pass kernel alone (eager launches, same batches)."""
     import torch
@@ -234,6 +298,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return run_sharded(a, rank, world, local)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

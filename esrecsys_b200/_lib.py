@@ -56,6 +56,8 @@ _SIGNATURES = {
     "esr_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "esr_table_gather_f32": (C.c_int, [C.POINTER(EsrTable), _P, C.c_int64, _P, _P]),
     "esr_table_export_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P]),
+    "esr_rowwise_dot_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "esr_score_all_f32": (C.c_int, [C.POINTER(EsrTable), _P, C.c_int32, _P, _P]),
     "esr_check_ids_i32": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "esr_plan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_plan_build_i32": (C.c_int, [C.POINTER(EsrPlan), _P, C.c_size_t, _P]),
@@ -78,6 +80,9 @@ _SIGNATURES = {
     "esr_dense_adam_f32": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_int64, _P]),
     "esr_dense_sgdm_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, _P]),
+    "esr_stl_triplet_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "esr_spotify_fwd_bwd_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          _P, _P, _P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "esr_route_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_route_plan_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
     "esr_plan_compact_i32": (C.c_int, [C.POINTER(EsrPlan), _P, _P, _P, _P, _P]),

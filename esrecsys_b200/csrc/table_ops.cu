@@ -177,6 +177,52 @@ __global__ void __launch_bounds__(kThreads) k_dense_sgdm(float* __restrict__ p, 
   }
 }
 
+// out[b] = sum_d x[b,d] * y[b,d]   (jax.vmap(jnp.dot) wikipedia/models.py:35-36; sum(a*b,-1) pinterest/models.py:67-72)
+__global__ void __launch_bounds__(kThreads) k_rowwise_dot(const float* __restrict__ x, const float* __restrict__ y,
+                                                          int64_t B, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x * (int64_t)(kThreads / 32) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float acc = 0.f;
+  for (int c = lane; c < D; c += 32) acc = fmaf(x[b * D + c], y[b * D + c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc;
+}
+
+// scores[v, t] = E[v] . Q[t]   (Glove.score_all wikipedia/models.py:40-55; find_top_k
+// pinterest/make_recommendations.py:57).  One warp per table row, queries staged in shared memory;
+// the table is streamed once (HBM-bound: V*R bytes).
+constexpr int kMaxQueries = 64;
+__global__ void __launch_bounds__(kThreads) k_score_all(const float* __restrict__ r0, const float* __restrict__ r1,
+                                                        const uint8_t* __restrict__ ver, int64_t V, int D,
+                                                        const float* __restrict__ Q, int T, float* __restrict__ out) {
+  extern __shared__ float qs[];  // [T][D]
+  for (int i = threadIdx.x; i < T * D; i += kThreads) qs[i] = Q[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int D4 = D / 4;
+  for (int64_t v = blockIdx.x * (int64_t)(kThreads / 32) + (threadIdx.x >> 5); v < V;
+       v += (int64_t)gridDim.x * (kThreads / 32)) {
+    const float4* row = cur_row(r0, r1, ver, v, D4);
+    for (int t0 = 0; t0 < T; t0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int c = lane; c < D4; c += 32) {
+        const float4 x = ld_stream(row + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (t0 + k < T) acc[k] += f4_dot(x, reinterpret_cast<const float4*>(qs + (t0 + k) * D)[c]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0 && t0 + k < T) out[v * T + t0 + k] = s;
+      }
+    }
+  }
+}
+
 int tpr_for(int D4) {
   int t = 1;
   while (t < D4 && t < 32) t <<= 1;
@@ -299,6 +345,33 @@ extern "C" int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_
   ESR_REQUIRE(p && g && trace);
   ESR_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(trace)) % 16) == 0);
   k_dense_sgdm<<<dense_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p, g, trace, n, lr, momentum);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+extern "C" int esr_rowwise_dot_f32(const float* x, const float* y, int64_t B, int32_t D, float* out, esr_stream_t stream_) {
+  ESR_REQUIRE(B >= 0 && D > 0 && (B == 0 || (x && y && out)));
+  if (B == 0) return ESR_OK;
+  k_rowwise_dot<<<(unsigned)ceil_div(B, kThreads / 32), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(x, y, B, D, out);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+extern "C" int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float* scores, esr_stream_t stream_) {
+  ESR_REQUIRE(table_ok(t) && T >= 1 && T <= kMaxQueries && queries && scores);
+  ESR_REQUIRE((reinterpret_cast<uintptr_t>(queries) % 16) == 0);
+  if (t->V == 0) return ESR_OK;
+  const size_t smem = (size_t)T * t->D * sizeof(float);
+  if (smem > 200 * 1024) return ESR_ENOTSUP;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    ESR_CUDA(cudaFuncSetAttribute(k_score_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t want = ceil_div(t->V, kThreads / 32);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  k_score_all<<<(unsigned)(want < cap ? want : cap), kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
+      t->rows[0], t->rows[1], t->ver, t->V, t->D, queries, T, scores);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

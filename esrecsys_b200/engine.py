@@ -52,6 +52,20 @@ class EmbeddingTable:
             t.bias.copy_(torch.as_tensor(bias).to(torch.float32).reshape(-1))
         return t
 
+    @classmethod
+    def wrap(cls, rows, bias=None, acc=None, bias_acc=None):
+        """Zero-copy single-buffer view over existing (V,D) / (V,) CUDA tensors (reference-style params)."""
+        t = cls.__new__(cls)
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.shape[1] % 4 == 0
+        t.device = rows.device
+        t.V, t.D, t.sparse = rows.shape[0], rows.shape[1], False
+        t.rows0, t.rows1, t.ver = rows, None, None
+        t.acc = acc
+        t.bias = bias.reshape(-1) if bias is not None else None
+        t.bias_acc = bias_acc.reshape(-1) if bias_acc is not None else None
+        t._struct = None
+        return t
+
     def struct(self) -> L.EsrTable:
         if self._struct is None:
             s = L.EsrTable()
@@ -242,3 +256,22 @@ def check_ids(ids, V):
     n_bad = torch.zeros(1, dtype=torch.int32, device=ids.device)
     L.check(L.lib().esr_check_ids_i32(L.ptr(ids), ids.numel(), int(V), L.ptr(n_bad), L.stream_ptr()), "esr_check_ids_i32")
     return int(n_bad.item())
+
+
+def rowwise_dot(x, y):
+    """jax.vmap(jnp.dot) over rows (wikipedia/models.py:35-36); sum(a*b, -1) (pinterest/models.py:67-72)."""
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    L.check(L.lib().esr_rowwise_dot_f32(L.ptr(x), L.ptr(y), x.shape[0], x.shape[1], L.ptr(out), L.stream_ptr()),
+            "esr_rowwise_dot_f32")
+    return out
+
+
+def score_all(table: EmbeddingTable, queries):
+    """(V, T) scores of every table row against T query vectors (Glove.score_all)."""
+    queries = queries.contiguous()
+    T = queries.shape[0]
+    out = torch.empty(table.V, T, dtype=torch.float32, device=table.device)
+    L.check(L.lib().esr_score_all_f32(C.byref(table.struct()), L.ptr(queries), T, L.ptr(out), L.stream_ptr()),
+            "esr_score_all_f32")
+    return out

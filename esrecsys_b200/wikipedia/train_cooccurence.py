@@ -1,0 +1,70 @@
+"""Hot-path functions of wikipedia/train_cooccurence.py with the same names and argument meaning:
+``apply_model`` (:71-89), ``update_model`` (:99-101), ``find_knn`` (:91-97), ``train_epoch`` (:103-112).
+
+``apply_model`` returns per-row gradients (``RowGrads``) instead of the dense ``(V,D)`` pytree; the
+reference-exact optimizer (dense ``optax.adam``) is applied by ``update_model`` through
+``TrainState.apply_gradients``.  The fused fast path (sparse Adagrad, no gradient materialised) is
+``esrecsys_b200.trainer.GloveTrainer``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .. import engine
+from ..train_state import RowGrads, TrainState
+from .models import Glove
+
+_cache = {}
+
+
+def _workspace(table, B, bias_mode):
+    key = (table.rows0.data_ptr(), B, bias_mode)
+    if key not in _cache:
+        _cache.clear()
+        _cache[key] = (engine.IndexPlan(2 * B, table.V, table.device),
+                       engine.GloveStep(table, B, bias_mode=bias_mode, emit_grads=True))
+    return _cache[key]
+
+
+def apply_model(state: TrainState, inputs, target, bias_mode="reference_broadcast"):
+    """Computes the gradients and loss for a single batch (train_cooccurence.py:71-89)."""
+    params = state.params
+    E = params["_token_embedding"]["embedding"]
+    table = engine.EmbeddingTable.wrap(E, params["_bias"]["embedding"])
+    ids = torch.as_tensor(np.asarray(inputs) if not torch.is_tensor(inputs) else inputs).to(table.device, torch.int32)
+    ids = ids.reshape(-1).contiguous()
+    B = ids.numel() // 2
+    target = torch.as_tensor(target).to(table.device, torch.float32).contiguous()
+    plan, step = _workspace(table, B, bias_mode)
+    plan.build(ids)
+    sc = step.run(plan, target)
+    loss = sc[L.SC_LOSS].clone()
+    V = table.V
+    grads = {"_token_embedding": {"embedding": RowGrads(V, plan.uniq.clone(), plan.n_uniq.clone(), step.dE.clone())},
+             "_bias": {"embedding": RowGrads(V, plan.uniq.clone(), plan.n_uniq.clone(), step.db.clone().reshape(-1, 1))}}
+    return grads, loss
+
+
+def update_model(state: TrainState, grads):
+    """train_cooccurence.py:99-101."""
+    return state.apply_gradients(grads=grads)
+
+
+def find_knn(model: Glove, params, token):
+    """train_cooccurence.py:91-97: scores (V,T) and the ascending argsort over axis 0."""
+    scores = model.apply({"params": params}, token, method=Glove.score_all)
+    indices = torch.argsort(scores, dim=0, stable=True)
+    return scores, indices
+
+
+def train_epoch(state, steps_per_epoch, train_it):
+    """train_cooccurence.py:103-112."""
+    epoch_loss = []
+    for _ in range(steps_per_epoch):
+        inputs, targets = next(train_it)
+        grads, loss = apply_model(state, inputs, targets)
+        state = update_model(state, grads)
+        epoch_loss.append(loss)
+    return state, float(torch.stack(epoch_loss).mean().item())

@@ -82,6 +82,11 @@ int esr_table_gather_f32(const EsrTable* t, const int32_t* ids, int64_t n, float
                          esr_stream_t stream);
 /* out[V*D] = dense current table (what state.params['..']['embedding'] holds in the reference). */
 int esr_table_export_f32(const EsrTable* t, float* out, esr_stream_t stream);
+/* out[b] = sum_d x[b,d] y[b,d]: jax.vmap(jnp.dot) (wikipedia/models.py:35-36), sum(a*b,-1) (pinterest/models.py:67-72). */
+int esr_rowwise_dot_f32(const float* x, const float* y, int64_t B, int32_t D, float* out, esr_stream_t stream);
+/* scores[v, t] = table[v] . queries[t], (V,T) row-major, T <= 64: Glove.score_all (wikipedia/models.py:40-55),
+ * the product scan of find_top_k (pinterest/make_recommendations.py:57).  Streams the table once. */
+int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float* scores, esr_stream_t stream);
 /* Debug validator: *n_bad (device int32) = number of ids outside [0, V). */
 int esr_check_ids_i32(const int32_t* ids, int64_t n, int64_t V, int32_t* n_bad, esr_stream_t stream);
 
@@ -216,6 +221,27 @@ int esr_permute_rows_f32(const float* src, const int32_t* idx, const int32_t* n_
  * slots of unique row u in stable sorted order (deterministic); same for the optional bias grads. */
 int esr_segment_sum_rows_f32(const EsrPlan* plan, int32_t D, const float* g_in, const float* gb_in, float* g_out,
                              float* gb_out, esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ranking losses of the Spotify and shop-the-look trainers (reference shapes).
+ * ------------------------------------------------------------------------------------------ */
+/* STLModel.__call__ scoring (pinterest/models.py:67-72) + train_step loss and gradient
+ * (pinterest/train_shop_the_look.py:99-107): loss = (sum relu(1 + neg - pos) + reg * sum relu(||e|| - 1))
+ * / batch_size over the three (B,D) embedding matrices.  row_ws: float[B] scratch. */
+int esr_stl_triplet_f32(const float* scene, const float* pos, const float* neg, int64_t B, int32_t D,
+                        float regularization, float batch_size, float* d_scene, float* d_pos, float* d_neg,
+                        float* pos_score, float* neg_score, float* loss, float* row_ws, esr_stream_t stream);
+/* SpotifyModel.__call__ (spotify/models.py:48-91) + train_step loss (spotify/train_spotify.py:91-105)
+ * + jax.value_and_grad (:108-109) for a pack of playlists (one CTA each).  Ids are RAW (album ids are
+ * taken mod VA for the lookup, isin compares raw ids).  Playlist e: nc context rows, next_off[e+1] -
+ * next_off[e] next rows, o negatives; its stacked rows [ctx; next; neg] start at e*(nc+o) + next_off[e]
+ * in dXa / dXr / album_rows / artist_rows / l2.  pos_aff / neg_aff / l2 may be NULL. */
+int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, const float* artist_table, int32_t F,
+                            int32_t n_playlists, int32_t nc, int32_t o, int32_t max_m, const int32_t* album_ctx,
+                            const int32_t* artist_ctx, const int32_t* next_album, const int32_t* next_artist,
+                            const int32_t* next_off, const int32_t* neg_album, const int32_t* neg_artist,
+                            float regularization, float* loss, float* dXa, float* dXr, int32_t* album_rows,
+                            int32_t* artist_rows, float* pos_aff, float* neg_aff, float* l2, esr_stream_t stream);
 
 #ifdef __cplusplus
 }

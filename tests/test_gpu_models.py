@@ -1,0 +1,176 @@
+"""GPU parity of the reference-surface mirrors (Glove / SpotifyModel / STLModel + TrainState) against
+the NumPy oracle.  Tolerance 1e-5 (fp32), as the north star states."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from esrecsys_b200 import synth
+from oracle import glove as og
+from oracle import optim as oopt
+from oracle import spotify as osp
+from oracle import stl as ostl
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# wikipedia: Glove surface, apply_model / update_model with the reference's optimizer (dense Adam)
+# ------------------------------------------------------------------------------------------------
+def _glove_setup(V=2000, D=64, B=512, seed=0):
+    from esrecsys_b200.wikipedia.models import Glove
+    model = Glove(num_embeddings=V, features=D)
+    variables = model.init(seed, None)
+    params = variables["params"]
+    assert set(params) == {"_token_embedding", "_bias"}
+    assert params["_token_embedding"]["embedding"].shape == (V, D)
+    assert params["_bias"]["embedding"].shape == (V, 1)
+    assert float(params["_bias"]["embedding"].abs().sum()) == 0.0
+    params["_bias"]["embedding"].copy_(torch.randn(V, 1, generator=torch.Generator().manual_seed(1)) * 0.05)
+    ids, counts = synth.glove_batches(V, B, 4, seed + 1)
+    return model, params, ids, counts
+
+
+def test_glove_forward_and_score_all():
+    model, params, ids, counts = _glove_setup()
+    E, b = _np(params["_token_embedding"]["embedding"]), _np(params["_bias"]["embedding"]).reshape(-1)
+    out = model.apply({"params": params}, ids[0])
+    assert out.shape == (512, 512)                                   # the reference's (B,B) broadcast
+    np.testing.assert_allclose(_np(out), og.forward_literal(E, b, ids[0, 0], ids[0, 1]), rtol=RTOL, atol=ATOL)
+    from esrecsys_b200.wikipedia.models import Glove
+    tok = np.array([3, 17, 256, 1999, 3], np.int32)
+    sc = model.apply({"params": params}, tok, method=Glove.score_all)
+    assert sc.shape == (2000, 5)
+    np.testing.assert_allclose(_np(sc), og.score_all(E, tok), rtol=RTOL, atol=ATOL)
+    from esrecsys_b200.wikipedia.train_cooccurence import find_knn
+    scores, idx = find_knn(model, params, tok)
+    _, oidx = og.find_knn(_np(scores), np.arange(5)) if False else (None, np.argsort(_np(scores), axis=0, kind="stable"))
+    assert np.array_equal(_np(idx), oidx)
+
+
+@pytest.mark.parametrize("opt", ["adam", "sgd", "adagrad"])
+@pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
+def test_apply_model_update_model(opt, bias_mode):
+    from esrecsys_b200 import optim as O
+    from esrecsys_b200.train_state import TrainState
+    from esrecsys_b200.wikipedia.train_cooccurence import apply_model, update_model
+    model, params, ids, counts = _glove_setup()
+    E = _np(params["_token_embedding"]["embedding"]).copy()
+    b = _np(params["_bias"]["embedding"]).reshape(-1).copy()
+    tx = {"adam": O.adam(1e-3), "sgd": O.sgd(1e-2, momentum=0.9), "adagrad": O.adagrad(0.05)}[opt]
+    state = TrainState.create(apply_fn=model.apply, params=params, tx=tx)
+    st = dict(count=0, muE=np.zeros_like(E), nuE=np.zeros_like(E), mub=np.zeros_like(b), nub=np.zeros_like(b),
+              trE=np.zeros_like(E), trb=np.zeros_like(b))
+    aE, ab = np.full_like(E, 0.1), np.full_like(b, 0.1)
+    for k in range(3):
+        grads, loss = apply_model(state, ids[k], counts[k], bias_mode)
+        gr = og.loss_and_grads(E, b, ids[k, 0], ids[k, 1], counts[k], bias_mode)
+        dE, db = og.dense_grads(E.shape[0], gr, E.shape[1])
+        np.testing.assert_allclose(_np(grads["_token_embedding"]["embedding"].dense()), dE, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(_np(grads["_bias"]["embedding"].dense()).reshape(-1), db, rtol=RTOL, atol=ATOL)
+        state = update_model(state, grads)
+        if opt == "adam":
+            oloss = og.step_adam(E, b, st, ids[k, 0], ids[k, 1], counts[k], 1e-3, bias_mode)
+        elif opt == "sgd":
+            oloss = og.step_sgdm(E, b, st, ids[k, 0], ids[k, 1], counts[k], 1e-2, 0.9, bias_mode)
+        else:
+            oloss = og.step_adagrad(E, b, aE, ab, ids[k, 0], ids[k, 1], counts[k], 0.05, bias_mode)
+        np.testing.assert_allclose(float(loss), oloss, rtol=2e-5, atol=ATOL)
+    assert state.step == 3
+    np.testing.assert_allclose(_np(state.params["_token_embedding"]["embedding"]), E, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(_np(state.params["_bias"]["embedding"]).reshape(-1), b, rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# pinterest: scoring + triplet loss
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D", [(16, 64), (16, 32), (4096, 256), (1, 8), (33, 100)])
+def test_stl_triplet_matches_oracle(B, D):
+    from esrecsys_b200.pinterest.models import triplet_loss_and_grads
+    rng = np.random.default_rng(B + D)
+    s, p, n = (rng.standard_normal((B, D)).astype(np.float32) * sc for sc in (0.2, 0.2, 0.2))
+    s[: B // 2] *= 8.0          # some norms above 1 so the regulariser is active
+    p[B // 3:] *= 6.0
+    loss, ds, dp, dn, ps, ns = triplet_loss_and_grads(*(torch.from_numpy(x).cuda() for x in (s, p, n)), 0.1, 16)
+    ol, ods, odp, odn = ostl.triplet_loss_and_grads(s, p, n, 0.1, 16)
+    np.testing.assert_allclose(float(loss), ol, rtol=2e-5, atol=ATOL)
+    for got, want in ((ds, ods), (dp, odp), (dn, odn)):
+        np.testing.assert_allclose(_np(got), want, rtol=RTOL, atol=ATOL)
+    ops, ons = ostl.scores(s, p, n)
+    np.testing.assert_allclose(_np(ps), ops, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(_np(ns), ons, rtol=RTOL, atol=ATOL)
+
+
+def test_stlmodel_surface():
+    from esrecsys_b200.pinterest.models import STLModel
+    m = STLModel(output_size=64, num_scenes=500, num_products=700)
+    v = m.init(0)
+    ids = np.random.default_rng(0).integers(0, 500, size=(3, 16))
+    out = m.apply(v, ids[0], ids[1], ids[2], True)
+    assert len(out) == 5 and out[0].shape == (16,) and out[2].shape == (16, 64)
+    S = _np(v["params"]["scene_cnn"]["embedding"])
+    P = _np(v["params"]["product_cnn"]["embedding"])
+    np.testing.assert_allclose(_np(out[0]), np.sum(S[ids[0]] * P[ids[1]], -1), rtol=RTOL, atol=ATOL)
+    assert np.array_equal(_np(m.apply(v, ids[0], method=STLModel.get_scene_embed)), S[ids[0]])
+
+
+# ------------------------------------------------------------------------------------------------
+# spotify: fused forward/backward of train_step's loss, reference optimizer (dense SGD momentum)
+# ------------------------------------------------------------------------------------------------
+def _spotify_setup(F=32, VA=1000, VR=3000, seed=0):
+    from esrecsys_b200.spotify.models import SpotifyModel
+    model = SpotifyModel(feature_size=F, max_albums=VA, num_artists=VR)
+    v = model.init(seed)
+    assert set(v["params"]) == {"album_embed", "artist_embed"}
+    return model, v["params"]
+
+
+@pytest.mark.parametrize("m", [5, 7, 33, 120])
+def test_spotify_forward_and_grads(m):
+    model, params = _spotify_setup()
+    A, R = _np(params["album_embed"]["embedding"]), _np(params["artist_embed"]["embedding"])
+    rng = np.random.default_rng(m)
+    x = synth.spotify_example(rng, m, o=64, n_albums=5000, n_artists=3000)
+    # scale some rows up so the norm regulariser (reg = 1.0 here) and the self-affinity hinges are active
+    out = model.apply({"params": params}, x["track_context"], x["album_context"], x["artist_context"], x["next_track"],
+                      x["next_album"], x["next_artist"], x["neg_track"], x["neg_album"], x["neg_artist"])
+    want = osp.forward(A, R, x["album_context"], x["artist_context"], x["next_album"], x["next_artist"],
+                       x["neg_album"], x["neg_artist"])
+    for got, w in zip(out, want):
+        np.testing.assert_allclose(_np(got), w, rtol=RTOL, atol=ATOL)
+    for reg in (10.0, 0.5):
+        loss, grads = model.loss_and_grads(params, [x], regularization=reg)
+        gr = osp.loss_and_grads(A, R, x["album_context"], x["artist_context"], x["next_album"], x["next_artist"],
+                                x["neg_album"], x["neg_artist"], reg)
+        np.testing.assert_allclose(float(loss[0]), gr.loss, rtol=2e-5, atol=ATOL)
+        dA, dR = osp.dense_grads(A, R, gr)
+        np.testing.assert_allclose(_np(grads["album_embed"]["embedding"].dense()), dA, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(_np(grads["artist_embed"]["embedding"].dense()), dR, rtol=RTOL, atol=ATOL)
+
+
+def test_spotify_pack_equals_singles_and_train_step():
+    from esrecsys_b200 import optim as O
+    from esrecsys_b200.train_state import TrainState
+    model, params = _spotify_setup()
+    rng = np.random.default_rng(9)
+    xs = [synth.spotify_example(rng, m, o=64, n_albums=5000, n_artists=3000) for m in (5, 12, 40)]
+    loss_pack, _ = model.loss_and_grads(params, xs, 10.0)
+    for e, x in enumerate(xs):
+        l1, _ = model.loss_and_grads(params, [x], 10.0)
+        assert float(l1[0]) == float(loss_pack[e])                 # bit-identical: one CTA per playlist
+    # train_step with optax.sgd(lr, momentum) (spotify/train_spotify.py:238-241), dense
+    A, R = _np(params["album_embed"]["embedding"]).copy(), _np(params["artist_embed"]["embedding"]).copy()
+    trA, trR = np.zeros_like(A), np.zeros_like(R)
+    state = TrainState.create(apply_fn=model.apply, params=params, tx=O.sgd(1e-3, momentum=0.98))
+    for x in xs:
+        loss, grads = model.loss_and_grads(state.params, [x], 10.0)
+        state = state.apply_gradients(grads=grads)
+        ol = osp.train_step(A, R, trA, trR, x, 10.0, 1e-3, 0.98)
+        np.testing.assert_allclose(float(loss[0]), ol, rtol=2e-5, atol=ATOL)
+    np.testing.assert_allclose(_np(state.params["album_embed"]["embedding"]), A, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(_np(state.params["artist_embed"]["embedding"]), R, rtol=RTOL, atol=ATOL)
