@@ -169,7 +169,7 @@ class GloveStep:
     phases over an IndexPlan (include/esr.h: esr_glove_prep/rows/finish)."""
 
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", eps=1e-7,
-                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto"):
+                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto", dE=None, db=None):
         self.table = table
         self.B = int(B)
         dev = table.device
@@ -188,8 +188,9 @@ class GloveStep:
         self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
         self.scalars = torch.zeros(L.GLOVE_NSCAL, dtype=torch.float32, device=dev)
         n = max(2 * self.B, 1)
-        self.dE = torch.empty(n, table.D, dtype=torch.float32, device=dev) if emit_grads else None
-        self.db = torch.empty(n, dtype=torch.float32, device=dev) if emit_grads else None
+        # EMIT outputs; the caller may supply them (e.g. symmetric memory the owners read over NVLink)
+        self.dE = (dE if dE is not None else torch.empty(n, table.D, dtype=torch.float32, device=dev)) if emit_grads else None
+        self.db = (db if db is not None else torch.empty(n, dtype=torch.float32, device=dev)) if emit_grads else None
 
     def _args(self, plan):
         return C.byref(self.table.struct()), C.byref(plan.s), C.byref(self.cfg)

@@ -42,12 +42,15 @@ class LibesrOps:
         self._route_ws = None
         self._plans = {}
 
-    def route_plan(self, uniq, n_uniq, n_ranks):
+    def route_plan(self, uniq, n_uniq, n_ranks, out=None):
         cap = uniq.numel()
         i32 = dict(dtype=torch.int32, device=self.dev)
-        order = torch.empty(cap, **i32)
-        send_local = torch.empty(cap, **i32)
-        send_counts = torch.zeros(n_ranks, **i32)
+        if out is not None:
+            order, send_local, send_counts = out
+        else:
+            order = torch.empty(cap, **i32)
+            send_local = torch.empty(cap, **i32)
+            send_counts = torch.zeros(n_ranks, **i32)
         need = int(L.lib().esr_route_workspace_bytes(cap))
         if self._route_ws is None or self._route_ws.numel() < need:
             self._route_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
@@ -199,6 +202,116 @@ class ShardedGloveTrainer:
 
     def gather_dense(self):
         """All shards -> dense (V,D) table and (V,) bias on every rank (test / checkpoint helper)."""
+        E = torch.zeros(self.V, self.D, device=self.dev)
+        b = torch.zeros(self.V, device=self.dev)
+        idx = torch.arange(self.rank, self.V, self.n, device=self.dev)
+        E[idx] = self.shard.rows0
+        b[idx] = self.shard.bias
+        dist.all_reduce(E, group=self.group)
+        dist.all_reduce(b, group=self.group)
+        return E, b
+
+
+class PeerShardedGloveTrainer:
+    """Same step as ShardedGloveTrainer, but the exchanges are libesr kernels over NVLink peer memory
+    (csrc/peer_ops.cu) on buffers from torch's symmetric-memory rendezvous: no NCCL all-to-all, no id
+    exchange, no host-known sizes, no host synchronisation inside the step.
+
+      plan -> route plan (published) -> peer gather of the unique rows -> compact plan -> prep
+      -> all-reduce(3 floats) -> row pass (EMIT into symmetric memory) -> all-reduce(2) -> finish
+      -> barrier -> owners pull ids, merge gradients over peers, Adagrad -> barrier
+    """
+
+    def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0):
+        import torch.distributed._symmetric_memory as symm_mem
+        L.require_cuda()
+        self.group = group if group is not None else dist.group.WORLD
+        self.n = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.n > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch domain; ESR_MAX_PEERS)")
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.V, self.D, self.B, self.lr = int(V), int(D), int(B_local), float(lr)
+        n_slots = 2 * self.B
+        gname = self.group.group_name
+        self._hdls = []
+
+        def symm(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=self.dev)
+            h = symm_mem.rendezvous(t, gname)
+            self._hdls.append(h)
+            ptrs = (C.c_void_p * 8)(*[int(p) for p in h.buffer_ptrs])
+            return t, ptrs
+
+        V_loc = shard_rows(V, self.rank, self.n)
+        V_max = shard_rows(V, 0, self.n)
+        rows, self.p_rows = symm((V_max, D), torch.float32)
+        bias, self.p_bias = symm((V_max,), torch.float32)
+        rows.zero_()
+        bias.zero_()
+        self.shard = EmbeddingTable.wrap(rows[:V_loc], bias=bias[:V_loc],
+                                         acc=torch.full((V_loc, D), 0.1, device=self.dev),
+                                         bias_acc=torch.full((V_loc,), 0.1, device=self.dev))
+        self.send_counts, self.p_counts = symm((16,), torch.int32)
+        self.send_local, self.p_send_local = symm((n_slots,), torch.int32)
+        self.order, self.p_order = symm((n_slots,), torch.int32)
+        self.dE, self.p_dE = symm((n_slots, D), torch.float32)
+        self.db, self.p_db = symm((n_slots,), torch.float32)
+        self.ops = LibesrOps(self.dev)
+        self.plan = IndexPlan(n_slots, V, self.dev)
+        self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
+        self.cplan = IndexPlan(n_slots, n_slots, self.dev)
+        self.scratch = torch.empty(n_slots, dtype=torch.int32, device=self.dev)
+        self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
+                                 B_global=self.B * self.n, dE=self.dE, db=self.db)
+        self.recv_cap = self.n * n_slots
+        self.recv_ids = torch.empty(self.recv_cap, dtype=torch.int32, device=self.dev)
+        self.src_meta = torch.zeros(3 * 8 + 4, dtype=torch.int32, device=self.dev)
+        self.loss = None
+        self.barrier()
+
+    def barrier(self):
+        self._hdls[0].barrier()
+
+    def load_dense(self, E, b):
+        idx = torch.arange(self.rank, self.V, self.n)
+        self.shard.rows0.copy_(torch.as_tensor(E)[idx].to(self.dev))
+        self.shard.bias.copy_(torch.as_tensor(b).reshape(-1)[idx].to(self.dev))
+        torch.cuda.current_stream().synchronize()
+        self.barrier()
+
+    def step(self, ids, counts):
+        lib = L.lib()
+        sp = L.stream_ptr()
+        ids = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
+        counts = counts.to(self.dev, non_blocking=True)
+        plan, cplan, n = self.plan, self.cplan, self.n
+        plan.build(ids)
+        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(self.order, self.send_local, self.send_counts))
+        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
+                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
+        L.check(lib.esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner), L.ptr(cplan.uniq),
+                                         L.ptr(self.scratch), sp), "esr_plan_compact_i32")
+        cs = cplan.s
+        cs.n_slots = plan.n_slots
+        cs.perm, cs.useg, cs.seg_off, cs.n_uniq = plan.s.perm, plan.s.useg, plan.s.seg_off, plan.s.n_uniq
+        st = self.step_fn
+        st.prep(cplan, counts)
+        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: every rank has finished its fetch
+        st.rows(cplan)
+        dist.all_reduce(st.scalars[3:5], group=self.group)
+        st.finish(cplan)
+        self.barrier()                                          # every rank's dE / db / route plan is published
+        L.check(lib.esr_peer_pull_ids_i32(self.p_counts, self.p_send_local, n, self.rank, self.recv_cap,
+                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), sp), "esr_peer_pull_ids_i32")
+        L.check(lib.esr_peer_merge_adagrad_f32(C.byref(self.shard.struct()), self.p_order, self.p_dE, self.p_db, n,
+                                               L.ptr(self.recv_ids), L.ptr(self.src_meta), self.lr, 1e-7, sp),
+                "esr_peer_merge_adagrad_f32")
+        self.barrier()                                          # every owner has applied its updates
+        self.loss = st.scalars[L.SC_LOSS].clone()
+        return self.loss
+
+    def gather_dense(self):
         E = torch.zeros(self.V, self.D, device=self.dev)
         b = torch.zeros(self.V, device=self.dev)
         idx = torch.arange(self.rank, self.V, self.n, device=self.dev)

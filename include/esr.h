@@ -243,6 +243,28 @@ int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, const float* a
                             float regularization, float* loss, float* dXa, float* dXr, int32_t* album_rows,
                             int32_t* artist_rows, float* pos_aff, float* neg_aff, float* l2, esr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded table over NVLink peer memory (device pointers of every rank's buffers, e.g. from a
+ * symmetric-memory rendezvous; index = rank).  No host-known sizes, no NCCL on the data path; the
+ * caller separates fetch / update phases with device barriers.  See csrc/peer_ops.cu.
+ * ------------------------------------------------------------------------------------------ */
+#define ESR_MAX_PEERS 8
+/* out[u,:] = shard_{uniq[u] % n}[uniq[u] / n, :], out_bias[u] likewise, u < *n_uniq: the lookup of
+ * SURVEY.md 8(e) (index all-to-all + row all-to-all) as one gather over peer pointers. */
+int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks,
+                        const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t D, float* out,
+                        float* out_bias, esr_stream_t stream);
+/* Owner `me`: from every source rank's published esr_route_plan_i32 outputs (send_counts[n],
+ * send_local[]) copy the owner-local ids destined to me into recv_ids (source-major), and write
+ * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[n] = total. */
+int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* peer_send_local, int32_t n_ranks,
+                          int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, esr_stream_t stream);
+/* Owner side: merge the gradients all sources hold for my rows (dE_s[order_s[.]], db_s[...]; summed in
+ * source order, deterministic) and apply optax.adagrad to the shard in place. */
+int esr_peer_merge_adagrad_f32(EsrTable* shard, const void* const* peer_order, const void* const* peer_dE,
+                               const void* const* peer_db, int32_t n_ranks, const int32_t* recv_ids,
+                               const int32_t* src_meta, float lr, float eps, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q):
+def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -24,13 +24,13 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from esrecsys_b200 import synth
-        from esrecsys_b200.sharded import ShardedGloveTrainer
+        from esrecsys_b200.sharded import PeerShardedGloveTrainer, ShardedGloveTrainer
         from oracle import glove as og
         from oracle import optim as oopt
         E, b = synth.init_glove_tables(V, D, 0)
         b = (np.random.default_rng(5).standard_normal(V) * 0.05).astype(np.float32)
         ids, counts = synth.glove_batches(V, B_loc * world, steps, 1)     # global batches
-        tr = ShardedGloveTrainer(V, D, B_loc, lr=0.05, bias_mode=bias_mode)
+        tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode)
         tr.load_dense(E, b)
         Eo, bo = E.copy(), b.copy()
         aE, ab = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC), np.full_like(bo, oopt.ADAGRAD_INIT_ACC)
@@ -51,14 +51,15 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl_a2a", "peer_memory"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B_loc", [(5000, 64, 1024), (300, 128, 512)])
-def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode):
+def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode, peer):
     world = max(1, min(4, torch.cuda.device_count()))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200) + (V % 7)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, V, D, B_loc, 3, bias_mode, q)) for r in range(world)]
+    port = 29700 + (os.getpid() % 200) + (V % 7) + (50 if peer else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, V, D, B_loc, 3, bias_mode, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=500) for _ in procs]
