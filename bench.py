@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-uniform", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: row exchange over NVLink peer memory (libesr kernels) or NCCL all-to-all")
     return ap.parse_args()
 
 
@@ -226,10 +228,10 @@ def run_sharded(a, rank, world, local):
     import torch
     import torch.distributed as dist
     from esrecsys_b200 import synth
-    from esrecsys_b200.sharded import ShardedGloveTrainer
+    from esrecsys_b200.sharded import PeerShardedGloveTrainer, ShardedGloveTrainer
     V, D, B = a.vocab, a.dim, a.batch
     torch.manual_seed(a.seed)
-    tr = ShardedGloveTrainer(V, D, B, lr=a.lr)
+    tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr)
     tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
     ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
     dev_b = [(torch.from_numpy(ids[k]).cuda(), torch.from_numpy(counts[k]).cuda()) for k in range(a.nbatch)]
@@ -237,6 +239,7 @@ def run_sharded(a, rank, world, local):
     clocks = ClockSampler(local)
     clocks.start()
     clocks.active = True
+    dev_b = [(x[0].reshape(-1), x[1]) for x in dev_b]
     ms = timed_region_sharded(tr, dev_b, a.steps, a.warmup, None, world)
     pinned_loss = torch.zeros(64).pin_memory()
     ms_e2e = timed_region_sharded(tr, pin_b, a.steps, max(3, a.warmup // 4), pinned_loss, world)
@@ -249,7 +252,9 @@ def run_sharded(a, rank, world, local):
                    "dim": D, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "sparse adagrad (north star)",
                    "bias_mode": "reference_broadcast", "stream": "zipf(1)",
                    "l2": "no flush: per-step working set (fetched rows + shard rows + state) >> 126 MB L2",
-                   "parallelism": "row-sharded table, NCCL all-to-all ids/rows/grads, dp%d over pairs" % world},
+                   "parallelism": ("row-sharded table (cyclic), dp%d over pairs; " % world) + (
+                       "rows fetched and gradients merged by libesr kernels over NVLink peer memory, NCCL only for the "
+                       "5-float all-reduce" if a.exchange == "peer" else "NCCL all-to-all of ids / rows / gradients")},
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": a.steps * 40, "final_loss": float(tr.loss.item()),

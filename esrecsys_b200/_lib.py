@@ -44,7 +44,9 @@ class EsrGloveCfg(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("bias_mode", C.c_int32), ("rows_mode", C.c_int32),
                 ("impl", C.c_int32), ("B", C.c_int64), ("B_global", C.c_int64),
                 ("lr", C.c_float), ("eps", C.c_float), ("x_max", C.c_float), ("alpha", C.c_float),
-                ("chunk", C.c_int32), ("reserved", C.c_int32)]
+                ("chunk", C.c_int32), ("reserved", C.c_int32), ("emit_map", C.c_void_p),
+                ("emit_peers_dE", C.c_void_p), ("emit_peers_db", C.c_void_p), ("n_emit_peers", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -84,10 +86,12 @@ _SIGNATURES = {
     "esr_spotify_fwd_bwd_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           _P, _P, _P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "esr_peer_gather_f32": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
-    "esr_peer_pull_ids_i32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
-    "esr_peer_merge_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, _P, C.c_int32, _P, _P, C.c_float, C.c_float, _P]),
+    "esr_peer_emit_plan_i32": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, C.c_int64, _P, _P, _P]),
+    "esr_peer_pull_ids_i32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "esr_peer_merge_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_float,
+                                             C.c_float, _P]),
     "esr_route_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "esr_route_plan_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "esr_route_plan_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "esr_plan_compact_i32": (C.c_int, [C.POINTER(EsrPlan), _P, _P, _P, _P, _P]),
     "esr_gather_scalar_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "esr_permute_rows_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),

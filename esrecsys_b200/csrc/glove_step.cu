@@ -232,6 +232,15 @@ __device__ __forceinline__ void row_add(Row<NK>& acc, const Row<NK>& x) {
   for (int k = 0; k < NK; ++k) f4_add(acc.v[k], x.v[k]);
 }
 
+// EMIT destinations: with emit_peers the code emit_map[u] = owner << kEmitShift | index selects one of
+// up to ESR_MAX_PEERS base pointers (the owners' gradient inboxes, written over NVLink).
+constexpr int kEmitShift = 27;
+struct EmitPeers {
+  float* dE[ESR_MAX_PEERS];
+  float* db[ESR_MAX_PEERS];
+  int32_t on;
+};
+
 struct RowsArgs {
   const float* rows[2];
   float* wrows[2];
@@ -249,6 +258,8 @@ struct RowsArgs {
   int32_t* wl_light;  // head chunks of straddling segments with <= kHeavyParts partials
   int32_t* wl_heavy;
   float* dE;
+  const int32_t* emit_map;  // EMIT: gradient of unique row u goes to dE[emit_map[u]] (NULL: dE[u])
+  EmitPeers peers;
   int64_t n;
   int64_t nchunks;
   int32_t D4;
@@ -267,7 +278,13 @@ template <int NK>
 __device__ __forceinline__ void close_segment(const RowsArgs& a, int32_t key, int64_t u, const Row<NK>& self,
                                               const Row<NK>& accrow, const Row<NK>& grad, float bacc, int lane) {
   if (a.emit) {
-    row_store<NK, true>(grad, reinterpret_cast<float4*>(a.dE) + u * a.D4, lane, a.D4);
+    int64_t e = a.emit_map ? a.emit_map[u] : u;
+    float* base = a.dE;
+    if (a.peers.on) {
+      base = a.peers.dE[e >> kEmitShift];
+      e &= (1 << kEmitShift) - 1;
+    }
+    row_store<NK, true>(grad, reinterpret_cast<float4*>(base) + e * a.D4, lane, a.D4);
   } else {
     const int64_t row = key & kRowMask;
     const int v = (key >> 31) & 1;
@@ -551,7 +568,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
       bacc += a.per_pair ? g : rec.bs;
       if (is_end && started_here) {
         if (a.emit) {
-          grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.dE) + (uint64_t)u * D4, gl, a.D4, true);
+          uint64_t e = a.emit_map ? (uint64_t)a.emit_map[u] : (uint64_t)u;
+          float* base = a.dE;
+          if (a.peers.on) {
+            base = a.peers.dE[e >> kEmitShift];
+            e &= (1u << kEmitShift) - 1u;
+          }
+          grow_store<G, NV>(grad, reinterpret_cast<float4*>(base) + e * D4, gl, a.D4, true);
         } else {
           const uint32_t row = (uint32_t)(key_cur & kRowMask);
           const int v = (key_cur >> 31) & 1;
@@ -841,6 +864,8 @@ struct FinishArgs {
   float* bias_acc;
   uint8_t* ver;
   float* db;
+  const int32_t* emit_map;
+  EmitPeers peers;
   int32_t per_pair;
   int32_t emit;
   float B;  // B_global
@@ -855,7 +880,13 @@ __global__ void __launch_bounds__(kThreads) k_glove_finish(const FinishArgs a) {
     // App. A.1: db[v] = sum_slots -(2/B^2) (S1 - bs_r S0) = -(2/B^2) (n_v S1 - S0 sum bs_r); A.2: sum g
     const float gb = a.per_pair ? a.bsum[u] : (-2.f / (a.B * a.B)) * (nslots * S1 - S0 * a.bsum[u]);
     if (a.emit) {
-      a.db[u] = gb;
+      int64_t e = a.emit_map ? a.emit_map[u] : u;
+      float* base = a.db;
+      if (a.peers.on) {
+        base = a.peers.db[e >> kEmitShift];
+        e &= (1 << kEmitShift) - 1;
+      }
+      base[e] = gb;
     } else {
       const int64_t row = a.uniq[u];
       float p = a.bias[row], ac = a.bias_acc[row];
@@ -899,6 +930,19 @@ bool cfg_ok(const EsrGloveCfg* cfg, const EsrPlan* plan) {
   return true;
 }
 
+
+void load_emit_peers(const EsrGloveCfg* cfg, EmitPeers* p) {
+  p->on = 0;
+  for (int i = 0; i < ESR_MAX_PEERS; ++i) p->dE[i] = p->db[i] = nullptr;
+  if (cfg->emit_map && cfg->emit_peers_dE && cfg->emit_peers_db && cfg->n_emit_peers > 0) {
+    p->on = 1;
+    for (int i = 0; i < cfg->n_emit_peers && i < ESR_MAX_PEERS; ++i) {
+      p->dE[i] = static_cast<float*>(cfg->emit_peers_dE[i]);
+      p->db[i] = static_cast<float*>(cfg->emit_peers_db[i]);
+    }
+  }
+}
+
 RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, const GloveWs& w,
                         const float* scalars, float* dE) {
   RowsArgs a;
@@ -921,6 +965,8 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.parts = w.parts;
   a.rows_blk = w.rows_blk;
   a.dE = dE;
+  a.emit_map = cfg->emit_map;
+  load_emit_peers(cfg, &a.peers);
   a.n = plan->n_slots;
   a.D4 = t->D / 4;
   a.chunk = w.chunk;
@@ -1009,7 +1055,7 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
   if (cfg->B == 0) return ESR_OK;
   const bool emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
   ESR_REQUIRE(ws && plan->useg && plan->seg_off);
-  ESR_REQUIRE(!emit || (dE != nullptr && (reinterpret_cast<uintptr_t>(dE) % 16) == 0));
+  ESR_REQUIRE(!emit || cfg->emit_peers_dE != nullptr || (dE != nullptr && (reinterpret_cast<uintptr_t>(dE) % 16) == 0));
   if (cfg->impl != ESR_IMPL_AUTO && cfg->impl != ESR_IMPL_LDG && cfg->impl != ESR_IMPL_TMA) return ESR_EINVAL;
   const bool tma = cfg->impl == ESR_IMPL_TMA;
   if (ws_bytes < esr_glove_workspace_bytes(cfg->B, t->D, cfg->chunk)) return ESR_EWORKSPACE;
@@ -1057,7 +1103,7 @@ extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrG
   ESR_REQUIRE(cfg_ok(cfg, plan) && glove_table_ok(t, cfg->rows_mode == ESR_ROWS_UPDATE) && scalars != nullptr);
   const bool emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
   if (cfg->B == 0) return ESR_OK;
-  ESR_REQUIRE(ws && plan->uniq && plan->seg_off && plan->n_uniq && (!emit || db != nullptr));
+  ESR_REQUIRE(ws && plan->uniq && plan->seg_off && plan->n_uniq && (!emit || db != nullptr || cfg->emit_peers_db != nullptr));
   if (ws_bytes < esr_glove_workspace_bytes(cfg->B, t->D, cfg->chunk)) return ESR_EWORKSPACE;
   GloveWs w;
   carve_ws(ws, cfg->B, t->D, cfg->chunk, &w);
@@ -1071,6 +1117,8 @@ extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrG
   a.bias_acc = t->bias_acc;
   a.ver = t->ver;
   a.db = db;
+  a.emit_map = cfg->emit_map;
+  load_emit_peers(cfg, &a.peers);
   a.per_pair = cfg->bias_mode == ESR_BIAS_PER_PAIR;
   a.emit = emit;
   a.B = (float)cfg->B_global;

@@ -27,42 +27,54 @@ struct PeerPtrs {
   const void* p[ESR_MAX_PEERS];
 };
 
+// owner / local row of a global row id under cyclic sharding; shift/mask when n is a power of two
+struct Cyclic {
+  int n, shift;  // shift >= 0: n == 1 << shift
+  __device__ __forceinline__ int owner(int32_t row) const { return shift >= 0 ? (row & (n - 1)) : row % n; }
+  __device__ __forceinline__ int64_t local(int32_t row) const { return shift >= 0 ? (row >> shift) : row / n; }
+};
+
+// Persistent grid: groups of TPR lanes stride over quads of unique rows (sizes are only known on the
+// device, so a capacity-sized grid would launch mostly empty blocks).
 template <int TPR, int ROWS>
 __global__ void __launch_bounds__(kThreads) k_peer_gather(PeerPtrs rows, PeerPtrs bias, const int32_t* __restrict__ uniq,
-                                                          const int32_t* __restrict__ n_uniq, int64_t cap, int n_ranks,
+                                                          const int32_t* __restrict__ n_uniq, int64_t cap, Cyclic cyc,
                                                           int D4, float4* __restrict__ out, float* __restrict__ out_bias) {
   const int lane = threadIdx.x % TPR;
-  const int64_t group = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
   const int64_t n = min((int64_t)*n_uniq, cap);
-  const int64_t first = group * ROWS;
-  const float4* src[ROWS];
+  const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
+  for (int64_t first = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR) * ROWS; first < n; first += groups * ROWS) {
+    const float4* src[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const int64_t u = first + r;
-    src[r] = nullptr;
-    if (u < n) {
-      const int32_t row = uniq[u];
-      const int owner = row % n_ranks;
-      const int64_t local = row / n_ranks;
-      src[r] = reinterpret_cast<const float4*>(rows.p[owner]) + local * D4;
-      if (lane == 0) out_bias[u] = reinterpret_cast<const float*>(bias.p[owner])[local];
+    for (int r = 0; r < ROWS; ++r) {
+      const int64_t u = first + r;
+      src[r] = nullptr;
+      if (u < n) {
+        const int32_t row = uniq[u];
+        const int owner = cyc.owner(row);
+        const int64_t local = cyc.local(row);
+        src[r] = reinterpret_cast<const float4*>(rows.p[owner]) + local * D4;
+        if (lane == 0) out_bias[u] = reinterpret_cast<const float*>(bias.p[owner])[local];
+      }
     }
-  }
-  for (int c = lane; c < D4; c += TPR) {
-    float4 v[ROWS];
+    for (int c = lane; c < D4; c += TPR) {
+      float4 v[ROWS];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-      if (src[r]) v[r] = src[r][c];  // plain ld.global: peer addresses bypass L2, nothing to hint
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) v[r] = src[r][c];  // plain ld.global: peer addresses bypass L2, nothing to hint
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-      if (src[r]) out[(first + r) * D4 + c] = v[r];
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) st_stream(out + (first + r) * D4 + c, v[r]);
+    }
   }
 }
 
 // src_meta[s] = {offset of source s in recv_ids, count, displacement inside source s's bucket list}
+// slot_map[s][x] = position of owner-local row x in source s's list (-1: source s does not name x)
 __global__ void __launch_bounds__(kThreads) k_peer_pull_ids(PeerPtrs counts, PeerPtrs send_local, int n_ranks, int me,
                                                             int64_t recv_cap, int32_t* __restrict__ recv_ids,
-                                                            int32_t* __restrict__ src_meta) {
+                                                            int32_t* __restrict__ src_meta, int32_t* __restrict__ slot_map,
+                                                            int64_t map_stride) {
   __shared__ int off[ESR_MAX_PEERS + 1], cnt[ESR_MAX_PEERS], dsp[ESR_MAX_PEERS];
   __shared__ int cm[ESR_MAX_PEERS][ESR_MAX_PEERS];
   if ((int)threadIdx.x < n_ranks * n_ranks) {  // all n*n peer loads in flight at once
@@ -97,72 +109,126 @@ __global__ void __launch_bounds__(kThreads) k_peer_pull_ids(PeerPtrs counts, Pee
   for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < total; k += (int64_t)gridDim.x * kThreads) {
     int s = 0;
     while (s + 1 < n_ranks && k >= off[s + 1]) ++s;
-    recv_ids[k] = reinterpret_cast<const int32_t*>(send_local.p[s])[dsp[s] + (k - off[s])];
+    const int pos = (int)(k - off[s]);
+    const int32_t x = reinterpret_cast<const int32_t*>(send_local.p[s])[dsp[s] + pos];
+    recv_ids[k] = x;
+    slot_map[s * map_stride + x] = pos;
   }
 }
 
-// index of x in the ascending array a[0..n), or -1
-__device__ __forceinline__ int find_sorted(const int32_t* __restrict__ a, int n, int32_t x) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < x) lo = mid + 1;
-    else hi = mid;
+__global__ void __launch_bounds__(kThreads) k_peer_clear_map(const int32_t* __restrict__ recv_ids,
+                                                             const int32_t* __restrict__ src_meta, int n_ranks,
+                                                             int32_t* __restrict__ slot_map, int64_t map_stride) {
+  const int64_t total = src_meta[n_ranks * 3];
+  for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < total; k += (int64_t)gridDim.x * kThreads) {
+    int s = 0;
+    while (s + 1 < n_ranks && k >= src_meta[(s + 1) * 3]) ++s;
+    slot_map[s * map_stride + recv_ids[k]] = -1;
   }
-  return (lo < n && a[lo] == x) ? lo : -1;
 }
 
-template <int TPR>
-__global__ void __launch_bounds__(kThreads) k_peer_merge_adagrad(PeerPtrs order, PeerPtrs dE, PeerPtrs db, int n_ranks,
+// One thread per received (source, row) entry: resolve, through slot_map, where every source keeps
+// that row's gradient.  The entry of the FIRST source naming a row owns it: desc[k][q] = row index in
+// my inbox of source q's gradient (offset_q + position), -1 if source q does not name the row; entries that do
+// not own their row get all -1.  Splitting this off keeps the heavy kernel below free of dependent
+// 4-byte lookups, so its row loads are issued back to back.
+__global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const int32_t* __restrict__ recv_ids,
+                                                           const int32_t* __restrict__ src_meta,
+                                                           const int32_t* __restrict__ slot_map, int64_t map_stride,
+                                                           int32_t* __restrict__ desc) {
+  const int64_t total = src_meta[n_ranks * 3];
+  for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < total; k += (int64_t)gridDim.x * kThreads) {
+    int s = 0;
+    while (s + 1 < n_ranks && k >= src_meta[(s + 1) * 3]) ++s;
+    const int32_t x = recv_ids[k];
+    int pos[ESR_MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < ESR_MAX_PEERS; ++q) pos[q] = q < n_ranks ? slot_map[q * map_stride + x] : -1;
+    bool first = true;
+#pragma unroll
+    for (int q = 0; q < ESR_MAX_PEERS; ++q)
+      if (q < s && pos[q] >= 0) first = false;
+#pragma unroll
+    for (int q = 0; q < ESR_MAX_PEERS; ++q)
+      if (q < n_ranks) desc[k * n_ranks + q] = (first && q >= s && pos[q] >= 0) ? src_meta[q * 3 + 0] + pos[q] : -1;
+  }
+}
+
+// One group of TPR lanes per entry, EB entries per iteration: sum the row's gradients over the sources
+// in source order (from my inbox, where the sources' row passes scattered them), then optax.adagrad on
+// the local shard row.  Every load of the EB
+// entries (descriptors, bias scalars, then rows) is issued before its first use.
+template <int TPR, int EB>
+__global__ void __launch_bounds__(kThreads) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
+                                                                 const float* __restrict__ inbox_db, int n_ranks,
                                                                  const int32_t* __restrict__ recv_ids,
-                                                                 const int32_t* __restrict__ src_meta, int D4,
+                                                                 const int32_t* __restrict__ src_meta,
+                                                                 const int32_t* __restrict__ desc, int D4,
                                                                  float* __restrict__ rows, float* __restrict__ acc,
                                                                  float* __restrict__ bias, float* __restrict__ bias_acc,
                                                                  float lr, float eps) {
   const int lane = threadIdx.x % TPR;
   const int64_t total = src_meta[n_ranks * 3];
   const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
-  for (int64_t k = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; k < total; k += groups) {
-    int s = 0;
-    while (s + 1 < n_ranks && k >= src_meta[(s + 1) * 3]) ++s;
-    const int32_t x = recv_ids[k];
-    bool first = true;  // is s the first source that names row x?
-    for (int q = 0; q < s && first; ++q)
-      first = find_sorted(recv_ids + src_meta[q * 3], src_meta[q * 3 + 1], x) < 0;
-    if (!first) continue;
-    // gradient row index of x inside each source's dE (-1: that source does not name x):
-    // order_q[displ_q + position of x in source q's list], for this source and the later ones
-    int gi[ESR_MAX_PEERS];
+  for (int64_t k0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; k0 < total; k0 += groups * EB) {
+    int gi[EB][ESR_MAX_PEERS];
+    int32_t x[EB];
+    bool any[EB];
 #pragma unroll
-    for (int q = 0; q < ESR_MAX_PEERS; ++q) {
-      gi[q] = -1;
-      if (q < n_ranks && q >= s) {
-        const int pos = q == s ? (int)(k - src_meta[s * 3])
-                               : find_sorted(recv_ids + src_meta[q * 3], src_meta[q * 3 + 1], x);
-        if (pos >= 0) gi[q] = reinterpret_cast<const int32_t*>(order.p[q])[src_meta[q * 3 + 2] + pos];
+    for (int e = 0; e < EB; ++e) {
+      const int64_t k = k0 + e * groups;
+      any[e] = false;
+      x[e] = 0;
+#pragma unroll
+      for (int q = 0; q < ESR_MAX_PEERS; ++q) {
+        gi[e][q] = (k < total && q < n_ranks) ? desc[k * n_ranks + q] : -1;
+        any[e] = any[e] || gi[e][q] >= 0;
+      }
+      if (any[e]) x[e] = recv_ids[k];
+    }
+    // bias scalars (lane 0) -- loaded up front so their latency overlaps the row traffic
+    float bp[EB], ba[EB], bg[EB];
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      bp[e] = ba[e] = bg[e] = 0.f;
+      if (any[e] && lane == 0) {
+        bp[e] = bias[x[e]];
+        ba[e] = bias_acc[x[e]];
+#pragma unroll
+        for (int q = 0; q < ESR_MAX_PEERS; ++q)
+          if (q < n_ranks && gi[e][q] >= 0) bg[e] += inbox_db[gi[e][q]];
       }
     }
-    float4* p = reinterpret_cast<float4*>(rows) + (int64_t)x * D4;
-    float4* a = reinterpret_cast<float4*>(acc) + (int64_t)x * D4;
     for (int c = lane; c < D4; c += TPR) {
-      float4 g = f4_zero();
+      float4 g[EB], pv[EB], av[EB];
 #pragma unroll
-      for (int q = 0; q < ESR_MAX_PEERS; ++q)
-        if (q < n_ranks && gi[q] >= 0) f4_add(g, reinterpret_cast<const float4*>(dE.p[q])[(int64_t)gi[q] * D4 + c]);
-      float4 pv = p[c], av = ld_stream(a + c);
-      adagrad4(pv, av, g, lr, eps);
-      p[c] = pv;
-      st_stream(a + c, av);
+      for (int e = 0; e < EB; ++e) {
+        g[e] = f4_zero();
+        if (any[e]) {
+          pv[e] = reinterpret_cast<const float4*>(rows)[(int64_t)x[e] * D4 + c];
+          av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + (int64_t)x[e] * D4 + c);
+#pragma unroll
+          for (int q = 0; q < ESR_MAX_PEERS; ++q)
+            if (q < n_ranks && gi[e][q] >= 0)
+              f4_add(g[e], ld_stream(inbox_dE + (int64_t)gi[e][q] * D4 + c));
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EB; ++e) {
+        if (any[e]) {
+          adagrad4(pv[e], av[e], g[e], lr, eps);
+          reinterpret_cast<float4*>(rows)[(int64_t)x[e] * D4 + c] = pv[e];
+          st_stream(reinterpret_cast<float4*>(acc) + (int64_t)x[e] * D4 + c, av[e]);
+        }
+      }
     }
-    if (lane == 0) {
-      float g = 0.f;
 #pragma unroll
-      for (int q = 0; q < ESR_MAX_PEERS; ++q)
-        if (q < n_ranks && gi[q] >= 0) g += reinterpret_cast<const float*>(db.p[q])[gi[q]];
-      float pv = bias[x], av = bias_acc[x];
-      adagrad1(pv, av, g, lr, eps);
-      bias[x] = pv;
-      bias_acc[x] = av;
+    for (int e = 0; e < EB; ++e) {
+      if (any[e] && lane == 0) {
+        adagrad1(bp[e], ba[e], bg[e], lr, eps);
+        bias[x[e]] = bp[e];
+        bias_acc[x[e]] = ba[e];
+      }
     }
   }
 }
@@ -207,40 +273,106 @@ extern "C" int esr_peer_gather_f32(const void* const* peer_rows, const void* con
   const int D4 = D / 4;
   const int tpr = tpr_for(D4);
   constexpr int ROWS = 4;
-  const unsigned grid = (unsigned)ceil_div(ceil_div(cap, ROWS) * tpr, kThreads);
+  const int64_t want = ceil_div(ceil_div(cap, ROWS) * tpr, kThreads);
+  const int64_t persistent = (int64_t)sm_count() * 8;
+  const unsigned grid = (unsigned)(want < persistent ? want : persistent);
+  Cyclic cyc;
+  cyc.n = n_ranks;
+  cyc.shift = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == n_ranks) cyc.shift = b;
   ESR_DISPATCH_TPR(tpr, (k_peer_gather<TPR, ROWS><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-                            pr, pb, uniq, n_uniq, cap, n_ranks, D4, reinterpret_cast<float4*>(out), out_bias)));
+                            pr, pb, uniq, n_uniq, cap, cyc, D4, reinterpret_cast<float4*>(out), out_bias)));
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
 
 extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* peer_send_local, int32_t n_ranks,
-                                     int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta,
-                                     esr_stream_t stream_) {
+                                     int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, int32_t* slot_map,
+                                     int64_t map_stride, esr_stream_t stream_) {
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && recv_cap > 0 && recv_ids && src_meta);
+  ESR_REQUIRE(slot_map != nullptr && map_stride > 0);
   PeerPtrs pc, ps;
   ESR_REQUIRE(load_ptrs(&pc, peer_counts, n_ranks) && load_ptrs(&ps, peer_send_local, n_ranks));
   const int grid = 2 * sm_count();
   k_peer_pull_ids<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(pc, ps, n_ranks, me, recv_cap, recv_ids,
-                                                                             src_meta);
+                                                                             src_meta, slot_map, map_stride);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
 
-extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const void* const* peer_order, const void* const* peer_dE,
-                                          const void* const* peer_db, int32_t n_ranks, const int32_t* recv_ids,
-                                          const int32_t* src_meta, float lr, float eps, esr_stream_t stream_) {
-  ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0);
+extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+                                          const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
+                                          int64_t map_stride, int32_t* desc, float lr, float eps, esr_stream_t stream_) {
+  ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
   ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
-  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta);
-  PeerPtrs po, pe, pb;
-  ESR_REQUIRE(load_ptrs(&po, peer_order, n_ranks) && load_ptrs(&pe, peer_dE, n_ranks) && load_ptrs(&pb, peer_db, n_ranks));
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0);
+  ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D4 = shard->D / 4;
+  k_peer_resolve<<<4 * sm_count(), kThreads, 0, stream>>>(n_ranks, recv_ids, src_meta, slot_map, map_stride, desc);
+  ESR_LAUNCH_CHECK();
   const int tpr = tpr_for(D4);
   const int grid = 8 * sm_count();
-  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-                            po, pe, pb, n_ranks, recv_ids, src_meta, D4, shard->rows[0], shard->acc, shard->bias,
-                            shard->bias_acc, lr, eps)));
+  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 2><<<grid, kThreads, 0, stream>>>(
+                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, D4,
+                            shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)));
+  ESR_LAUNCH_CHECK();
+  k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+// emit_map[u] = owner << 27 | (offset of my bucket in owner's inbox + position inside the bucket)
+__global__ void __launch_bounds__(kThreads) k_peer_emit_plan(PeerPtrs counts, int n_ranks, int me, Cyclic cyc,
+                                                             const int32_t* __restrict__ uniq,
+                                                             const int32_t* __restrict__ n_uniq, int64_t cap,
+                                                             const int32_t* __restrict__ inv_order, int64_t inbox_cap,
+                                                             int32_t* __restrict__ emit_map, int32_t* __restrict__ err) {
+  __shared__ int cm[ESR_MAX_PEERS][ESR_MAX_PEERS];
+  __shared__ int off[ESR_MAX_PEERS], dsp[ESR_MAX_PEERS];
+  if ((int)threadIdx.x < n_ranks * n_ranks) {
+    const int s = threadIdx.x / n_ranks, q = threadIdx.x % n_ranks;
+    cm[s][q] = reinterpret_cast<const int32_t*>(counts.p[s])[q];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n_ranks) {
+    const int o = threadIdx.x;
+    int a = 0, d = 0;
+    for (int s = 0; s < me; ++s) a += cm[s][o];  // sources before me in owner o's inbox
+    for (int q = 0; q < o; ++q) d += cm[me][q];  // my buckets before owner o
+    off[o] = a;
+    dsp[o] = d;
+  }
+  __syncthreads();
+  const int64_t n = min((int64_t)*n_uniq, cap);
+  for (int64_t u = blockIdx.x * (int64_t)kThreads + threadIdx.x; u < n; u += (int64_t)gridDim.x * kThreads) {
+    const int o = cyc.owner(uniq[u]);
+    const int64_t idx = (int64_t)off[o] + inv_order[u] - dsp[o];
+    if (idx >= inbox_cap || idx >= (1 << 27)) {
+      *err = 1;
+      emit_map[u] = o << 27;  // clamp: keep the store in bounds
+    } else {
+      emit_map[u] = (o << 27) | (int32_t)idx;
+    }
+  }
+}
+
+extern "C" int esr_peer_emit_plan_i32(const void* const* peer_counts, int32_t n_ranks, int32_t me, const int32_t* uniq,
+                                      const int32_t* n_uniq, int64_t cap, const int32_t* inv_order, int64_t inbox_cap,
+                                      int32_t* emit_map, int32_t* err, esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && cap >= 0 && inbox_cap > 0);
+  if (cap == 0) return ESR_OK;
+  ESR_REQUIRE(uniq && n_uniq && inv_order && emit_map && err);
+  PeerPtrs pc;
+  ESR_REQUIRE(load_ptrs(&pc, peer_counts, n_ranks));
+  Cyclic cyc;
+  cyc.n = n_ranks;
+  cyc.shift = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == n_ranks) cyc.shift = b;
+  k_peer_emit_plan<<<2 * sm_count(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      pc, n_ranks, me, cyc, uniq, n_uniq, cap, inv_order, inbox_cap, emit_map, err);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

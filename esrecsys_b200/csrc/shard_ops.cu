@@ -38,14 +38,17 @@ __global__ void __launch_bounds__(kThreads) k_route_finish(const int32_t* __rest
                                                            const int32_t* __restrict__ n_uniq,
                                                            const int32_t* __restrict__ order, int64_t cap, int n_ranks,
                                                            int32_t* __restrict__ send_local,
-                                                           int32_t* __restrict__ send_counts) {
+                                                           int32_t* __restrict__ send_counts,
+                                                           int32_t* __restrict__ inv_order) {
   __shared__ int cnt[kMaxRanks];
   if (threadIdx.x < kMaxRanks) cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (k < *n_uniq) {
-    const int32_t row = uniq[order[k]];
+    const int32_t u = order[k];
+    const int32_t row = uniq[u];
     send_local[k] = row / n_ranks;
+    if (inv_order) inv_order[u] = (int32_t)k;
     atomicAdd(&cnt[row % n_ranks], 1);  // integer counts: order-independent
   }
   __syncthreads();
@@ -149,8 +152,8 @@ extern "C" size_t esr_route_workspace_bytes(int64_t cap) {
 }
 
 extern "C" int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks,
-                                  int32_t* order, int32_t* send_local, int32_t* send_counts, void* ws, size_t ws_bytes,
-                                  esr_stream_t stream_) {
+                                  int32_t* order, int32_t* send_local, int32_t* send_counts, int32_t* inv_order, void* ws,
+                                  size_t ws_bytes, esr_stream_t stream_) {
   ESR_REQUIRE(uniq && n_uniq && order && send_local && send_counts && cap >= 0 && n_ranks >= 1 && n_ranks <= kMaxRanks);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ESR_CUDA(cudaMemsetAsync(send_counts, 0, sizeof(int32_t) * n_ranks, stream));
@@ -172,7 +175,7 @@ extern "C" int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, in
   ESR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, owner, send_local, iota, order, (int)cap, 0, bits, stream));
   if (need > tmp_bytes) return ESR_EWORKSPACE;
   ESR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, owner, send_local, iota, order, (int)cap, 0, bits, stream));
-  k_route_finish<<<grid, kThreads, 0, stream>>>(uniq, n_uniq, order, cap, n_ranks, send_local, send_counts);
+  k_route_finish<<<grid, kThreads, 0, stream>>>(uniq, n_uniq, order, cap, n_ranks, send_local, send_counts, inv_order);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

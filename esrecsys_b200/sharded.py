@@ -45,8 +45,10 @@ class LibesrOps:
     def route_plan(self, uniq, n_uniq, n_ranks, out=None):
         cap = uniq.numel()
         i32 = dict(dtype=torch.int32, device=self.dev)
+        inv_order = None
         if out is not None:
-            order, send_local, send_counts = out
+            order, send_local, send_counts = out[:3]
+            inv_order = out[3] if len(out) > 3 else None
         else:
             order = torch.empty(cap, **i32)
             send_local = torch.empty(cap, **i32)
@@ -55,7 +57,7 @@ class LibesrOps:
         if self._route_ws is None or self._route_ws.numel() < need:
             self._route_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
         L.check(L.lib().esr_route_plan_i32(L.ptr(uniq), L.ptr(n_uniq), cap, n_ranks, L.ptr(order), L.ptr(send_local),
-                                           L.ptr(send_counts), L.ptr(self._route_ws), self._route_ws.numel(),
+                                           L.ptr(send_counts), L.ptr(inv_order), L.ptr(self._route_ws), self._route_ws.numel(),
                                            L.stream_ptr()), "esr_route_plan_i32")
         return order, send_local, send_counts
 
@@ -217,10 +219,14 @@ class PeerShardedGloveTrainer:
     (csrc/peer_ops.cu) on buffers from torch's symmetric-memory rendezvous: no NCCL all-to-all, no id
     exchange, no host-known sizes, no host synchronisation inside the step.
 
-      plan -> route plan (published) -> peer gather of the unique rows -> compact plan -> prep
-      -> all-reduce(3 floats) -> row pass (EMIT into symmetric memory) -> all-reduce(2) -> finish
-      -> barrier -> owners pull ids, merge gradients over peers, Adagrad -> barrier
+      side stream : index plan + route plan of batch t+1 (published in symmetric memory, double-buffered)
+      main stream : peer gather of the unique rows (NVLink loads) -> compact plan -> prep
+                    -> all-reduce(3 floats) -> emit plan -> row pass, whose gradient rows are STORED
+                    STRAIGHT INTO THE OWNERS' INBOXES over NVLink -> all-reduce(2) -> finish -> barrier
+                    -> owners pull the id lists, merge their inbox locally, Adagrad -> barrier
     """
+
+    DEPTH = 2
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0):
         import torch.distributed._symmetric_memory as symm_mem
@@ -243,6 +249,7 @@ class PeerShardedGloveTrainer:
             ptrs = (C.c_void_p * 8)(*[int(p) for p in h.buffer_ptrs])
             return t, ptrs
 
+        i32 = dict(dtype=torch.int32, device=self.dev)
         V_loc = shard_rows(V, self.rank, self.n)
         V_max = shard_rows(V, 0, self.n)
         rows, self.p_rows = symm((V_max, D), torch.float32)
@@ -252,22 +259,45 @@ class PeerShardedGloveTrainer:
         self.shard = EmbeddingTable.wrap(rows[:V_loc], bias=bias[:V_loc],
                                          acc=torch.full((V_loc, D), 0.1, device=self.dev),
                                          bias_acc=torch.full((V_loc,), 0.1, device=self.dev))
-        self.send_counts, self.p_counts = symm((16,), torch.int32)
-        self.send_local, self.p_send_local = symm((n_slots,), torch.int32)
-        self.order, self.p_order = symm((n_slots,), torch.int32)
-        self.dE, self.p_dE = symm((n_slots, D), torch.float32)
-        self.db, self.p_db = symm((n_slots,), torch.float32)
+        # route plan published per step parity: peers read set k of step t while set 1-k is rebuilt for t+1
+        self.pub = []
+        for _ in range(self.DEPTH):
+            counts, p_counts = symm((16,), torch.int32)
+            send_local, p_send_local = symm((n_slots,), torch.int32)
+            self.pub.append(dict(counts=counts, p_counts=p_counts, send_local=send_local, p_send_local=p_send_local,
+                                 order=torch.empty(n_slots, **i32), inv_order=torch.empty(n_slots, **i32)))
+        # gradient inbox: the sources' row passes scatter their rows for my shard straight into it (NVLink stores)
+        self.inbox_cap = n_slots * min(self.n, 4)
+        self.inbox_dE, self.p_inbox_dE = symm((self.inbox_cap, D), torch.float32)
+        self.inbox_db, self.p_inbox_db = symm((self.inbox_cap,), torch.float32)
+        self.emit_map = torch.zeros(n_slots, **i32)
+        self.err = torch.zeros(1, **i32)
         self.ops = LibesrOps(self.dev)
-        self.plan = IndexPlan(n_slots, V, self.dev)
+        self.plans = [IndexPlan(n_slots, V, self.dev) for _ in range(self.DEPTH)]
         self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
         self.cplan = IndexPlan(n_slots, n_slots, self.dev)
-        self.scratch = torch.empty(n_slots, dtype=torch.int32, device=self.dev)
+        self.scratch = torch.empty(n_slots, **i32)
         self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
-                                 B_global=self.B * self.n, dE=self.dE, db=self.db)
-        self.recv_cap = self.n * n_slots
-        self.recv_ids = torch.empty(self.recv_cap, dtype=torch.int32, device=self.dev)
-        self.src_meta = torch.zeros(3 * 8 + 4, dtype=torch.int32, device=self.dev)
+                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db)
+        cfg = self.step_fn.cfg
+        cfg.emit_map = L.ptr(self.emit_map)
+        cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
+        cfg.emit_peers_db = C.cast(self.p_inbox_db, C.c_void_p)
+        cfg.n_emit_peers = self.n
+        self.recv_cap = self.inbox_cap
+        self.recv_ids = torch.empty(self.recv_cap, **i32)
+        self.src_meta = torch.zeros(3 * 8 + 4, **i32)
+        self.map_stride = V_max
+        self.slot_map = torch.full((self.n, V_max), -1, **i32)
+        self.desc = torch.empty(self.recv_cap * self.n, **i32)
+        self.s_side = torch.cuda.Stream(self.dev)
+        self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self._keep = [None] * self.DEPTH
+        self.t = 0
         self.loss = None
+        self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        torch.cuda.current_stream().synchronize()
         self.barrier()
 
     def barrier(self):
@@ -281,13 +311,27 @@ class PeerShardedGloveTrainer:
         self.barrier()
 
     def step(self, ids, counts):
+        """ids: int32 (2, B_local) global rows (host pinned or device); counts: f32 (B_local,).
+        Enqueues one step; returns the GLOBAL loss as a device scalar."""
         lib = L.lib()
-        sp = L.stream_ptr()
-        ids = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
-        counts = counts.to(self.dev, non_blocking=True)
-        plan, cplan, n = self.plan, self.cplan, self.n
-        plan.build(ids)
-        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(self.order, self.send_local, self.send_counts))
+        n, k = self.n, self.t % self.DEPTH
+        plan, pub, cplan, st = self.plans[k], self.pub[k], self.cplan, self.step_fn
+        main = torch.cuda.current_stream(self.dev)
+        side = self.s_side
+        # ---- side stream: everything that depends on the ids only ----
+        side.wait_stream(main)                 # inputs may have been produced on the caller's stream
+        side.wait_event(self.ev_done[k])       # peers are done with publish set k (barrier of step t-2 passed)
+        with torch.cuda.stream(side):
+            d_ids = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
+            d_counts = counts.to(self.dev, non_blocking=True)
+            self._keep[k] = (d_ids, d_counts, ids, counts)
+            plan.build(d_ids)
+            self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"],
+                                                                pub["inv_order"]))
+            self.ev_plan[k].record(side)
+        main.wait_event(self.ev_plan[k])
+        # ---- main stream ----
+        sp = L.stream_ptr(main)
         L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
                                         self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
         L.check(lib.esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner), L.ptr(cplan.uniq),
@@ -295,20 +339,28 @@ class PeerShardedGloveTrainer:
         cs = cplan.s
         cs.n_slots = plan.n_slots
         cs.perm, cs.useg, cs.seg_off, cs.n_uniq = plan.s.perm, plan.s.useg, plan.s.seg_off, plan.s.n_uniq
-        st = self.step_fn
-        st.prep(cplan, counts)
-        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: every rank has finished its fetch
-        st.rows(cplan)
+        st.prep(cplan, d_counts)
+        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: all fetches done, all route plans published
+        L.check(lib.esr_peer_emit_plan_i32(pub["p_counts"], n, self.rank, L.ptr(plan.uniq), L.ptr(plan.n_uniq),
+                                           plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
+                                           L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
+        st.rows(cplan)                                          # gradient rows go straight to the owners' inboxes
         dist.all_reduce(st.scalars[3:5], group=self.group)
         st.finish(cplan)
-        self.barrier()                                          # every rank's dE / db / route plan is published
-        L.check(lib.esr_peer_pull_ids_i32(self.p_counts, self.p_send_local, n, self.rank, self.recv_cap,
-                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), sp), "esr_peer_pull_ids_i32")
-        L.check(lib.esr_peer_merge_adagrad_f32(C.byref(self.shard.struct()), self.p_order, self.p_dE, self.p_db, n,
-                                               L.ptr(self.recv_ids), L.ptr(self.src_meta), self.lr, 1e-7, sp),
-                "esr_peer_merge_adagrad_f32")
+        self.barrier()                                          # every rank's gradients have landed in the inboxes
+        L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
+                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
+                                          sp), "esr_peer_pull_ids_i32")
+        L.check(lib.esr_peer_merge_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
+                                               L.ptr(self.recv_ids),
+                                               L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride, L.ptr(self.desc),
+                                               self.lr, 1e-7, sp), "esr_peer_merge_adagrad_f32")
         self.barrier()                                          # every owner has applied its updates
-        self.loss = st.scalars[L.SC_LOSS].clone()
+        self.ev_done[k].record(main)
+        slot = self.t % self.loss_log.numel()
+        self.loss_log[slot: slot + 1].copy_(st.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
+        self.loss = self.loss_log[slot]
+        self.t += 1
         return self.loss
 
     def gather_dense(self):

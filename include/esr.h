@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define ESR_VERSION 100 /* 0.1.0 */
+#define ESR_MAX_PEERS 8 /* ranks of one NVSwitch domain addressed through peer pointers */
 
 typedef void* esr_stream_t; /* cudaStream_t */
 
@@ -136,6 +137,15 @@ typedef struct EsrGloveCfg {
   float alpha;         /* 0.75   wikipedia/train_cooccurence.py:81 */
   int32_t chunk;       /* sorted slots per work item; 0 => default */
   int32_t reserved;
+  const int32_t* emit_map; /* EMIT_GRADS only: gradient of unique row u is written to dE[emit_map[u]] /
+                              db[emit_map[u]] (e.g. owner-bucket order of the sharded path); NULL => u */
+  /* Optional peer scatter of the EMIT outputs (row-sharded path): when set, emit_map[u] encodes
+   * owner << 27 | index and the gradient row is stored to emit_peers_dE[owner] + index*D (resp.
+   * emit_peers_db[owner] + index) -- the owners' inboxes, written over NVLink by the row pass itself. */
+  void* const* emit_peers_dE;
+  void* const* emit_peers_db;
+  int32_t n_emit_peers;
+  int32_t reserved2;
 } EsrGloveCfg;
 
 /* Scalars block (device float[ESR_GLOVE_NSCAL]) shared by the three phases.  After
@@ -203,9 +213,11 @@ int esr_dense_sgdm_f32(float* p, const float* g, float* trace, int64_t n, float 
 size_t esr_route_workspace_bytes(int64_t cap);
 /* uniq[0..*n_uniq) sorted unique global rows of this rank's batch (EsrPlan.uniq).  Outputs:
  * order[k] = index into uniq of the k-th row in owner-bucket order (stable), send_local[k] = its
- * owner-local row id (payload of the id all-to-all), send_counts[r] = rows owned by rank r. */
+ * owner-local row id (payload of the id all-to-all), send_counts[r] = rows owned by rank r,
+ * inv_order[order[k]] = k (optional, may be NULL: the EsrGloveCfg.emit_map of the peer-memory path). */
 int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks, int32_t* order,
-                       int32_t* send_local, int32_t* send_counts, void* ws, size_t ws_bytes, esr_stream_t stream);
+                       int32_t* send_local, int32_t* send_counts, int32_t* inv_order, void* ws, size_t ws_bytes,
+                       esr_stream_t stream);
 /* Re-express a plan in unique-row indices (sorted_keys := useg, partner := unique index of the
  * partner row, uniq := 0..U-1) so a step can run on the compact table of fetched rows without a
  * second sort.  perm / useg / seg_off / n_uniq of the original plan stay valid.  scratch: [n_slots]. */
@@ -248,22 +260,32 @@ int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, const float* a
  * symmetric-memory rendezvous; index = rank).  No host-known sizes, no NCCL on the data path; the
  * caller separates fetch / update phases with device barriers.  See csrc/peer_ops.cu.
  * ------------------------------------------------------------------------------------------ */
-#define ESR_MAX_PEERS 8
 /* out[u,:] = shard_{uniq[u] % n}[uniq[u] / n, :], out_bias[u] likewise, u < *n_uniq: the lookup of
  * SURVEY.md 8(e) (index all-to-all + row all-to-all) as one gather over peer pointers. */
 int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks,
                         const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t D, float* out,
                         float* out_bias, esr_stream_t stream);
 /* Owner `me`: from every source rank's published esr_route_plan_i32 outputs (send_counts[n],
- * send_local[]) copy the owner-local ids destined to me into recv_ids (source-major), and write
- * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[n] = total. */
+ * send_local[]) copy the owner-local ids destined to me into recv_ids (source-major), write
+ * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[3n] = total,
+ * and slot_map[s*map_stride + x] = position of row x in source s's list (slot_map is all -1 on entry
+ * and is restored to -1 by esr_peer_merge_adagrad_f32). */
+/* Source side, after every rank published its route plan: emit_map[u] = owner << 27 | (offset of my
+ * bucket inside owner's inbox + position of row u in that bucket), for the row pass's peer scatter.
+ * err[0] is set to 1 if an index would exceed inbox_cap. */
+int esr_peer_emit_plan_i32(const void* const* peer_counts, int32_t n_ranks, int32_t me, const int32_t* uniq,
+                           const int32_t* n_uniq, int64_t cap, const int32_t* inv_order, int64_t inbox_cap,
+                           int32_t* emit_map, int32_t* err, esr_stream_t stream);
 int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* peer_send_local, int32_t n_ranks,
-                          int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, esr_stream_t stream);
-/* Owner side: merge the gradients all sources hold for my rows (dE_s[order_s[.]], db_s[...]; summed in
- * source order, deterministic) and apply optax.adagrad to the shard in place. */
-int esr_peer_merge_adagrad_f32(EsrTable* shard, const void* const* peer_order, const void* const* peer_dE,
-                               const void* const* peer_db, int32_t n_ranks, const int32_t* recv_ids,
-                               const int32_t* src_meta, float lr, float eps, esr_stream_t stream);
+                          int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, int32_t* slot_map,
+                          int64_t map_stride, esr_stream_t stream);
+/* Owner side: merge the gradients the sources scattered into my inbox (inbox_dE[recv_cap, D],
+ * inbox_db[recv_cap], source-major like recv_ids; summed in source order, deterministic) and apply
+ * optax.adagrad to the shard in place.  All loads are local. */
+int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db,
+                               int32_t n_ranks, const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
+                               int64_t map_stride, int32_t* desc /* scratch [recv_cap * n_ranks] */, float lr, float eps,
+                               esr_stream_t stream);
 
 #ifdef __cplusplus
 }
