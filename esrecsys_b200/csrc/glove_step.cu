@@ -112,7 +112,7 @@ size_t carve_ws(void* base, int64_t B, int32_t D, int32_t chunk_in, GloveWs* w) 
   t.parts = c.take<float>(cap_chunks * 2);
   t.prep_blk = c.take<float>((size_t)t.prep_blocks * 3);
   t.rows_blk = c.take<float>((size_t)cap_row_blocks * 2);
-  t.wl_count = c.take<int32_t>(2);
+  t.wl_count = c.take<int32_t>(4);
   t.wl_light = c.take<int32_t>(cap_chunks);
   t.wl_heavy = c.take<int32_t>(cap_chunks);
   if (w) *w = t;
@@ -255,6 +255,7 @@ struct RowsArgs {
   float* parts;
   float* rows_blk;
   int32_t* wl_count;  // [0] light, [1] heavy work-list lengths
+  int32_t* work_counter;  // dynamic work distribution of the persistent row pass
   int32_t* wl_light;  // head chunks of straddling segments with <= kHeavyParts partials
   int32_t* wl_heavy;
   float* dE;
@@ -487,21 +488,46 @@ __device__ __forceinline__ void grow_store(const Row<NV>& r, float4* __restrict_
   }
 }
 
+// Per-group staging of a chunk's metadata in shared memory: keys[0] is the key before the chunk,
+// keys[1 + s] slot s, keys[1 + cnt] the key after it.  Filled with coalesced loads once per chunk, so
+// the slot loop never waits on a dependent global load for its bookkeeping.
+struct __align__(16) GroupMeta {
+  SlotRec rec[32];
+  int32_t keys[36];
+};
+
 template <int G, int NV, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArgs a) {
+  extern __shared__ __align__(16) unsigned char meta_raw[];
   __shared__ float red[32 * 2];
   constexpr int GP = 32 / G;  // chunks per warp
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, grp = lane / G;
-  const int64_t c = (blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * GP + grp;
+  GroupMeta& gm = reinterpret_cast<GroupMeta*>(meta_raw)[(threadIdx.x >> 5) * GP + grp];
+  // Blocks are scheduled in index order; the sorted stream ends with the cold rows (singleton
+  // segments: three DRAM rows per slot), the expensive chunks.  Walk the chunks from the END so the
+  // long blocks start first and the cheap hot-row chunks fill the tail (longest-processing-time first).
+  const int64_t c = a.nchunks - 1 - ((blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * GP + grp);
   const uint32_t D4 = (uint32_t)a.D4;
   const int64_t p0 = c * a.chunk;
-  const int cnt = c < a.nchunks ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+  const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
   const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
   const float4* const rows0 = reinterpret_cast<const float4*>(a.rows[0]);
   const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
   const float4* const accp = reinterpret_cast<const float4*>(a.acc);
   float sums[2] = {0.f, 0.f};  // group-uniform
+
+  // ---- stage the chunk's metadata (lane-parallel, coalesced) ----
+  for (int s = gl; s < cnt; s += G) {
+    gm.keys[1 + s] = a.skv[p0 + s];
+    gm.rec[s] = a.rec[p0 + s];
+  }
+  if (gl == 0 && cnt > 0) {
+    gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
+    gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+    gm.keys[2 + cnt] = kNoKey;
+  }
+  __syncwarp();
 
   Row<NV> cur, grad;
   row_zero(cur);
@@ -519,10 +545,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
   Row<NV> Pn;  // partner row of slot s (prefetched during slot s-1)
   row_zero(Pn);
   if (cnt > 0) {
-    key_prev = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-    key_cur = a.skv[p0];
-    rec = a.rec[p0];
-    if (cnt > 1) rec1 = a.rec[p0 + 1];
+    key_prev = gm.keys[0];
+    key_cur = gm.keys[1];
+    rec = gm.rec[0];
+    if (cnt > 1) rec1 = gm.rec[1];
     u = a.useg[p0];
     const uint32_t q = (uint32_t)(rec.code & kRowMask);
     grow_load<G, NV>(Pn, ((rec.code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl, a.D4, false);
@@ -533,8 +559,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
     Row<NV> P = Pn, A;
     bool is_head = false, is_end = false;
     if (active) {
-      key_next = p0 + s + 1 < a.n ? a.skv[p0 + s + 1] : kNoKey;
-      if (s + 2 < cnt) rec2 = a.rec[p0 + s + 2];
+      key_next = gm.keys[2 + s];
+      if (s + 2 < cnt) rec2 = gm.rec[s + 2];
       is_head = key_cur != key_prev;
       is_end = key_cur != key_next;
       const uint32_t row = (uint32_t)(key_cur & kRowMask);
@@ -605,6 +631,215 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
     rec1 = rec2;
   }
   // per-block S1 / S2 partials: lane 0 of every group carries its group's value
+  float v[2] = {gl == 0 ? sums[0] : 0.f, gl == 0 ? sums[1] : 0.f};
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) {
+    a.rows_blk[blockIdx.x * 2 + 0] = v[0];
+    a.rows_blk[blockIdx.x * 2 + 1] = v[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2, group variant with ASYNC STAGING (default for D >= 128): same work split as
+// k_glove_rows_grp, but the rows travel global -> shared with cp.async (LDGSTS), every lane
+// copying and later reading back its own 16-byte columns, so rows in flight cost no registers
+// and the prefetch runs ahead of the consumer:
+//   partner row of slot s+2, self + accumulator rows of slot s+1 are in flight while slot s is
+//   consumed (ncu on the register variant: 45 % of the stall samples sat on the first use of a
+//   row that was issued only one slot earlier).
+// Per group: 3 partner buffers + 1 self + 1 accumulator buffer of R bytes.  Two commit groups per
+// slot, oldest first: {self, acc of s+1}, {partner of s+2}; cp.async.wait_group 1 at the top of
+// slot s therefore guarantees partner(s), self(s), acc(s) and leaves partner(s+1) in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool keep) {
+  if (keep) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+template <int G, int NV>
+__device__ __forceinline__ void grow_copy_async(uint32_t dst, const float4* __restrict__ src, int gl, int D4, bool keep) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    if (c < D4) cp_async16(dst + 16u * c, src + c, keep);
+  }
+}
+template <int G, int NV>
+__device__ __forceinline__ void grow_from_smem(Row<NV>& r, const float4* sp, int gl, int D4) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    r.v[k] = c < D4 ? sp[c] : f4_zero();
+  }
+}
+
+template <int G, int NV, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const RowsArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  __shared__ float red[32 * 2];
+  constexpr int GP = 32 / G;  // chunks per warp
+  constexpr int NB = 5;       // row buffers per group: P0 P1 P2 S A
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, grp = lane / G;
+  const int gidx = (threadIdx.x >> 5) * GP + grp;
+  GroupMeta& gm = reinterpret_cast<GroupMeta*>(dyn_raw)[gidx];
+  const uint32_t D4 = (uint32_t)a.D4;
+  const uint32_t RB = D4 * 16u;
+  unsigned char* bufs = dyn_raw + (size_t)kWarps * GP * sizeof(GroupMeta) + (size_t)gidx * NB * RB;
+  const uint32_t bufs_u32 = (uint32_t)__cvta_generic_to_shared(bufs);
+  const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+  const float4* const rows0 = reinterpret_cast<const float4*>(a.rows[0]);
+  const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
+  const float4* const accp = reinterpret_cast<const float4*>(a.acc);
+  float sums[2] = {0.f, 0.f};
+  // Persistent warps pull work items (GP consecutive chunks) from a counter.  Items are handed out from
+  // the END of the sorted stream: the cold rows (singleton segments, three DRAM rows per slot) are the
+  // long items, so they start first and the cheap hot-row chunks fill in behind them (LPT order), and a
+  // warp that drew cheap items simply draws more of them.
+  const int64_t nitems = (a.nchunks + GP - 1) / GP;
+  for (;;) {
+  int64_t item = 0;
+  if (lane == 0) item = atomicAdd(a.work_counter, 1);
+  item = __shfl_sync(FULL, item, 0);
+  if (item >= nitems) break;
+  const int64_t c = a.nchunks - 1 - (item * GP + grp);
+  const int64_t p0 = c * a.chunk;
+  const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+  __syncwarp();  // the previous item's readers are done with gm
+  for (int s = gl; s < cnt; s += G) {
+    gm.keys[1 + s] = a.skv[p0 + s];
+    gm.rec[s] = a.rec[p0 + s];
+  }
+  if (gl == 0 && cnt > 0) {
+    gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
+    gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+    gm.keys[2 + cnt] = kNoKey;
+    gm.keys[3 + cnt] = kNoKey;
+  }
+  __syncwarp();
+
+  // issue helpers ------------------------------------------------------------------------------
+  auto issue_partner = [&](int s) {  // partner row of slot s -> P[s % 3]
+    if (s < cnt) {
+      const int32_t code = gm.rec[s].code;
+      const uint32_t q = (uint32_t)(code & kRowMask);
+      grow_copy_async<G, NV>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl,
+                             a.D4, true);
+    }
+  };
+  // self / accumulator rows of slot s (self: chunk start or segment head; acc: a segment that both
+  // starts and ends inside this chunk closes at s).  `started` = the segment containing s started here.
+  auto issue_self_acc = [&](int s, bool started_if_not_head) {
+    if (s < cnt) {
+      const int32_t k0 = gm.keys[s], k1 = gm.keys[1 + s], k2 = gm.keys[2 + s];
+      const bool head = k1 != k0, end = k1 != k2;
+      const uint32_t row = (uint32_t)(k1 & kRowMask);
+      if (s == 0 || head)
+        grow_copy_async<G, NV>(bufs_u32 + 3u * RB, ((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, true);
+      if (!a.emit && end && (head || started_if_not_head))
+        grow_copy_async<G, NV>(bufs_u32 + 4u * RB, accp + (uint64_t)row * D4, gl, a.D4, false);
+    }
+  };
+
+  Row<NV> cur, grad;
+  row_zero(cur);
+  row_zero(grad);
+  float bacc = 0.f;
+  bool started_here = false;
+  int64_t u = cnt > 0 ? a.useg[p0] : 0;
+  // prologue: {self, acc of slot 0} {partner 0} {nothing} {partner 1}
+  issue_self_acc(0, false);
+  cp_async_commit();
+  issue_partner(0);
+  cp_async_commit();
+  cp_async_commit();
+  issue_partner(1);
+  cp_async_commit();
+
+  for (int s = 0; s < a.chunk; ++s) {
+    const bool active = s < cnt;
+    cp_async_wait1();  // partner(s), self(s), acc(s) have landed; partner(s+1) may still be in flight
+    Row<NV> P, A;
+    row_zero(P);
+    bool is_head = false, is_end = false;
+    int32_t key_cur = kNoKey;
+    SlotRec rec;
+    rec.code = 0; rec.w = 0.f; rec.t = 0.f; rec.bs = 0.f;
+    if (active) {
+      const int32_t k0 = gm.keys[s], k2 = gm.keys[2 + s];
+      key_cur = gm.keys[1 + s];
+      rec = gm.rec[s];
+      is_head = key_cur != k0;
+      is_end = key_cur != k2;
+      grow_from_smem<G, NV>(P, reinterpret_cast<const float4*>(bufs + (size_t)(s % 3) * RB), gl, a.D4);
+      if (s == 0 || is_head) {
+        grow_from_smem<G, NV>(cur, reinterpret_cast<const float4*>(bufs + 3 * (size_t)RB), gl, a.D4);
+        row_zero(grad);
+        bacc = 0.f;
+        started_here = is_head;
+        if (is_head && s > 0) ++u;
+      }
+      if (!a.emit && is_end && started_here)
+        grow_from_smem<G, NV>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
+    }
+    // every buffer read above is private to the lane that filled it: refill without a barrier
+    issue_self_acc(s + 1, started_here && !is_end);
+    cp_async_commit();
+    issue_partner(s + 2);
+    cp_async_commit();
+
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) d += f4_dot(cur.v[k], P.v[k]);
+    const float dot = group_sum<G>(d);
+    if (active) {
+      const float res = rec.t - dot;
+      const float rr = a.per_pair ? res - rec.bs : res;
+      const float g = a.c2B * rec.w * (a.per_pair ? rr : res - mbs);
+      if (rec.code & kRoleBit) {
+        sums[0] = fmaf(rec.w, res, sums[0]);
+        sums[1] = fmaf(rec.w * rr, rr, sums[1]);
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) f4_fma(grad.v[k], g, P.v[k]);
+      bacc += a.per_pair ? g : rec.bs;
+      if (is_end && started_here) {
+        if (a.emit) {
+          uint64_t e = a.emit_map ? (uint64_t)a.emit_map[u] : (uint64_t)u;
+          float* base = a.dE;
+          if (a.peers.on) {
+            base = a.peers.dE[e >> kEmitShift];
+            e &= (1u << kEmitShift) - 1u;
+          }
+          grow_store<G, NV>(grad, reinterpret_cast<float4*>(base) + e * D4, gl, a.D4, true);
+        } else {
+          const uint32_t row = (uint32_t)(key_cur & kRowMask);
+          const int v = (key_cur >> 31) & 1;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+          grow_store<G, NV>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
+          grow_store<G, NV>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
+        }
+        if (gl == 0) a.bsum[u] = bacc;
+      } else if (is_end || s == cnt - 1) {
+        const int slot = (!is_end && started_here) ? 1 : 0;
+        grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.part) + (uint64_t)(c * 2 + slot) * D4, gl, a.D4, false);
+        if (gl == 0) {
+          a.parts[c * 2 + slot] = bacc;
+          if (slot == 1) {
+            const int64_t np = (a.seg_off[u + 1] - 1) / a.chunk - c + 1;
+            const int heavy = np > kHeavyParts;
+            const int e = atomicAdd(a.wl_count + heavy, 1);
+            (heavy ? a.wl_heavy : a.wl_light)[e] = (int32_t)c;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }  // work loop
   float v[2] = {gl == 0 ? sums[0] : 0.f, gl == 0 ? sums[1] : 0.f};
   block_sum<2>(v, red);
   if (threadIdx.x == 0) {
@@ -956,6 +1191,7 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.useg = plan->useg;
   a.seg_off = plan->seg_off;
   a.wl_count = w.wl_count;
+  a.work_counter = w.wl_count + 2;
   a.wl_light = w.wl_light;
   a.wl_heavy = w.wl_heavy;
   a.nchunks = w.nchunks;
@@ -1009,12 +1245,32 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 }
 
 template <int G, int NV, int NKC>
-static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream) {
+static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
+                           bool use_async = false) {
   constexpr int GP = 32 / G;
-  const int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
-  if (phases & 1) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 2 * sizeof(int32_t), stream));
-    k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)><<<row_blocks, kThreads, 0, stream>>>(a);
+  int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
+  if (use_async) row_blocks = (int)std::min<int64_t>(row_blocks, 2 * (int64_t)sm_count());  // persistent, work-stealing
+  if ((phases & 1) && use_async) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
+    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
+    static size_t configured = 0;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && smem > configured) {
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      configured = smem;
+    }
+    k_glove_rows_grp_async<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
+    ESR_LAUNCH_CHECK();
+  } else if (phases & 1) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
+    constexpr size_t smem = (size_t)kWarps * GP * sizeof(GroupMeta);
+    static bool configured = false;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && !configured) {
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   }
   if (phases & 2) {
@@ -1027,7 +1283,7 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
 template <int NK, int S, int MINB>
 static int launch_rows(const RowsArgs& a, const GloveWs& w, float* scalars, bool tma, int phases, cudaStream_t stream) {
   int row_blocks = w.row_blocks;
-  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 2 * sizeof(int32_t), stream));
+  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
   if (tma) {
     const size_t smem = (size_t)kWarps * kTmaStages * 3 * a.D4 * 16;
     static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per NK: largest dynamic smem opted in
@@ -1070,10 +1326,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     if (d4 <= 4) return launch_rows_grp<1, 4, 1>(a, w, scalars, phases, stream);
     if (d4 <= 8) return launch_rows_grp<2, 4, 1>(a, w, scalars, phases, stream);
     if (d4 <= 16) return launch_rows_grp<4, 4, 1>(a, w, scalars, phases, stream);
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream);
+    const bool as = cfg->reserved != 1;  // reserved == 1: keep rows in registers (A/B probe)
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as);
   }
   switch (nk) {
     case 1:
