@@ -49,6 +49,12 @@ class EsrGloveCfg(C.Structure):
                 ("reserved2", C.c_int32)]
 
 
+class EsrInbatchCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("loss_kind", C.c_int32), ("Bq", C.c_int64), ("Bk", C.c_int64),
+                ("diag_off", C.c_int64), ("D", C.c_int32), ("splits", C.c_int32), ("margin", C.c_float),
+                ("scale", C.c_float), ("b_norm", C.c_float), ("reserved", C.c_int32)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -96,6 +102,9 @@ _SIGNATURES = {
     "esr_gather_scalar_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "esr_permute_rows_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "esr_segment_sum_rows_f32": (C.c_int, [C.POINTER(EsrPlan), C.c_int32, _P, _P, _P, _P, _P]),
+    "esr_inbatch_workspace_bytes": (C.c_size_t, [C.POINTER(EsrInbatchCfg)]),
+    "esr_inbatch_fwd_bwd_bf16": (C.c_int, [_P, _P, C.POINTER(EsrInbatchCfg), _P, _P, _P, _P, C.c_size_t, _P]),
+    "esr_inbatch_ws_layout": (C.c_int, [C.POINTER(EsrInbatchCfg), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -276,3 +276,49 @@ def score_all(table: EmbeddingTable, queries):
     L.check(L.lib().esr_score_all_f32(C.byref(table.struct()), L.ptr(queries), T, L.ptr(out), L.stream_ptr()),
             "esr_score_all_f32")
     return out
+
+
+class InBatchScorer:
+    """B x B in-batch-negative scoring + loss + gradients on the tensor cores
+    (``esr_inbatch_fwd_bwd_bf16``; csrc/inbatch_scores.cu).  Generalises the triplet scoring of
+    pinterest/models.py:67-72 + pinterest/train_shop_the_look.py:99-104 to in-batch negatives
+    (BASELINE.json configs[2], configs[3]).  The positive of query ``i`` is item ``i + diag_off``."""
+
+    def __init__(self, Bq, D, Bk=None, loss="hinge", diag_off=0, margin=1.0, scale=1.0, b_norm=None, splits=0, device=None):
+        self.device = _dev(device)
+        cfg = L.EsrInbatchCfg()
+        cfg.struct_size = C.sizeof(L.EsrInbatchCfg)
+        cfg.loss_kind = {"hinge": L.LOSS_HINGE, "softmax": L.LOSS_SOFTMAX}[loss]
+        cfg.Bq, cfg.Bk = int(Bq), int(Bk if Bk is not None else Bq)
+        cfg.diag_off, cfg.D, cfg.splits = int(diag_off), int(D), int(splits)
+        cfg.margin, cfg.scale = float(margin), float(scale)
+        cfg.b_norm = float(b_norm if b_norm is not None else Bq)
+        self.cfg = cfg
+        self.Bq, self.Bk, self.D = cfg.Bq, cfg.Bk, cfg.D
+        self.ws_bytes = int(L.lib().esr_inbatch_workspace_bytes(C.byref(cfg)))
+        if self.ws_bytes == 0:
+            raise L.EsrError("esr_inbatch_workspace_bytes: unsupported shape (D must be 64, 128, 192 or 256)")
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.dQ = torch.empty(self.Bq, self.D, dtype=torch.float32, device=self.device)
+        self.dK = torch.empty(self.Bk, self.D, dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def run(self, Q, K, stream=None):
+        """Q (Bq, D), K (Bk, D) fp32 CUDA.  Returns (loss[1], dQ, dK) device tensors (reused across calls)."""
+        assert Q.is_cuda and K.is_cuda and Q.dtype == torch.float32 and K.dtype == torch.float32
+        assert Q.is_contiguous() and K.is_contiguous() and tuple(Q.shape) == (self.Bq, self.D) and tuple(K.shape) == (self.Bk, self.D)
+        L.check(L.lib().esr_inbatch_fwd_bwd_bf16(L.ptr(Q), L.ptr(K), C.byref(self.cfg), L.ptr(self.dQ), L.ptr(self.dK),
+                                                 L.ptr(self.loss), L.ptr(self.ws), self.ws_bytes, L.stream_ptr(stream)),
+                "esr_inbatch_fwd_bwd_bf16")
+        return self.loss, self.dQ, self.dK
+
+    def debug_views(self):
+        """(G bf16 [Bq, Bk], diag f32 [Bq], cnt i32 [JS, Bq], lse f32 [Bq]) views into the workspace (tests)."""
+        o = (C.c_int64 * 8)()
+        L.check(L.lib().esr_inbatch_ws_layout(C.byref(self.cfg), o), "esr_inbatch_ws_layout")
+        g_off, ldG, d_off, c_off, JS, l_off = int(o[0]), int(o[1]), int(o[2]), int(o[3]), int(o[4]), int(o[5])
+        G = self.ws[g_off:g_off + self.Bq * ldG * 2].view(torch.bfloat16).view(self.Bq, ldG)[:, :self.Bk]
+        diag = self.ws[d_off:d_off + 4 * self.Bq].view(torch.float32)
+        cnt = self.ws[c_off:c_off + 4 * JS * self.Bq].view(torch.int32).view(JS, self.Bq)
+        lse = self.ws[l_off:l_off + 4 * self.Bq].view(torch.float32)
+        return G, diag, cnt, lse

@@ -256,6 +256,40 @@ int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, const float* a
                             int32_t* artist_rows, float* pos_aff, float* neg_aff, float* l2, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * In-batch-negative scoring on the tensor cores (tcgen05 / TMEM / TMA; csrc/inbatch_scores.cu).
+ * Generalises the explicit-triplet scoring + hinge of the shop-the-look trainer
+ * (pinterest/models.py:67-72, pinterest/train_shop_the_look.py:99-104) and the affinity hinge of the
+ * Spotify trainer (spotify/train_spotify.py:91-94) to the B x B in-batch-negative form BASELINE.json
+ * names for configs[2] and configs[3]: S = Q K^T with bf16 operands and fp32 accumulation; the positive
+ * of query i is item i + diag_off, every other item is a negative.
+ *   ESR_LOSS_HINGE   : loss = (1/b_norm) sum_i sum_{j != pos(i)} relu(margin + scale*S_ij - scale*S_i,pos(i))
+ *   ESR_LOSS_SOFTMAX : loss = (1/b_norm) sum_i [logsumexp_j(scale*S_ij) - scale*S_i,pos(i)]
+ * Q [Bq, D], K [Bk, D] fp32 row-major (gathered rows / tower outputs), rounded to bf16 (RNE) inside;
+ * dQ, dK are the gradients with respect to those inputs (straight-through), fp32.  The fp32 score matrix
+ * is never written to memory; the workspace holds a bf16 [Bq, Bk] matrix (hinge: exact {0,1} mask,
+ * softmax: probabilities).  D in {64, 128, 192, 256}.  Contract: oracle/inbatch.py.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsrInbatchCfg {
+  uint32_t struct_size;
+  int32_t loss_kind; /* ESR_LOSS_* */
+  int64_t Bq;        /* queries (rows of Q) */
+  int64_t Bk;        /* items (rows of K); == Bq on one GPU, the all-gathered batch when sharded */
+  int64_t diag_off;  /* positive of query i is item i + diag_off (rank * Bq when sharded) */
+  int32_t D;
+  int32_t splits;    /* split-K of the two backward contractions; 0 => auto */
+  float margin;      /* hinge margin (1.0 in the reference) */
+  float scale;       /* score multiplier (1 / temperature); > 0 */
+  float b_norm;      /* loss divisor: the GLOBAL number of queries */
+  int32_t reserved;
+} EsrInbatchCfg;
+
+size_t esr_inbatch_workspace_bytes(const EsrInbatchCfg* cfg);
+int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const EsrInbatchCfg* cfg, float* dQ, float* dK,
+                             float* loss, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* Test / profiling aid: byte offsets inside the workspace of {G, ldG (elements), diag, cnt, JS, lse, S, Qh}. */
+int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out8);
+
+/* ------------------------------------------------------------------------------------------
  * Row-sharded table over NVLink peer memory (device pointers of every rank's buffers, e.g. from a
  * symmetric-memory rendezvous; index = rank).  No host-known sizes, no NCCL on the data path; the
  * caller separates fetch / update phases with device barriers.  See csrc/peer_ops.cu.

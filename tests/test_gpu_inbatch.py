@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 in-batch score kernel (esr_inbatch_fwd_bwd_bf16) against oracle/inbatch.py.
+
+Tolerances: the contract rounds Q, K to bf16 first, so every product is exact in fp32 and only the
+summation order differs -> scores / losses / gradients within 1e-5 (abs + rel).  A hinge mask bit can
+legitimately differ where |margin| < 1e-5 (the two summation orders straddle zero); the backward is
+therefore checked against the oracle evaluated on the KERNEL's own mask (exact), and the mask itself
+against the oracle's outside that band.  Softmax probabilities are rounded to bf16 by contract: the
+backward is checked on the kernel's own bf16 probabilities, and those against the oracle's to 1 bf16 ulp."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import inbatch as oib
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(Bq, Bk, D, seed, spread=1.0):
+    rng = np.random.default_rng(seed)
+    Q = (rng.standard_normal((Bq, D)) * spread / np.sqrt(np.sqrt(D))).astype(np.float32)
+    K = (rng.standard_normal((Bk, D)) * spread / np.sqrt(np.sqrt(D))).astype(np.float32)
+    return Q, K
+
+
+def _run(Q, K, **kw):
+    from esrecsys_b200.engine import InBatchScorer
+    sc = InBatchScorer(Q.shape[0], Q.shape[1], Bk=K.shape[0], **kw)
+    loss, dQ, dK = sc.run(torch.from_numpy(Q).cuda(), torch.from_numpy(K).cuda())
+    torch.cuda.synchronize()
+    G, diag, cnt, lse = sc.debug_views()
+    return (float(loss.item()), dQ.cpu().numpy(), dK.cpu().numpy(), G.float().cpu().numpy(), diag.cpu().numpy(),
+            cnt.cpu().numpy(), lse.cpu().numpy())
+
+
+SHAPES = [(128, 128, 128, 0), (256, 256, 64, 0), (384, 384, 128, 0), (200, 200, 128, 0), (1024, 1024, 256, 0),
+          (128, 512, 128, 256), (333, 777, 192, 100), (2048, 2048, 128, 0)]
+
+
+@pytest.mark.parametrize("Bq,Bk,D,off", SHAPES)
+def test_hinge_parity(Bq, Bk, D, off):
+    Q, K = _data(Bq, Bk, D, 1)
+    loss, dQ, dK, G, diag, cnt, _ = _run(Q, K, loss="hinge", diag_off=off)
+    S, Qh, Kh = oib.scores(Q, K)
+    pj = np.arange(Bq) + off
+    np.testing.assert_allclose(diag, S[np.arange(Bq), pj], rtol=1e-5, atol=1e-5)
+    mask, h = oib.hinge_mask(S, off)
+    gm = G > 0.5
+    assert set(np.unique(G)) <= {0.0, 1.0}
+    differ = gm != mask
+    assert np.all(np.abs(h[differ]) < 1e-4), "mask differs outside the rounding band: %d cells" % differ.sum()
+    assert differ.mean() < 1e-4
+    np.testing.assert_array_equal(cnt.sum(0), gm.sum(1))
+    ref_loss = np.sum(np.where(gm, h, 0).astype(np.float64)) / Bq
+    assert abs(loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    rdQ, rdK = oib.hinge_backward(gm, Qh, Kh, off)
+    np.testing.assert_allclose(dQ, rdQ, rtol=1e-5, atol=1e-5 * np.abs(rdQ).max())
+    np.testing.assert_allclose(dK, rdK, rtol=1e-5, atol=1e-5 * np.abs(rdK).max())
+
+
+@pytest.mark.parametrize("Bq,Bk,D,off", SHAPES)
+def test_softmax_parity(Bq, Bk, D, off):
+    Q, K = _data(Bq, Bk, D, 2)
+    loss, dQ, dK, G, diag, _, lse = _run(Q, K, loss="softmax", diag_off=off)
+    S, Qh, Kh = oib.scores(Q, K)
+    P, rlse = oib.softmax_probs(S)
+    np.testing.assert_allclose(lse, rlse, rtol=1e-5, atol=1e-5)
+    rloss, _, _, Pb = oib.softmax(Q, K, off)
+    assert abs(loss - rloss) <= 1e-5 * max(1.0, abs(rloss))
+    # probabilities: bf16 by contract -> within one bf16 ulp (2^-8 relative) of the oracle's
+    np.testing.assert_allclose(G, Pb, rtol=2.0 ** -7, atol=1e-30)
+    rdQ, rdK = oib.softmax_backward(G, Qh, Kh, off)
+    np.testing.assert_allclose(dQ, rdQ, rtol=1e-5, atol=1e-5 * np.abs(rdQ).max())
+    np.testing.assert_allclose(dK, rdK, rtol=1e-5, atol=1e-5 * np.abs(rdK).max())
+    # and end to end against the oracle's own rounding: a handful of 1-ulp flips of P only
+    _, odQ, odK, _ = oib.softmax(Q, K, off)
+    assert np.abs(dQ - odQ).max() <= 2e-3 * np.abs(odQ).max()
+
+
+def test_hinge_margin_scale_norm_and_determinism():
+    Q, K = _data(512, 512, 128, 3)
+    a = _run(Q, K, loss="hinge", margin=0.25, scale=0.5, b_norm=4096.0)
+    b = _run(Q, K, loss="hinge", margin=0.25, scale=0.5, b_norm=4096.0)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    S, Qh, Kh = oib.scores(Q, K)
+    mask, h = oib.hinge_mask(S, 0, 0.25, 0.5)
+    gm = a[3] > 0.5
+    assert np.all(np.abs(h[gm != mask]) < 1e-4)
+    rdQ, rdK = oib.hinge_backward(gm, Qh, Kh, 0, 0.5, 4096.0)
+    np.testing.assert_allclose(a[1], rdQ, rtol=1e-5, atol=1e-5 * np.abs(rdQ).max())
+    np.testing.assert_allclose(a[2], rdK, rtol=1e-5, atol=1e-5 * np.abs(rdK).max())
+    ref_loss = np.sum(np.where(gm, h, 0).astype(np.float64)) / 4096.0
+    assert abs(a[0] - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+
+
+def test_splitk_matches_single():
+    Q, K = _data(640, 640, 128, 5)
+    a = _run(Q, K, loss="softmax", splits=1)
+    b = _run(Q, K, loss="softmax", splits=4)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-5, atol=1e-7)
+
+
+def test_full_size_properties():
+    """BASELINE configs[2] size (B = 8192, D = 128): size-independent checks -- sum_j dS_ij = 0 per row for
+    softmax (dQ of a constant K is 0), and the loss of identical rows is log(B)."""
+    B, D = 8192, 128
+    Q = np.full((B, D), 0.25, np.float32)
+    K = np.full((B, D), 0.5, np.float32)
+    loss, dQ, dK, G, *_ = _run(Q, K, loss="softmax")
+    assert abs(loss - np.log(B)) < 1e-4
+    # p_ij = 1/B = 2^-13 exactly in bf16 -> dQ_i = (sum_j p_ij K_j - K_i)/B = 0
+    assert np.abs(dQ).max() < 1e-9 and np.abs(dK).max() < 1e-9
+    Q, K = _data(B, B, D, 7)
+    loss, dQ, dK, G, diag, cnt, _ = _run(Q, K, loss="hinge")
+    S, Qh, Kh = oib.scores(Q, K)
+    np.testing.assert_allclose(diag, np.diag(S), rtol=1e-5, atol=1e-5)
+    gm = G > 0.5
+    rdQ, rdK = oib.hinge_backward(gm, Qh, Kh, 0)
+    np.testing.assert_allclose(dQ, rdQ, rtol=1e-5, atol=1e-5 * np.abs(rdQ).max())
+    np.testing.assert_allclose(dK, rdK, rtol=1e-5, atol=1e-5 * np.abs(rdK).max())
