@@ -52,7 +52,7 @@ class EsrGloveCfg(C.Structure):
 class EsrInbatchCfg(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("loss_kind", C.c_int32), ("Bq", C.c_int64), ("Bk", C.c_int64),
                 ("diag_off", C.c_int64), ("D", C.c_int32), ("splits", C.c_int32), ("margin", C.c_float),
-                ("scale", C.c_float), ("b_norm", C.c_float), ("reserved", C.c_int32)]
+                ("scale", C.c_float), ("b_norm", C.c_float), ("chunk_rows", C.c_int32)]
 
 
 _P = C.c_void_p

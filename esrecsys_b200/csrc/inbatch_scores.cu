@@ -20,10 +20,14 @@
 //   k_inbatch_cast   fp32 -> bf16 (RNE) of Q and K; diag_i = Q~_i . K~_pos(i) in fp32
 //   k_inbatch_scores persistent per (i-block, j-range): Q tile resident in smem, K tiles through a
 //                    TMA/mbarrier ring, one elected thread issues tcgen05.mma (128x128x16, cta_group::1)
-//                    into a double-buffered TMEM accumulator, 4 epilogue warps tcgen05.ld the tile and
+//                    into a double-buffered TMEM accumulator, 8 epilogue warps tcgen05.ld the tile and
 //                    apply the loss.  MODE 0 hinge, 1 softmax row statistics, 2 softmax probabilities.
 //   k_inbatch_lse    merges the per-j-range (max, sum) pairs into logsumexp_i
 //   k_inbatch_bwd    tcgen05 GEMM, one 128 x D tile per CTA (grid.y: dQ | dK, grid.z: split-K)
+// The query rows can be processed in CHUNKS (cfg.chunk_rows; automatic above 512 MB of G): the G buffer then
+// holds one chunk and is reused, which bounds the workspace for very large batches.  Measured on B200 at
+// B = 8192: L2-sized chunks (33 MB) were SLOWER than one pass (166 vs 122 us) -- the backward kernel is bound
+// by operand-fetch latency per k-block, not by HBM -- so one pass is the default.
 //   k_inbatch_finish fixed-order split-K sum, diagonal terms, scale; loss reduction (deterministic)
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -38,8 +42,10 @@ constexpr int kTile = 128;                         // score tile edge = UMMA M =
 constexpr int kBK = 64;                            // bf16 per 128-byte swizzle row = one k-block
 constexpr uint32_t kKBlkBytes = kTile * kBK * 2;   // 16 KB: [128 rows][128 B], SWIZZLE_128B, K-major
 constexpr uint32_t kAtomBytes = kBK * kBK * 2;     // 8 KB: [64 k-rows][128 B] MN-major atom column
-constexpr int kIbThreads = 256;
+constexpr int kIbThreads = 384;                    // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kBwdThreads = 256;                   // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
 constexpr int kMaxJS = 16;
+constexpr int64_t kChunkBytes = 512ll << 20;       // cap of one row chunk of G (workspace bound; chunk_rows overrides)
 constexpr int kMaxSplit = 8;
 constexpr int kSmCountPlan = 148;                  // B200; only steers the work split
 
@@ -141,8 +147,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // ------------------------------------------------------------------------------------------------
 struct IbPlan {
   int Bq, Bk, D, off;
-  int n_ib, n_jb, JS, j_per;  // score kernel grid (n_ib, JS); each CTA walks j_per j-blocks
-  int S;                      // split-K of the backward GEMMs
+  int n_ib, n_jb;
+  int Bc, n_ic, n_chunks;     // row chunk: Bc rows (n_ic i-blocks); G holds ONE chunk and is reused
+  int JS, j_per;              // score kernel grid (n_ic, JS); each CTA walks j_per j-blocks
+  int R;                      // column ranges the per-row statistics are kept for: 2 * JS (two epilogue halves)
+  int Sq, Sk;                 // split-K of dQ (over items) and of dK (over the chunk's queries)
   int64_t ldG;
 };
 
@@ -151,12 +160,12 @@ struct IbWs {
   __nv_bfloat16* Kh;
   __nv_bfloat16* G;
   float* diag;
-  int32_t* cnt;    // [JS][Bq]  hinge: active negatives of row i inside j-range js
-  float2* stats;   // [JS][Bq]  softmax: (running max, sum of exp) of row i inside j-range js
-  float* lse;      // [Bq]
+  float* cnt;      // [R][Bq]  hinge: active negatives of row i inside column range r (exact small integers)
+  float2* stats;   // [R][Bq]  softmax: (running max, sum of exp2) of row i inside column range r, log2 domain
+  float* lse2;     // [Bq]     log2-domain logsumexp
   float* lossp;    // [n_ib * JS]
-  float* partQ;    // [S][Bq][D]
-  float* partK;    // [S][Bk][D]
+  float* partQ;    // [Sq][Bq][D]
+  float* partK;    // [n_chunks * Sk][Bk][D]
 };
 
 IbPlan make_plan(const EsrInbatchCfg* c) {
@@ -167,17 +176,39 @@ IbPlan make_plan(const EsrInbatchCfg* c) {
   p.off = (int)c->diag_off;
   p.n_ib = (int)ceil_div(p.Bq, kTile);
   p.n_jb = (int)ceil_div(p.Bk, kTile);
-  int js = kSmCountPlan / p.n_ib;
+  p.ldG = (int64_t)p.n_jb * kTile;
+  // row chunks: one chunk of G (Bc x ldG bf16) is written by the score kernel and read straight back by
+  // the two backward contractions, so it lives in L2; chunk_rows > 0 overrides (>= Bq: a single chunk).
+  int64_t bc = c->chunk_rows > 0 ? c->chunk_rows : kChunkBytes / (p.ldG * 2);
+  bc = bc / kTile * kTile;
+  bc = bc < kTile ? kTile : bc;
+  const int64_t nch = ceil_div((int64_t)p.n_ib * kTile, bc);
+  p.n_ic = (int)ceil_div(p.n_ib, nch);  // balanced chunks
+  p.Bc = p.n_ic * kTile;
+  p.n_chunks = (int)ceil_div(p.n_ib, p.n_ic);
+  int js = kSmCountPlan / p.n_ic;
   js = js < 1 ? 1 : js;
   js = js > p.n_jb ? p.n_jb : js;
   js = js > kMaxJS ? kMaxJS : js;
   p.j_per = (int)ceil_div(p.n_jb, js);
   p.JS = (int)ceil_div(p.n_jb, p.j_per);
-  int s = c->splits > 0 ? c->splits : kSmCountPlan / (p.n_ib + p.n_jb);
-  s = s < 1 ? 1 : s;
-  s = s > kMaxSplit ? kMaxSplit : s;
-  p.S = s;
-  p.ldG = (int64_t)p.n_jb * kTile;
+  p.R = 2 * p.JS;
+  // backward: dQ has n_ic tiles per chunk with ceil(Bk/64) k-blocks, dK has n_jb tiles with Bc/64 k-blocks.
+  // Pick the k-blocks per CTA so that both kinds of CTA run about the same length and one wave fills the SMs.
+  const int nkb_q = (int)ceil_div(p.Bk, kBK), nkb_k = (int)ceil_div(p.Bc, kBK);
+  int best = nkb_q > nkb_k ? nkb_q : nkb_k;
+  for (int t = best; t >= 1; --t) {
+    int64_t sq = ceil_div(nkb_q, t), sk = ceil_div(nkb_k, t);
+    sq = sq > kMaxSplit ? kMaxSplit : sq;
+    sk = sk > kMaxSplit ? kMaxSplit : sk;
+    if ((int64_t)p.n_ic * sq + (int64_t)p.n_jb * sk > kSmCountPlan) break;
+    best = t;
+  }
+  p.Sq = (int)ceil_div(nkb_q, best);
+  p.Sk = (int)ceil_div(nkb_k, best);
+  if (c->splits > 0) p.Sq = p.Sk = c->splits;
+  p.Sq = p.Sq > kMaxSplit ? kMaxSplit : p.Sq;
+  p.Sk = p.Sk > kMaxSplit ? kMaxSplit : p.Sk;
   return p;
 }
 
@@ -186,14 +217,14 @@ size_t carve_ib(void* base, const IbPlan& p, IbWs* w) {
   IbWs t;
   t.Qh = c.take<__nv_bfloat16>((size_t)p.Bq * p.D);
   t.Kh = c.take<__nv_bfloat16>((size_t)p.Bk * p.D);
-  t.G = c.take<__nv_bfloat16>((size_t)p.Bq * p.ldG);
+  t.G = c.take<__nv_bfloat16>((size_t)p.Bc * p.ldG);
   t.diag = c.take<float>(p.Bq);
-  t.cnt = c.take<int32_t>((size_t)p.JS * p.Bq);
-  t.stats = c.take<float2>((size_t)p.JS * p.Bq);
-  t.lse = c.take<float>(p.Bq);
+  t.cnt = c.take<float>((size_t)p.R * p.Bq);
+  t.stats = c.take<float2>((size_t)p.R * p.Bq);
+  t.lse2 = c.take<float>(p.Bq);
   t.lossp = c.take<float>((size_t)p.n_ib * p.JS);
-  t.partQ = c.take<float>((size_t)p.S * p.Bq * p.D);
-  t.partK = c.take<float>((size_t)p.S * p.Bk * p.D);
+  t.partQ = c.take<float>((size_t)p.Sq * p.Bq * p.D);
+  t.partK = c.take<float>((size_t)p.n_chunks * p.Sk * p.Bk * p.D);
   if (w) *w = t;
   return c.off;
 }
@@ -245,20 +276,32 @@ __global__ void __launch_bounds__(256) k_inbatch_cast(const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------
 // k_inbatch_scores
+//   grid (i-blocks of the chunk, JS column ranges); 384 threads:
+//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11 epilogue -- warp w owns
+//   TMEM lanes 32*(w%4).. (one thread per score row) and columns 64*half.. of every tile, half = (w-4)/4.
+//   The epilogue is the bound (128x128 elementwise cells per 128x128x128 MMA), so it is written to
+//   ~5 instructions per cell with a warp-uniform fast path for tiles that touch neither the diagonal nor
+//   the right edge.
 // ------------------------------------------------------------------------------------------------
 struct ScoreArgs {
   const float* diag;
-  __nv_bfloat16* G;
+  __nv_bfloat16* G;   // this chunk's rows: G[(i - i_base) * ldG + j]
   int64_t ldG;
-  int32_t* cnt;
+  float* cnt;
   float2* stats;
-  const float* lse;
+  const float* lse2;
   float* lossp;
-  int Bq, Bk, off, n_jb, j_per;
+  int Bq, Bk, off, n_jb, j_per, ib0;  // ib0: first i-block of the chunk
   float margin, scale;
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int KB, int NS, int MODE>
 __global__ void __launch_bounds__(kIbThreads, 1)
@@ -266,7 +309,7 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   extern __shared__ unsigned char ib_smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * NS + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float red[4];
+  __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(ib_smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
   const uint32_t q_smem = base;
@@ -275,7 +318,7 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   const uint32_t q_bar = smem_u32(&bars[0]);
   const uint32_t full0 = smem_u32(&bars[1]), empty0 = smem_u32(&bars[1 + NS]);
   const uint32_t tfull0 = smem_u32(&bars[1 + 2 * NS]), tempty0 = smem_u32(&bars[1 + 2 * NS + 2]);
-  const int ib = blockIdx.x, js = blockIdx.y;
+  const int ib = a.ib0 + blockIdx.x, js = blockIdx.y;
   const int jb0 = js * a.j_per;
   const int jb1 = min(a.n_jb, jb0 + a.j_per);
 
@@ -291,7 +334,7 @@ __global__ void __launch_bounds__(kIbThreads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8u * s, 1);
-      mbar_init(tempty0 + 8u * s, 4);  // one arrival per epilogue warp
+      mbar_init(tempty0 + 8u * s, 8);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -353,98 +396,146 @@ __global__ void __launch_bounds__(kIbThreads, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = one row of the tile (TMEM lane), 4 chunks of 32 columns =====
-    const int q = warp & 3;
+    // ===== epilogue: thread = one score row (TMEM lane) x one 64-column half of every tile =====
+    // TMEM -> register reads run at ~64 B/clk per SM (a 128x128 fp32 tile = 1024 clk, twice its MMA time), so
+    // they are software-pipelined: the two 32-column loads of tile t+1 are in flight while tile t is consumed.
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const int i = ib * kTile + r;
     const bool rv = i < a.Bq;
     const int jpos = i + a.off;
-    const float sii = (rv && MODE == 0) ? a.scale * a.diag[i] : 0.f;
-    const float lse = (rv && MODE == 2) ? a.lse[i] : 0.f;
-    float lsum = 0.f;
-    int cnt = 0;
+    const int i_first = ib * kTile + q * 32;  // first row of this warp
+    // MODE 0: h = scale*S + c0, c0 = margin - scale*S_ii.  MODE 1/2 work in the log2 domain: t = S * (scale*log2 e).
+    const float c0 = (rv && MODE == 0) ? a.margin - a.scale * a.diag[i] : 0.f;
+    const float sl2 = a.scale * kLog2e;
+    const float nlse2 = (rv && MODE == 2) ? -a.lse2[i] : 0.f;
+    float ls0 = 0.f, ls1 = 0.f, cn0 = 0.f, cn1 = 0.f;
     float mx = -INFINITY, sm = 0.f;
-    int it = 0;
-    for (int jb = jb0; jb < jb1; ++jb, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tfull0 + 8u * acc, acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + ch * 32), v);
-        tmem_ld_wait();
-        if (ch == 3) {  // every column of this accumulator is in registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-        }
-        const int jbase = jb * kTile + ch * 32;
-        if (MODE == 0) {
-          uint32_t pk[16];
+    __nv_bfloat16* const grow = a.G + (int64_t)(blockIdx.x * kTile + r) * a.ldG;
+    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+
+    // one 32-column block of scores (registers v) at columns jbase..jbase+31
+    auto consume = [&](const uint32_t (&v)[32], int jbase) {
+      // warp-uniform: does this 32x32 block touch the right edge, or (hinge) the positives' diagonal?
+      const bool edge = jbase + 32 > a.Bk;
+      const bool ondiag = MODE == 0 && (i_first + a.off < jbase + 32) && (i_first + 31 + a.off >= jbase);
+      if (MODE == 0) {
+        uint32_t pk[16];
+        if (!edge && !ondiag) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float h0 = fmaf(a.scale, __uint_as_float(v[e]), c0), h1 = fmaf(a.scale, __uint_as_float(v[e + 1]), c0);
+            ls0 += fmaxf(h0, 0.f);
+            ls1 += fmaxf(h1, 0.f);
+            // 1.0f where h > 0 else 0.0f (|h| is never in (0, 2^-100)); bf16(1.0) is the upper half of 1.0f
+            const float m0 = __saturatef(h0 * 1.2676506e30f), m1 = __saturatef(h1 * 1.2676506e30f);
+            cn0 += m0;
+            cn1 += m1;
+            pk[e >> 1] = __byte_perm(__float_as_uint(m0), __float_as_uint(m1), 0x7632);
+          }
+        } else {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             uint32_t bits = 0;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const int j = jbase + e + h2;
-              const float h = a.margin + a.scale * __uint_as_float(v[e + h2]) - sii;
-              const bool m = rv && j < a.Bk && j != jpos && h > 0.f;
-              lsum += m ? h : 0.f;
-              cnt += m ? 1 : 0;
+              const float h = fmaf(a.scale, __uint_as_float(v[e + h2]), c0);
+              const bool m = j < a.Bk && j != jpos && h > 0.f;
+              ls0 += m ? h : 0.f;
+              cn0 += m ? 1.f : 0.f;
               bits |= m ? (0x3F80u << (16 * h2)) : 0u;
             }
             pk[e >> 1] = bits;
           }
-          if (rv) {
-            uint4* dst = reinterpret_cast<uint4*>(a.G + (int64_t)i * a.ldG + jbase);
+        }
+        if (rv) {
+          uint4* dst = reinterpret_cast<uint4*>(grow + jbase);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
-          }
-        } else if (MODE == 1) {
-          float cm = -INFINITY;
+          for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
+        }
+      } else if (MODE == 1) {
+        float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float s = a.scale * __uint_as_float(v[e]);
-            cm = (jbase + e < a.Bk) ? fmaxf(cm, s) : cm;
-          }
-          if (cm > -INFINITY) {
-            const float nm = fmaxf(mx, cm);
-            float add = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float s = a.scale * __uint_as_float(v[e]);
-              add += (jbase + e < a.Bk) ? exp2f((s - nm) * kLog2e) : 0.f;
-            }
-            sm = sm * exp2f((mx - nm) * kLog2e) + add;
-            mx = nm;
-          }
-        } else {
-          uint32_t pk[16];
+        for (int e = 0; e < 32; e += 2) {
+          const float t0 = sl2 * __uint_as_float(v[e]), t1 = sl2 * __uint_as_float(v[e + 1]);
+          cm0 = (!edge || jbase + e < a.Bk) ? fmaxf(cm0, t0) : cm0;
+          cm1 = (!edge || jbase + e + 1 < a.Bk) ? fmaxf(cm1, t1) : cm1;
+        }
+        const float cm = fmaxf(cm0, cm1);
+        if (cm > -INFINITY) {
+          const float nm = fmaxf(mx, cm);
+          float ad0 = 0.f, ad1 = 0.f;
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float s0 = a.scale * __uint_as_float(v[e]), s1 = a.scale * __uint_as_float(v[e + 1]);
-            const float p0 = (rv && jbase + e < a.Bk) ? exp2f((s0 - lse) * kLog2e) : 0.f;
-            const float p1 = (rv && jbase + e + 1 < a.Bk) ? exp2f((s1 - lse) * kLog2e) : 0.f;
-            pk[e >> 1] = pack_bf16(p0, p1);
+            const float x0 = ex2_approx(fmaf(sl2, __uint_as_float(v[e]), -nm));
+            const float x1 = ex2_approx(fmaf(sl2, __uint_as_float(v[e + 1]), -nm));
+            ad0 += (!edge || jbase + e < a.Bk) ? x0 : 0.f;
+            ad1 += (!edge || jbase + e + 1 < a.Bk) ? x1 : 0.f;
           }
-          if (rv) {
-            uint4* dst = reinterpret_cast<uint4*>(a.G + (int64_t)i * a.ldG + jbase);
+          sm = sm * ex2_approx(mx - nm) + (ad0 + ad1);
+          mx = nm;
+        }
+      } else {
+        uint32_t pk[16];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ex2_approx(fmaf(sl2, __uint_as_float(v[e]), nlse2));
+          float p1 = ex2_approx(fmaf(sl2, __uint_as_float(v[e + 1]), nlse2));
+          if (edge) {
+            p0 = jbase + e < a.Bk ? p0 : 0.f;
+            p1 = jbase + e + 1 < a.Bk ? p1 : 0.f;
           }
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+        if (rv) {
+          uint4* dst = reinterpret_cast<uint4*>(grow + jbase);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
         }
       }
+    };
+    // issue the two loads of tile `it` (accumulator it & 1) once the MMA warp has committed it
+    auto issue = [&](int it, uint32_t (&va)[32], uint32_t (&vb)[32]) {
+      const int acc = it & 1;
+      mbar_wait(tfull0 + 8u * acc, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      tmem_ld32(tcol + (uint32_t)(acc * kTile), va);
+      tmem_ld32(tcol + (uint32_t)(acc * kTile + 32), vb);
+    };
+    // the loads of tile `it` have landed: hand the accumulator back to the MMA warp
+    auto landed = [&](int it) {
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8u * (it & 1));
+    };
+    const int nt = jb1 - jb0;
+    uint32_t a0[32], a1[32], b0[32], b1[32];
+    if (nt > 0) issue(0, a0, a1);
+#pragma unroll 1
+    for (int it = 0; it < nt; it += 2) {
+      landed(it);
+      if (it + 1 < nt) issue(it + 1, b0, b1);
+      consume(a0, (jb0 + it) * kTile + half * 64);
+      consume(a1, (jb0 + it) * kTile + half * 64 + 32);
+      if (it + 1 < nt) {
+        landed(it + 1);
+        if (it + 2 < nt) issue(it + 2, a0, a1);
+        consume(b0, (jb0 + it + 1) * kTile + half * 64);
+        consume(b1, (jb0 + it + 1) * kTile + half * 64 + 32);
+      }
     }
+    const int range = js * 2 + half;
     if (MODE == 0) {
-      if (rv) a.cnt[(int64_t)js * a.Bq + i] = cnt;
-      const float ws = warp_sum(lsum);
-      if (lane == 0) red[q] = ws;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      if (q == 0 && lane == 0) a.lossp[ib * gridDim.y + js] = (red[0] + red[1]) + (red[2] + red[3]);
+      if (rv) a.cnt[(int64_t)range * a.Bq + i] = cn0 + cn1;
+      const float ws = warp_sum(rv ? ls0 + ls1 : 0.f);
+      if (lane == 0) red[warp - 4] = ws;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      if (warp == 4 && lane == 0)
+        a.lossp[ib * gridDim.y + js] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
     } else if (MODE == 1) {
-      if (rv) a.stats[(int64_t)js * a.Bq + i] = make_float2(mx, sm);
+      if (rv) a.stats[(int64_t)range * a.Bq + i] = make_float2(mx, sm);
     }
   }
   tc_fence_before();
@@ -453,33 +544,36 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
-// logsumexp_i from the per-j-range statistics (fixed order).
-__global__ void __launch_bounds__(256) k_inbatch_lse(const float2* __restrict__ stats, int JS, int Bq, float* __restrict__ lse) {
+// log2-domain logsumexp_i from the per-range statistics (fixed order).
+__global__ void __launch_bounds__(256) k_inbatch_lse(const float2* __restrict__ stats, int R, int Bq, float* __restrict__ lse2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bq) return;
   float M = -INFINITY;
-  for (int s = 0; s < JS; ++s) M = fmaxf(M, stats[(int64_t)s * Bq + i].x);
+  for (int s = 0; s < R; ++s) M = fmaxf(M, stats[(int64_t)s * Bq + i].x);
   float t = 0.f;
-  for (int s = 0; s < JS; ++s) {
+  for (int s = 0; s < R; ++s) {
     const float2 v = stats[(int64_t)s * Bq + i];
-    t += v.y * exp2f((v.x - M) * kLog2e);
+    t += v.y * exp2f(v.x - M);
   }
-  lse[i] = M + logf(t);
+  lse2[i] = M + log2f(t);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_inbatch_bwd: C[128 x D] (split-K partial) = A[128 x Kr] * X[Kr x D]
-//   which == 0 : dQ rows (i)  A = G        K-major  box {64 j, 128 i}      X = K~ rows j   MN-major
-//   which == 1 : dK rows (j)  A = G^T      MN-major 2 boxes {64 j, 64 i}   X = Q~ rows i   MN-major
+// k_inbatch_bwd: C[128 x D] (split-K partial) = A[128 x Kr] * X[Kr x D] for one row chunk of G
+//   which == 0 : dQ rows i of the chunk   A = G    K-major  box {64 j, 128 i}     X = K~ rows j  MN-major
+//                split sp < Sq over the items j
+//   which == 1 : dK rows j (all items)    A = G^T  MN-major 2 boxes {64 j, 64 i}  X = Q~ rows i  MN-major
+//                split sp < Sk over the chunk's queries; partial index chunk * Sk + sp
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
   float* partQ;
   float* partK;
-  int Bq, Bk, S;
+  int Bq, Bk, Sq, Sk;
+  int i0, rows, chunk;  // chunk = query rows [i0, i0 + rows)
 };
 
 template <int NA, int NS>
-__global__ void __launch_bounds__(kIbThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
     k_inbatch_bwd(const __grid_constant__ CUtensorMap tmGk, const __grid_constant__ CUtensorMap tmGmn,
                   const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmQb, const BwdArgs a) {
   extern __shared__ unsigned char ib_smem_raw[];
@@ -490,11 +584,11 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   constexpr uint32_t kStageBytes = kKBlkBytes + NA * kAtomBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, which = blockIdx.y, sp = blockIdx.z;
-  const int M = which ? a.Bk : a.Bq;
-  const int Kr = which ? a.Bq : a.Bk;
-  if (mt * kTile >= M) return;  // uniform for the CTA, before any barrier or allocation
+  const int M = which ? a.Bk : a.rows;      // output rows of this GEMM
+  const int Kr = which ? a.rows : a.Bk;     // reduction length
+  if (mt * kTile >= M || sp >= (which ? a.Sk : a.Sq)) return;  // uniform for the CTA, before any barrier or allocation
   const int nkb = (Kr + kBK - 1) / kBK;
-  const int per = (nkb + a.S - 1) / a.S;
+  const int per = (nkb + (which ? a.Sk : a.Sq) - 1) / (which ? a.Sk : a.Sq);
   const int kb0 = sp * per, kb1 = min(nkb, kb0 + per);
   const uint32_t base = (smem_u32(ib_smem_raw) + 1023u) & ~1023u;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NS]), done_bar = smem_u32(&bars[2 * NS]);
@@ -527,13 +621,15 @@ __global__ void __launch_bounds__(kIbThreads, 1)
         const uint32_t As = base + stage * kStageBytes, Bs = As + kKBlkBytes;
         mbar_expect_tx(fb, kStageBytes);
         if (which == 0) {
-          tma_load_2d(As, &tmGk, kb * kBK, mt * kTile, fb);
+          tma_load_2d(As, &tmGk, kb * kBK, mt * kTile, fb);   // G rows are chunk-local
+#pragma unroll
+          for (int n = 0; n < NA; ++n) tma_load_2d(Bs + n * kAtomBytes, &tmKb, n * 64, kb * kBK, fb);
         } else {
           tma_load_2d(As, &tmGmn, mt * kTile, kb * kBK, fb);
           tma_load_2d(As + kAtomBytes, &tmGmn, mt * kTile + 64, kb * kBK, fb);
-        }
 #pragma unroll
-        for (int n = 0; n < NA; ++n) tma_load_2d(Bs + n * kAtomBytes, which ? &tmQb : &tmKb, n * 64, kb * kBK, fb);
+          for (int n = 0; n < NA; ++n) tma_load_2d(Bs + n * kAtomBytes, &tmQb, n * 64, a.i0 + kb * kBK, fb);
+        }
         if (++stage == NS) {
           stage = 0;
           phase ^= 1u;
@@ -565,8 +661,9 @@ __global__ void __launch_bounds__(kIbThreads, 1)
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int row = mt * kTile + q * 32 + lane;
-    float* out = (which ? a.partK : a.partQ) + ((int64_t)sp * M + row) * D;
+    const int row = mt * kTile + q * 32 + lane;  // local output row
+    float* out = which ? a.partK + ((int64_t)(a.chunk * a.Sk + sp) * a.Bk + row) * D
+                       : a.partQ + ((int64_t)sp * a.Bq + a.i0 + row) * D;
     const bool has = kb0 < kb1;
     if (has) {
       mbar_wait(done_bar, 0);
@@ -605,16 +702,16 @@ struct FinishIbArgs {
   const float* partK;
   const __nv_bfloat16* Qh;
   const __nv_bfloat16* Kh;
-  const int32_t* cnt;
+  const float* cnt;
   const float* lossp;
-  const float* lse;
+  const float* lse2;
   const float* diag;
   float* dQ;
   float* dK;
   float* loss;
-  int Bq, Bk, D, off, S, JS, nlossp, softmax;
-  float coef;   // scale / B_norm
-  float inv_bn; // 1 / B_norm
+  int Bq, Bk, D, off, Sq, SkAll, R, nlossp, softmax;
+  float coef;    // scale / B_norm
+  float inv_bn;  // 1 / B_norm
   float scale;
 };
 
@@ -634,9 +731,10 @@ __global__ void __launch_bounds__(256) k_inbatch_finish(const FinishIbArgs a) {
     const int64_t row = e / D4;
     const int c4 = (int)(e % D4);
     const int M = isK ? a.Bk : a.Bq;
+    const int S = isK ? a.SkAll : a.Sq;
     const float* part = isK ? a.partK : a.partQ;
     float4 s = f4_zero();
-    for (int sp = 0; sp < a.S; ++sp) f4_add(s, reinterpret_cast<const float4*>(part + ((int64_t)sp * M + row) * a.D)[c4]);
+    for (int sp = 0; sp < S; ++sp) f4_add(s, __ldcs(reinterpret_cast<const float4*>(part + ((int64_t)sp * M + row) * a.D) + c4));
     // diagonal term: query i and its positive item pos(i) = i + off
     const int64_t i = isK ? row - a.off : row;
     const int64_t other = isK ? i : row + a.off;  // row of the OTHER matrix
@@ -644,9 +742,8 @@ __global__ void __launch_bounds__(256) k_inbatch_finish(const FinishIbArgs a) {
     if (has) {
       float w = 1.f;
       if (!a.softmax) {
-        int c = 0;
-        for (int js = 0; js < a.JS; ++js) c += a.cnt[(int64_t)js * a.Bq + i];
-        w = (float)c;
+        w = 0.f;
+        for (int r = 0; r < a.R; ++r) w += a.cnt[(int64_t)r * a.Bq + i];
       }
       const float4 o = bf16x4_to_f4((isK ? a.Qh : a.Kh) + other * a.D + 4 * c4);
       s.x = fmaf(-w, o.x, s.x);
@@ -664,7 +761,7 @@ __global__ void __launch_bounds__(256) k_inbatch_finish(const FinishIbArgs a) {
       for (int i = threadIdx.x; i < a.Bq; i += blockDim.x) {
         const int64_t pj = (int64_t)i + a.off;
         const float pos = (pj >= 0 && pj < a.Bk) ? a.scale * a.diag[i] : 0.f;
-        acc += (double)(a.lse[i] - pos);
+        acc += (double)(a.lse2[i] * 0.6931471805599453f - pos);
       }
     } else {
       for (int i = threadIdx.x; i < a.nlossp; i += blockDim.x) acc += (double)a.lossp[i];
@@ -711,7 +808,7 @@ bool ib_cfg_ok(const EsrInbatchCfg* c) {
   if (c->Bq <= 0 || c->Bk <= 0 || c->Bq > (1 << 20) || c->Bk > (1 << 20)) return false;
   if (c->D != 64 && c->D != 128 && c->D != 192 && c->D != 256) return false;
   if (c->loss_kind != ESR_LOSS_HINGE && c->loss_kind != ESR_LOSS_SOFTMAX) return false;
-  if (!(c->b_norm > 0.f) || !(c->scale > 0.f)) return false;
+  if (!(c->b_norm > 0.f) || !(c->scale > 0.f) || c->chunk_rows < 0 || c->splits < 0) return false;
   return true;
 }
 
@@ -756,7 +853,7 @@ int launch_bwd(const CUtensorMap& gk, const CUtensorMap& gmn, const CUtensorMap&
   const size_t smem = (size_t)NS * (kKBlkBytes + NA * kAtomBytes) + 1024;
   const int rc = set_smem(k_inbatch_bwd<NA, NS>, smem);
   if (rc != ESR_OK) return rc;
-  k_inbatch_bwd<NA, NS><<<grid, kIbThreads, smem, st>>>(gk, gmn, kb, qb, ba);
+  k_inbatch_bwd<NA, NS><<<grid, kBwdThreads, smem, st>>>(gk, gmn, kb, qb, ba);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
@@ -771,19 +868,21 @@ extern "C" size_t esr_inbatch_workspace_bytes(const EsrInbatchCfg* cfg) {
   return carve_ib(nullptr, make_plan(cfg), nullptr) + 256;
 }
 
-extern "C" int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out /* [8] */) {
+extern "C" int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out /* [10] */) {
   ESR_REQUIRE(ib_cfg_ok(cfg) && out);
   const IbPlan p = make_plan(cfg);
   IbWs w;
   carve_ib(nullptr, p, &w);
-  out[0] = (int64_t)reinterpret_cast<uintptr_t>(w.G);     // byte offset of G (bf16 [Bq][ldG])
+  out[0] = (int64_t)reinterpret_cast<uintptr_t>(w.G);     // byte offset of G (bf16 [Bc][ldG], LAST chunk processed)
   out[1] = p.ldG;
   out[2] = (int64_t)reinterpret_cast<uintptr_t>(w.diag);  // float [Bq]
-  out[3] = (int64_t)reinterpret_cast<uintptr_t>(w.cnt);   // int32 [JS][Bq]
-  out[4] = p.JS;
-  out[5] = (int64_t)reinterpret_cast<uintptr_t>(w.lse);   // float [Bq]
-  out[6] = p.S;
+  out[3] = (int64_t)reinterpret_cast<uintptr_t>(w.cnt);   // float [R][Bq]
+  out[4] = p.R;
+  out[5] = (int64_t)reinterpret_cast<uintptr_t>(w.lse2);  // float [Bq], log2 domain
+  out[6] = p.n_chunks;
   out[7] = (int64_t)reinterpret_cast<uintptr_t>(w.Qh);    // bf16 [Bq][D]
+  out[8] = p.Bc;
+  out[9] = p.Sq * 100 + p.Sk;
   return ESR_OK;
 }
 
@@ -800,11 +899,10 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   carve_ib(ws, p, &w);
   const int softmax = cfg->loss_kind == ESR_LOSS_SOFTMAX;
 
-  CUtensorMap tmQ, tmK, tmGk, tmGmn, tmKb, tmQb;
-  const bool ok = make_tmap(&tmQ, w.Qh, p.D, p.Bq, p.D, kBK, kTile) && make_tmap(&tmK, w.Kh, p.D, p.Bk, p.D, kBK, kTile) &&
-                  make_tmap(&tmGk, w.G, p.Bk, p.Bq, p.ldG, kBK, kTile) && make_tmap(&tmGmn, w.G, p.Bk, p.Bq, p.ldG, 64, kBK) &&
-                  make_tmap(&tmKb, w.Kh, p.D, p.Bk, p.D, 64, kBK) && make_tmap(&tmQb, w.Qh, p.D, p.Bq, p.D, 64, kBK);
-  if (!ok) return ESR_ENOTSUP;
+  CUtensorMap tmQ, tmK, tmKb, tmQb;
+  if (!(make_tmap(&tmQ, w.Qh, p.D, p.Bq, p.D, kBK, kTile) && make_tmap(&tmK, w.Kh, p.D, p.Bk, p.D, kBK, kTile) &&
+        make_tmap(&tmKb, w.Kh, p.D, p.Bk, p.D, 64, kBK) && make_tmap(&tmQb, w.Qh, p.D, p.Bq, p.D, 64, kBK)))
+    return ESR_ENOTSUP;
 
   const int nmax = p.Bq > p.Bk ? p.Bq : p.Bk;
   k_inbatch_cast<<<(unsigned)ceil_div(nmax, 8), 256, 0, st>>>(Q, K, p.Bq, p.Bk, p.D, p.off, w.Qh, w.Kh, w.diag);
@@ -816,24 +914,21 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   sa.ldG = p.ldG;
   sa.cnt = w.cnt;
   sa.stats = w.stats;
-  sa.lse = w.lse;
+  sa.lse2 = w.lse2;
   sa.lossp = w.lossp;
   sa.Bq = p.Bq;
   sa.Bk = p.Bk;
   sa.off = p.off;
   sa.n_jb = p.n_jb;
   sa.j_per = p.j_per;
+  sa.ib0 = 0;
   sa.margin = cfg->margin;
   sa.scale = cfg->scale;
-  const dim3 sgrid(p.n_ib, p.JS);
   int rc;
-  if (!softmax) {
-    if ((rc = launch_scores_d(p.D, 0, tmQ, tmK, sa, sgrid, st)) != ESR_OK) return rc;
-  } else {
-    if ((rc = launch_scores_d(p.D, 1, tmQ, tmK, sa, sgrid, st)) != ESR_OK) return rc;
-    k_inbatch_lse<<<(unsigned)ceil_div(p.Bq, 256), 256, 0, st>>>(w.stats, p.JS, p.Bq, w.lse);
+  if (softmax) {  // row statistics of the whole batch first (no G traffic), then logsumexp
+    if ((rc = launch_scores_d(p.D, 1, tmQ, tmK, sa, dim3(p.n_ib, p.JS), st)) != ESR_OK) return rc;
+    k_inbatch_lse<<<(unsigned)ceil_div(p.Bq, 256), 256, 0, st>>>(w.stats, p.R, p.Bq, w.lse2);
     ESR_LAUNCH_CHECK();
-    if ((rc = launch_scores_d(p.D, 2, tmQ, tmK, sa, sgrid, st)) != ESR_OK) return rc;
   }
 
   BwdArgs ba;
@@ -841,15 +936,30 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   ba.partK = w.partK;
   ba.Bq = p.Bq;
   ba.Bk = p.Bk;
-  ba.S = p.S;
-  const dim3 bgrid(p.n_ib > p.n_jb ? p.n_ib : p.n_jb, 2, p.S);
-  switch (p.D) {
-    case 64: rc = launch_bwd<1, 6>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
-    case 128: rc = launch_bwd<2, 6>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
-    case 192: rc = launch_bwd<3, 4>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
-    default: rc = launch_bwd<4, 4>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
+  ba.Sq = p.Sq;
+  ba.Sk = p.Sk;
+  for (int c = 0; c < p.n_chunks; ++c) {
+    const int ib0 = c * p.n_ic;
+    const int n_ic = p.n_ib - ib0 < p.n_ic ? p.n_ib - ib0 : p.n_ic;
+    const int i0 = ib0 * kTile;
+    const int rows = p.Bq - i0 < n_ic * kTile ? p.Bq - i0 : n_ic * kTile;
+    sa.ib0 = ib0;
+    if ((rc = launch_scores_d(p.D, softmax ? 2 : 0, tmQ, tmK, sa, dim3(n_ic, p.JS), st)) != ESR_OK) return rc;
+    CUtensorMap tmGk, tmGmn;  // this chunk's rows only: rows beyond `rows` read as zero
+    if (!(make_tmap(&tmGk, w.G, p.Bk, rows, p.ldG, kBK, kTile) && make_tmap(&tmGmn, w.G, p.Bk, rows, p.ldG, 64, kBK)))
+      return ESR_ENOTSUP;
+    ba.i0 = i0;
+    ba.rows = rows;
+    ba.chunk = c;
+    const dim3 bgrid(n_ic > p.n_jb ? n_ic : p.n_jb, 2, p.Sq > p.Sk ? p.Sq : p.Sk);
+    switch (p.D) {
+      case 64: rc = launch_bwd<1, 6>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
+      case 128: rc = launch_bwd<2, 6>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
+      case 192: rc = launch_bwd<3, 4>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
+      default: rc = launch_bwd<4, 4>(tmGk, tmGmn, tmKb, tmQb, ba, bgrid, st); break;
+    }
+    if (rc != ESR_OK) return rc;
   }
-  if (rc != ESR_OK) return rc;
 
   FinishIbArgs fa;
   fa.partQ = w.partQ;
@@ -858,7 +968,7 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   fa.Kh = w.Kh;
   fa.cnt = w.cnt;
   fa.lossp = w.lossp;
-  fa.lse = w.lse;
+  fa.lse2 = w.lse2;
   fa.diag = w.diag;
   fa.dQ = dQ;
   fa.dK = dK;
@@ -867,8 +977,9 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   fa.Bk = p.Bk;
   fa.D = p.D;
   fa.off = p.off;
-  fa.S = p.S;
-  fa.JS = p.JS;
+  fa.Sq = p.Sq;
+  fa.SkAll = p.n_chunks * p.Sk;
+  fa.R = p.R;
   fa.nlossp = p.n_ib * p.JS;
   fa.softmax = softmax;
   fa.coef = cfg->scale / cfg->b_norm;

@@ -284,7 +284,8 @@ class InBatchScorer:
     pinterest/models.py:67-72 + pinterest/train_shop_the_look.py:99-104 to in-batch negatives
     (BASELINE.json configs[2], configs[3]).  The positive of query ``i`` is item ``i + diag_off``."""
 
-    def __init__(self, Bq, D, Bk=None, loss="hinge", diag_off=0, margin=1.0, scale=1.0, b_norm=None, splits=0, device=None):
+    def __init__(self, Bq, D, Bk=None, loss="hinge", diag_off=0, margin=1.0, scale=1.0, b_norm=None, splits=0,
+                 chunk_rows=0, device=None):
         self.device = _dev(device)
         cfg = L.EsrInbatchCfg()
         cfg.struct_size = C.sizeof(L.EsrInbatchCfg)
@@ -293,6 +294,7 @@ class InBatchScorer:
         cfg.diag_off, cfg.D, cfg.splits = int(diag_off), int(D), int(splits)
         cfg.margin, cfg.scale = float(margin), float(scale)
         cfg.b_norm = float(b_norm if b_norm is not None else Bq)
+        cfg.chunk_rows = int(chunk_rows)
         self.cfg = cfg
         self.Bq, self.Bk, self.D = cfg.Bq, cfg.Bk, cfg.D
         self.ws_bytes = int(L.lib().esr_inbatch_workspace_bytes(C.byref(cfg)))
@@ -313,12 +315,19 @@ class InBatchScorer:
         return self.loss, self.dQ, self.dK
 
     def debug_views(self):
-        """(G bf16 [Bq, Bk], diag f32 [Bq], cnt i32 [JS, Bq], lse f32 [Bq]) views into the workspace (tests)."""
-        o = (C.c_int64 * 8)()
+        """(G bf16 [rows of the LAST chunk, Bk], diag f32 [Bq], cnt f32 [R, Bq], lse f32 [Bq] (natural log)) out of
+        the workspace (tests; pass chunk_rows >= Bq to keep the whole dL/dS matrix in one chunk)."""
+        o = (C.c_int64 * 10)()
         L.check(L.lib().esr_inbatch_ws_layout(C.byref(self.cfg), o), "esr_inbatch_ws_layout")
-        g_off, ldG, d_off, c_off, JS, l_off = int(o[0]), int(o[1]), int(o[2]), int(o[3]), int(o[4]), int(o[5])
-        G = self.ws[g_off:g_off + self.Bq * ldG * 2].view(torch.bfloat16).view(self.Bq, ldG)[:, :self.Bk]
+        g_off, ldG, d_off, c_off, R, l_off, n_chunks, _, Bc = (int(o[k]) for k in range(9))
+        rows = self.Bq - (n_chunks - 1) * Bc
+        G = self.ws[g_off:g_off + rows * ldG * 2].view(torch.bfloat16).view(rows, ldG)[:, :self.Bk]
         diag = self.ws[d_off:d_off + 4 * self.Bq].view(torch.float32)
-        cnt = self.ws[c_off:c_off + 4 * JS * self.Bq].view(torch.int32).view(JS, self.Bq)
-        lse = self.ws[l_off:l_off + 4 * self.Bq].view(torch.float32)
+        cnt = self.ws[c_off:c_off + 4 * R * self.Bq].view(torch.float32).view(R, self.Bq)
+        lse = self.ws[l_off:l_off + 4 * self.Bq].view(torch.float32) * 0.6931471805599453
         return G, diag, cnt, lse
+
+    def plan(self):
+        o = (C.c_int64 * 10)()
+        L.check(L.lib().esr_inbatch_ws_layout(C.byref(self.cfg), o), "esr_inbatch_ws_layout")
+        return dict(n_chunks=int(o[6]), chunk_rows=int(o[8]), R=int(o[4]), Sq=int(o[9]) // 100, Sk=int(o[9]) % 100)

@@ -1,0 +1,135 @@
+"""In-batch-negative trainers of BASELINE.json configs[2] and configs[3] on libesr.
+
+The reference scores explicit negatives (spotify/train_spotify.py:77-106: 64 sampled tracks per
+playlist; pinterest/train_shop_the_look.py:93-109: one pre-sampled negative product per pair); the
+north star replaces them by the other items of the batch:
+
+* ``SharedTableInBatch``  -- configs[2]: ONE id-embedding table (2M x 128), a batch of (query id, item id)
+  pairs, step = gather rows -> B x B scores + loss + dQ/dK on the tensor cores
+  (``esr_inbatch_fwd_bwd_bf16``) -> per-row segment sum of the 2B gradient rows -> sparse Adagrad.
+* ``TwoTowerInBatch``     -- configs[3]: scene-id and product-id tables (x 256) each followed by a 2-layer
+  MLP tower ``Linear -> ReLU -> Linear`` (the north-star substitute for the CNN towers of
+  pinterest/models.py:23-46), same scorer; tables take sparse Adagrad, tower weights ``optax.adam``
+  (pinterest/train_shop_the_look.py:175).  The tower GEMMs are plain library GEMMs (cuBLAS through torch).
+
+Contract: oracle/inbatch.py (``shared_table_step`` / ``two_tower_step``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import engine
+
+
+class _RowUpdater:
+    """Gradient rows (n, D) keyed by row id -> deterministic per-row sum -> sparse Adagrad in place."""
+
+    def __init__(self, table: engine.EmbeddingTable, n_slots: int, lr: float, eps: float = 1e-7):
+        self.table, self.lr, self.eps = table, float(lr), float(eps)
+        self.plan = engine.IndexPlan(n_slots, table.V, table.device, with_partner=False)
+        self.gsum = torch.empty(n_slots, table.D, dtype=torch.float32, device=table.device)
+
+    def apply(self, ids_i32, grads, stream=None):
+        self.plan.build(ids_i32, stream)
+        L.check(L.lib().esr_segment_sum_rows_f32(C.byref(self.plan.s), self.table.D, L.ptr(grads), None, L.ptr(self.gsum), None,
+                                                 L.stream_ptr(stream)), "esr_segment_sum_rows_f32")
+        engine.sparse_adagrad(self.table, self.plan.uniq, self.plan.n_uniq, self.gsum, None, self.lr, self.eps, stream)
+
+
+class SharedTableInBatch:
+    """configs[2]: Spotify-style skip-gram over one table with in-batch negatives."""
+
+    def __init__(self, table: engine.EmbeddingTable, B: int, lr: float = 0.05, loss: str = "hinge", margin: float = 1.0,
+                 scale: float = 1.0):
+        assert not table.sparse and table.acc is not None, "single-buffer table with an Adagrad slot (sparse=False, adagrad=True)"
+        self.table, self.B = table, int(B)
+        dev = table.device
+        self.scorer = engine.InBatchScorer(B, table.D, loss=loss, margin=margin, scale=scale, device=dev)
+        self.X = torch.empty(2 * self.B, table.D, dtype=torch.float32, device=dev)      # [Q ; K] gathered rows
+        self.dX = torch.empty(2 * self.B, table.D, dtype=torch.float32, device=dev)     # [dQ ; dK]
+        self.scorer.dQ, self.scorer.dK = self.dX[:self.B], self.dX[self.B:]
+        self.upd = _RowUpdater(table, 2 * self.B, lr)
+
+    def step(self, ids, stream=None):
+        """ids: int32 CUDA (2, B) = [query ids ; item ids].  Returns the device loss scalar."""
+        flat = ids.reshape(-1)
+        assert flat.dtype == torch.int32 and flat.is_cuda and flat.numel() == 2 * self.B
+        L.check(L.lib().esr_table_gather_f32(C.byref(self.table.struct()), L.ptr(flat), 2 * self.B, L.ptr(self.X),
+                                             L.stream_ptr(stream)), "esr_table_gather_f32")
+        loss, _, _ = self.scorer.run(self.X[:self.B], self.X[self.B:], stream)
+        self.upd.apply(flat, self.dX, stream)
+        return loss
+
+
+class MLPTower:
+    """``Linear(D, H) -> ReLU -> Linear(H, O)`` with explicit backward; weights updated by ``optax.adam``
+    semantics through ``esr_dense_adam_f32``."""
+
+    def __init__(self, D, H, O, gen, device, lr=1e-3):
+        mk = lambda i, o: (torch.randn(i, o, generator=gen) / np.sqrt(i)).to(device)
+        self.p = {"W1": mk(D, H), "b1": torch.zeros(H, device=device), "W2": mk(H, O), "b2": torch.zeros(O, device=device)}
+        self.g = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.mu = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.nu = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.count, self.lr = 0, float(lr)
+
+    def forward(self, x):
+        self.x = x
+        self.h = torch.relu(torch.addmm(self.p["b1"], x, self.p["W1"]))
+        return torch.addmm(self.p["b2"], self.h, self.p["W2"])
+
+    def backward(self, dy):
+        g = self.g
+        torch.mm(self.h.t(), dy, out=g["W2"])
+        torch.sum(dy, 0, out=g["b2"])
+        dh = torch.mm(dy, self.p["W2"].t())
+        dh.mul_(self.h > 0)
+        torch.mm(self.x.t(), dh, out=g["W1"])
+        torch.sum(dh, 0, out=g["b1"])
+        return torch.mm(dh, self.p["W1"].t())
+
+    def update(self):
+        self.count += 1
+        for k in self.p:
+            engine.dense_adam(self.p[k], self.g[k], self.mu[k], self.nu[k], self.lr, self.count)
+
+
+class TwoTowerInBatch:
+    """configs[3]: scene / product id tables + MLP towers, B x B in-batch negatives."""
+
+    def __init__(self, scene_table, product_table, B, hidden=None, out=None, lr=0.05, tower_lr=1e-3, loss="softmax",
+                 margin=1.0, scale=1.0, seed=0):
+        for t in (scene_table, product_table):
+            assert not t.sparse and t.acc is not None
+        self.ts, self.tp, self.B = scene_table, product_table, int(B)
+        dev = scene_table.device
+        D = scene_table.D
+        H = int(hidden or D)
+        O = int(out or D)
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+        self.scene_tower = MLPTower(D, H, O, gen, dev, tower_lr)
+        self.product_tower = MLPTower(D, H, O, gen, dev, tower_lr)
+        self.scorer = engine.InBatchScorer(B, O, loss=loss, margin=margin, scale=scale, device=dev)
+        self.xs = torch.empty(self.B, D, dtype=torch.float32, device=dev)
+        self.xp = torch.empty(self.B, D, dtype=torch.float32, device=dev)
+        self.us = _RowUpdater(scene_table, self.B, lr)
+        self.up = _RowUpdater(product_table, self.B, lr)
+
+    def step(self, scene_ids, product_ids):
+        """int32 CUDA (B,) each.  Returns the device loss scalar."""
+        self.ts.gather(scene_ids, out=self.xs)
+        self.tp.gather(product_ids, out=self.xp)
+        q = self.scene_tower.forward(self.xs)
+        k = self.product_tower.forward(self.xp)
+        loss, dq, dk = self.scorer.run(q.contiguous(), k.contiguous())
+        dxs = self.scene_tower.backward(dq)
+        dxp = self.product_tower.backward(dk)
+        self.scene_tower.update()
+        self.product_tower.update()
+        self.us.apply(scene_ids, dxs.contiguous())
+        self.up.apply(product_ids, dxp.contiguous())
+        return loss

@@ -266,8 +266,8 @@ int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, const float* a
  *   ESR_LOSS_SOFTMAX : loss = (1/b_norm) sum_i [logsumexp_j(scale*S_ij) - scale*S_i,pos(i)]
  * Q [Bq, D], K [Bk, D] fp32 row-major (gathered rows / tower outputs), rounded to bf16 (RNE) inside;
  * dQ, dK are the gradients with respect to those inputs (straight-through), fp32.  The fp32 score matrix
- * is never written to memory; the workspace holds a bf16 [Bq, Bk] matrix (hinge: exact {0,1} mask,
- * softmax: probabilities).  D in {64, 128, 192, 256}.  Contract: oracle/inbatch.py.
+ * is never written to memory; the workspace holds one row chunk of the bf16 dL/dS matrix (hinge: exact
+ * {0,1} mask, softmax: probabilities) that the backward contractions read straight back out of L2.  D in {64, 128, 192, 256}.  Contract: oracle/inbatch.py.
  * ------------------------------------------------------------------------------------------ */
 typedef struct EsrInbatchCfg {
   uint32_t struct_size;
@@ -280,14 +280,16 @@ typedef struct EsrInbatchCfg {
   float margin;      /* hinge margin (1.0 in the reference) */
   float scale;       /* score multiplier (1 / temperature); > 0 */
   float b_norm;      /* loss divisor: the GLOBAL number of queries */
-  int32_t reserved;
+  int32_t chunk_rows; /* query rows per pass; 0 => auto (one pass's bf16 dL/dS block stays resident in L2) */
 } EsrInbatchCfg;
 
 size_t esr_inbatch_workspace_bytes(const EsrInbatchCfg* cfg);
 int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const EsrInbatchCfg* cfg, float* dQ, float* dK,
                              float* loss, void* ws, size_t ws_bytes, esr_stream_t stream);
-/* Test / profiling aid: byte offsets inside the workspace of {G, ldG (elements), diag, cnt, JS, lse, S, Qh}. */
-int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out8);
+/* Test / profiling aid, out10 = {byte offset of G (the LAST row chunk processed), ldG (elements), offset of diag,
+ * offset of cnt (float [R][Bq]), R, offset of lse2 (log2 domain), n_chunks, offset of Qh, rows per chunk,
+ * Sq * 100 + Sk}. */
+int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out10);
 
 /* ------------------------------------------------------------------------------------------
  * Row-sharded table over NVLink peer memory (device pointers of every rank's buffers, e.g. from a

@@ -115,3 +115,67 @@ def softmax(Q, K, off=0, scale=1.0, b_norm=None):
     Pb = bf16_round(P)
     dQ, dK = softmax_backward(Pb, Qh, Kh, off, scale, b_norm)
     return loss, dQ, dK, Pb
+
+
+# --------------------------------------------------------------------------------------------------
+# Whole training steps of the in-batch configs (contract of esrecsys_b200/inbatch.py)
+# --------------------------------------------------------------------------------------------------
+def _loss_and_grads(kind, Q, K, margin, scale):
+    if kind == "hinge":
+        loss, dQ, dK, _ = hinge(Q, K, 0, margin, scale)
+    else:
+        loss, dQ, dK, _ = softmax(Q, K, 0, scale)
+    return loss, dQ, dK
+
+
+def _adagrad_rows(E, acc, ids, grads, lr, eps=1e-7):
+    """Batch-synchronous sparse Adagrad: gradients of duplicate ids are summed first (what XLA's
+    scatter-add VJP of jnp.take gives -- SURVEY.md App. A.6), then optax.adagrad on the touched rows."""
+    uniq, inv = np.unique(ids, return_inverse=True)
+    g = np.zeros((uniq.size, E.shape[1]), np.float64)
+    np.add.at(g, inv, grads.astype(np.float64))
+    g = g.astype(np.float32)
+    a = acc[uniq] + g * g
+    E[uniq] = E[uniq] - np.float32(lr) * g * (np.float32(1.0) / np.sqrt(a + np.float32(eps)))
+    acc[uniq] = a
+
+
+def shared_table_step(E, acc, q_ids, k_ids, lr, kind="hinge", margin=1.0, scale=1.0):
+    """configs[2]: one table, (query, item) id pairs, in-batch negatives.  Updates E, acc in place; returns the loss."""
+    loss, dQ, dK = _loss_and_grads(kind, E[q_ids], E[k_ids], margin, scale)
+    _adagrad_rows(E, acc, np.concatenate([q_ids, k_ids]), np.concatenate([dQ, dK]), lr)
+    return loss
+
+
+def mlp_forward(x, p):
+    h = np.maximum(x @ p["W1"] + p["b1"], 0).astype(np.float32)
+    return (h @ p["W2"] + p["b2"]).astype(np.float32), h
+
+
+def mlp_backward(x, h, dy, p):
+    g = {"W2": h.T @ dy, "b2": dy.sum(0)}
+    dh = (dy @ p["W2"].T) * (h > 0)
+    g["W1"] = x.T @ dh
+    g["b1"] = dh.sum(0)
+    return (dh @ p["W1"].T).astype(np.float32), {k: v.astype(np.float32) for k, v in g.items()}
+
+
+def two_tower_step(Es, accs, Ep, accp, ps, pp, opt_s, opt_p, s_ids, p_ids, lr, tower_lr, kind="softmax", margin=1.0,
+                   scale=1.0):
+    """configs[3]: id tables -> 2-layer MLP towers -> in-batch loss; tables sparse Adagrad, towers optax.adam
+    (``opt_*``: dict(count, mu, nu) of dicts).  In place; returns the loss."""
+    from . import optim as oo
+    xs, xp = Es[s_ids], Ep[p_ids]
+    q, hs = mlp_forward(xs, ps)
+    k, hp = mlp_forward(xp, pp)
+    loss, dq, dk = _loss_and_grads(kind, q, k, margin, scale)
+    dxs, gs = mlp_backward(xs, hs, dq, ps)
+    dxp, gp = mlp_backward(xp, hp, dk, pp)
+    for p, g, opt in ((ps, gs, opt_s), (pp, gp, opt_p)):
+        for name in p:
+            p[name], opt["mu"][name], opt["nu"][name], _ = oo.adam_update(p[name], g[name], opt["mu"][name], opt["nu"][name],
+                                                                          opt["count"], tower_lr)
+        opt["count"] += 1
+    _adagrad_rows(Es, accs, s_ids, dxs, lr)
+    _adagrad_rows(Ep, accp, p_ids, dxp, lr)
+    return loss

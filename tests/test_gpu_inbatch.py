@@ -24,6 +24,7 @@ def _data(Bq, Bk, D, seed, spread=1.0):
 
 def _run(Q, K, **kw):
     from esrecsys_b200.engine import InBatchScorer
+    kw.setdefault("chunk_rows", 1 << 20)     # one chunk: the whole dL/dS matrix stays inspectable
     sc = InBatchScorer(Q.shape[0], Q.shape[1], Bk=K.shape[0], **kw)
     loss, dQ, dK = sc.run(torch.from_numpy(Q).cuda(), torch.from_numpy(K).cuda())
     torch.cuda.synchronize()
@@ -100,21 +101,93 @@ def test_splitk_matches_single():
     np.testing.assert_allclose(a[2], b[2], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("kind", ["hinge", "softmax"])
+@pytest.mark.parametrize("Bq,Bk,off,chunk", [(1000, 1000, 0, 256), (700, 1500, 300, 128), (2048, 2048, 0, 512)])
+def test_row_chunks_match_single_pass(kind, Bq, Bk, off, chunk):
+    """The L2-resident row-chunked schedule (the default at large B) against one pass over the whole matrix:
+    same mask / probabilities, only the split of the dK sum differs."""
+    Q, K = _data(Bq, Bk, 128, 6)
+    a = _run(Q, K, loss=kind, diag_off=off)
+    b = _run(Q, K, loss=kind, diag_off=off, chunk_rows=chunk)
+    assert abs(a[0] - b[0]) <= 1e-6 * max(1.0, abs(a[0]))
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-5, atol=1e-5 * np.abs(a[1]).max())
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-5, atol=1e-5 * np.abs(a[2]).max())
+
+
 def test_full_size_properties():
     """BASELINE configs[2] size (B = 8192, D = 128): size-independent checks -- sum_j dS_ij = 0 per row for
     softmax (dQ of a constant K is 0), and the loss of identical rows is log(B)."""
     B, D = 8192, 128
     Q = np.full((B, D), 0.25, np.float32)
     K = np.full((B, D), 0.5, np.float32)
-    loss, dQ, dK, G, *_ = _run(Q, K, loss="softmax")
+    loss, dQ, dK, G, *_ = _run(Q, K, loss="softmax", chunk_rows=0)
     assert abs(loss - np.log(B)) < 1e-4
     # p_ij = 1/B = 2^-13 exactly in bf16 -> dQ_i = (sum_j p_ij K_j - K_i)/B = 0
     assert np.abs(dQ).max() < 1e-9 and np.abs(dK).max() < 1e-9
     Q, K = _data(B, B, D, 7)
+    from esrecsys_b200.engine import InBatchScorer
+    assert InBatchScorer(B, D, chunk_rows=2048).plan()["n_chunks"] == 4
+    auto = _run(Q, K, loss="hinge", chunk_rows=2048)
     loss, dQ, dK, G, diag, cnt, _ = _run(Q, K, loss="hinge")
+    np.testing.assert_allclose(auto[1], dQ, rtol=1e-5, atol=1e-5 * np.abs(dQ).max())
+    np.testing.assert_allclose(auto[2], dK, rtol=1e-5, atol=1e-5 * np.abs(dK).max())
     S, Qh, Kh = oib.scores(Q, K)
     np.testing.assert_allclose(diag, np.diag(S), rtol=1e-5, atol=1e-5)
     gm = G > 0.5
     rdQ, rdK = oib.hinge_backward(gm, Qh, Kh, 0)
     np.testing.assert_allclose(dQ, rdQ, rtol=1e-5, atol=1e-5 * np.abs(rdQ).max())
     np.testing.assert_allclose(dK, rdK, rtol=1e-5, atol=1e-5 * np.abs(rdK).max())
+
+
+@pytest.mark.parametrize("kind", ["hinge", "softmax"])
+def test_shared_table_steps_match_oracle(kind):
+    """configs[2] shape (scaled down): 3 consecutive steps, duplicate-heavy Zipf ids."""
+    from esrecsys_b200 import engine, synth
+    from esrecsys_b200.inbatch import SharedTableInBatch
+    V, D, B, lr = 5000, 128, 512, 0.05
+    rng = np.random.default_rng(11)
+    E = (rng.standard_normal((V, D)) / D ** 0.25).astype(np.float32)
+    q, k = synth.pair_batches(V, V, B, 3, 5)
+    table = engine.EmbeddingTable.from_dense(E, sparse=False, adagrad=True)
+    tr = SharedTableInBatch(table, B, lr=lr, loss=kind)
+    Eo, acc = E.copy(), np.full_like(E, 0.1)
+    for s in range(3):
+        ids = torch.from_numpy(np.stack([q[s], k[s]])).cuda()
+        got = float(tr.step(ids).item())
+        want = oib.shared_table_step(Eo, acc, q[s], k[s], lr, kind)
+        assert abs(got - want) <= 2e-5 * max(1.0, abs(want))
+    # Rows match to 1e-5 except where a hinge-mask bit sits inside the rounding band of the two summation orders
+    # (or a bf16 probability flips by one ulp): those rows move by ~lr * delta_g / sqrt(acc), bounded below.
+    got, gacc = table.rows0.cpu().numpy(), table.acc.cpu().numpy()
+    bad = np.abs(got - Eo) > 1e-5 + 1e-5 * np.abs(Eo)
+    assert bad.mean() < 2e-3, bad.mean()
+    assert np.abs(got - Eo).max() < 1e-3
+    np.testing.assert_allclose(gacc, acc, rtol=2e-3, atol=1e-6)
+
+
+def test_two_tower_steps_match_oracle():
+    """configs[3] shape (scaled down): id tables + MLP towers + softmax in-batch loss, 3 steps."""
+    from esrecsys_b200 import engine, synth
+    from esrecsys_b200.inbatch import TwoTowerInBatch
+    V, D, B = 3000, 64, 256
+    rng = np.random.default_rng(12)
+    Es = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+    Ep = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+    ts = engine.EmbeddingTable.from_dense(Es, sparse=False, adagrad=True)
+    tp = engine.EmbeddingTable.from_dense(Ep, sparse=False, adagrad=True)
+    tr = TwoTowerInBatch(ts, tp, B, lr=0.05, tower_lr=1e-3, loss="softmax", scale=4.0, seed=3)
+    ps = {k: v.cpu().numpy().copy() for k, v in tr.scene_tower.p.items()}
+    pp = {k: v.cpu().numpy().copy() for k, v in tr.product_tower.p.items()}
+    mk = lambda p: dict(count=0, mu={k: np.zeros_like(v) for k, v in p.items()}, nu={k: np.zeros_like(v) for k, v in p.items()})
+    os_, op_ = mk(ps), mk(pp)
+    Eso, Epo = Es.copy(), Ep.copy()
+    accs, accp = np.full_like(Es, 0.1), np.full_like(Ep, 0.1)
+    s_ids, p_ids = synth.pair_batches(V, V, B, 3, 9)
+    for s in range(3):
+        got = float(tr.step(torch.from_numpy(s_ids[s]).cuda(), torch.from_numpy(p_ids[s]).cuda()).item())
+        want = oib.two_tower_step(Eso, accs, Epo, accp, ps, pp, os_, op_, s_ids[s], p_ids[s], 0.05, 1e-3, "softmax", 1.0, 4.0)
+        assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (s, got, want)
+    np.testing.assert_allclose(ts.rows0.cpu().numpy(), Eso, rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(tp.rows0.cpu().numpy(), Epo, rtol=1e-3, atol=2e-4)
+    for k in ps:
+        np.testing.assert_allclose(tr.scene_tower.p[k].cpu().numpy(), ps[k], rtol=1e-3, atol=2e-4)
