@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "esr_common.cuh"
 
@@ -84,6 +85,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(x), "r"(y)
                : "memory");
+}
+// 2-D tiled TMA store (SASS UTMASTG): smem box -> global at element coords (x, y); rows/columns outside the
+// tensor's extent are clipped.  Bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the smem source of every committed store group has been read (the staging buffer may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -293,6 +309,7 @@ struct ScoreArgs {
   float* lossp;
   int Bq, Bk, off, n_jb, j_per, ib0;  // ib0: first i-block of the chunk
   float margin, scale;
+  int debug;  // profiling probes (ESR_IB_DEBUG): 1 skip epilogue math, 2 skip TMEM loads, 4 skip MMAs, 8 skip TMA
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -305,7 +322,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 template <int KB, int NS, int MODE>
 __global__ void __launch_bounds__(kIbThreads, 1)
-    k_inbatch_scores(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const ScoreArgs a) {
+    k_inbatch_scores(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmGst, const ScoreArgs a) {
   extern __shared__ unsigned char ib_smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * NS + 4];
   __shared__ uint32_t tmem_slot;
@@ -315,16 +333,25 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   const uint32_t q_smem = base;
   const uint32_t k_smem = base + KB * kKBlkBytes;
   constexpr uint32_t kStageBytes = KB * kKBlkBytes;
+  // per epilogue warp: a [32 rows][128 B] SWIZZLE_128B staging block of its 32 x 64 bf16 piece of G
+  const uint32_t stg_smem = k_smem + NS * kStageBytes + (uint32_t)(warp >= 4 ? warp - 4 : 0) * 4096u;
   const uint32_t q_bar = smem_u32(&bars[0]);
   const uint32_t full0 = smem_u32(&bars[1]), empty0 = smem_u32(&bars[1 + NS]);
   const uint32_t tfull0 = smem_u32(&bars[1 + 2 * NS]), tempty0 = smem_u32(&bars[1 + 2 * NS + 2]);
   const int ib = a.ib0 + blockIdx.x, js = blockIdx.y;
   const int jb0 = js * a.j_per;
   const int jb1 = min(a.n_jb, jb0 + a.j_per);
+  // Every CTA of a column range walks the same K tiles; started together they would all hit the same L2
+  // lines at the same time (measured: 3500 clk per tile, LTS 65 % busy on a 2 MB operand).  Rotate the
+  // starting tile per i-block so concurrent CTAs read different tiles.
+  const int nt = jb1 - jb0;
+  const int rot = nt > 0 ? (int)((blockIdx.x * 5u) % (unsigned)nt) : 0;
+#define ESR_JB(it) (jb0 + ((it) + rot >= nt ? (it) + rot - nt : (it) + rot))
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
+    if (MODE != 1) tma_prefetch_desc(&tmGst);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_bar, 1);
@@ -352,12 +379,17 @@ __global__ void __launch_bounds__(kIbThreads, 1)
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(q_smem + kb * kKBlkBytes, &tmQ, kb * kBK, ib * kTile, q_bar);
       int stage = 0;
       uint32_t phase = 0;
-      for (int jb = jb0; jb < jb1; ++jb) {
+      for (int it = 0; it < nt; ++it) {
+        const int jb = ESR_JB(it);
         mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-        mbar_expect_tx(full0 + 8u * stage, kStageBytes);
+        if (a.debug & 8) {
+          mbar_arrive(full0 + 8u * stage);
+        } else {
+          mbar_expect_tx(full0 + 8u * stage, kStageBytes);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(k_smem + stage * kStageBytes + kb * kKBlkBytes, &tmK, kb * kBK, jb * kTile, full0 + 8u * stage);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(k_smem + stage * kStageBytes + kb * kKBlkBytes, &tmK, kb * kBK, jb * kTile, full0 + 8u * stage);
+        }
         if (++stage == NS) {
           stage = 0;
           phase ^= 1u;
@@ -371,15 +403,14 @@ __global__ void __launch_bounds__(kIbThreads, 1)
       mbar_wait(q_bar, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int jb = jb0; jb < jb1; ++jb, ++it) {
+      for (int it = 0; it < nt; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < ((a.debug & 4) ? 0 : KB); ++kb) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = make_sdesc(q_smem + kb * kKBlkBytes + k * 32u, 0u, 1024u);
@@ -411,11 +442,11 @@ __global__ void __launch_bounds__(kIbThreads, 1)
     const float nlse2 = (rv && MODE == 2) ? -a.lse2[i] : 0.f;
     float ls0 = 0.f, ls1 = 0.f, cn0 = 0.f, cn1 = 0.f;
     float mx = -INFINITY, sm = 0.f;
-    __nv_bfloat16* const grow = a.G + (int64_t)(blockIdx.x * kTile + r) * a.ldG;
     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
 
     // one 32-column block of scores (registers v) at columns jbase..jbase+31
     auto consume = [&](const uint32_t (&v)[32], int jbase) {
+      if (a.debug & 1) return;
       // warp-uniform: does this 32x32 block touch the right edge, or (hinge) the positives' diagonal?
       const bool edge = jbase + 32 > a.Bk;
       const bool ondiag = MODE == 0 && (i_first + a.off < jbase + 32) && (i_first + 31 + a.off >= jbase);
@@ -449,10 +480,15 @@ __global__ void __launch_bounds__(kIbThreads, 1)
             pk[e >> 1] = bits;
           }
         }
-        if (rv) {
-          uint4* dst = reinterpret_cast<uint4*>(grow + jbase);
+        // Direct stores would be 16 B per lane into 32 different rows: 32 LSU wavefronts per instruction
+        // (measured: 2000 clk per tile, the whole kernel).  Stage the warp's 32 x 64 block in smem in the
+        // TMA 128-byte swizzle (conflict-free st.shared.v4), one TMA store per tile writes it out.
+        {
+          const int c0 = ((jbase >> 5) & 1) * 4;  // first 16-byte chunk of this 32-column block inside the 128-byte row
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
+          for (int k4 = 0; k4 < 4; ++k4)
+            st_shared_v4(stg_smem + (uint32_t)lane * 128u + (uint32_t)(((c0 + k4) ^ (lane & 7)) * 16),
+                         make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]));
         }
       } else if (MODE == 1) {
         float cm0 = -INFINITY, cm1 = -INFINITY;
@@ -488,10 +524,15 @@ __global__ void __launch_bounds__(kIbThreads, 1)
           }
           pk[e >> 1] = pack_bf16(p0, p1);
         }
-        if (rv) {
-          uint4* dst = reinterpret_cast<uint4*>(grow + jbase);
+        // Direct stores would be 16 B per lane into 32 different rows: 32 LSU wavefronts per instruction
+        // (measured: 2000 clk per tile, the whole kernel).  Stage the warp's 32 x 64 block in smem in the
+        // TMA 128-byte swizzle (conflict-free st.shared.v4), one TMA store per tile writes it out.
+        {
+          const int c0 = ((jbase >> 5) & 1) * 4;  // first 16-byte chunk of this 32-column block inside the 128-byte row
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) dst[k4] = make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]);
+          for (int k4 = 0; k4 < 4; ++k4)
+            st_shared_v4(stg_smem + (uint32_t)lane * 128u + (uint32_t)(((c0 + k4) ^ (lane & 7)) * 16),
+                         make_uint4(pk[4 * k4], pk[4 * k4 + 1], pk[4 * k4 + 2], pk[4 * k4 + 3]));
         }
       }
     };
@@ -500,6 +541,7 @@ __global__ void __launch_bounds__(kIbThreads, 1)
       const int acc = it & 1;
       mbar_wait(tfull0 + 8u * acc, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
+      if (a.debug & 2) return;
       tmem_ld32(tcol + (uint32_t)(acc * kTile), va);
       tmem_ld32(tcol + (uint32_t)(acc * kTile + 32), vb);
     };
@@ -510,22 +552,41 @@ __global__ void __launch_bounds__(kIbThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8u * (it & 1));
     };
-    const int nt = jb1 - jb0;
+    // staging buffer hand-over around the two consume() calls of a tile
+    auto stage_begin = [&]() {
+      if (MODE == 1 || (a.debug & 1)) return;
+      if (lane == 0) tma_store_wait_read();  // the previous tile's store has read the buffer
+      __syncwarp();
+    };
+    auto stage_end = [&](int jb) {
+      if (MODE == 1 || (a.debug & 1)) return;
+      fence_async_smem();  // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmGst, stg_smem, jb * kTile + half * 64, (int)blockIdx.x * kTile + q * 32);
+        tma_store_commit();
+      }
+    };
     uint32_t a0[32], a1[32], b0[32], b1[32];
     if (nt > 0) issue(0, a0, a1);
 #pragma unroll 1
     for (int it = 0; it < nt; it += 2) {
       landed(it);
       if (it + 1 < nt) issue(it + 1, b0, b1);
-      consume(a0, (jb0 + it) * kTile + half * 64);
-      consume(a1, (jb0 + it) * kTile + half * 64 + 32);
+      stage_begin();
+      consume(a0, ESR_JB(it) * kTile + half * 64);
+      consume(a1, ESR_JB(it) * kTile + half * 64 + 32);
+      stage_end(ESR_JB(it));
       if (it + 1 < nt) {
         landed(it + 1);
         if (it + 2 < nt) issue(it + 2, a0, a1);
-        consume(b0, (jb0 + it + 1) * kTile + half * 64);
-        consume(b1, (jb0 + it + 1) * kTile + half * 64 + 32);
+        stage_begin();
+        consume(b0, ESR_JB(it + 1) * kTile + half * 64);
+        consume(b1, ESR_JB(it + 1) * kTile + half * 64 + 32);
+        stage_end(ESR_JB(it + 1));
       }
     }
+    if (MODE != 1 && lane == 0) tma_store_wait_all();  // global writes complete before the kernel ends
     const int range = js * 2 + half;
     if (MODE == 0) {
       if (rv) a.cnt[(int64_t)range * a.Bq + i] = cn0 + cn1;
@@ -542,6 +603,7 @@ __global__ void __launch_bounds__(kIbThreads, 1)
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+#undef ESR_JB
 }
 
 // log2-domain logsumexp_i from the per-range statistics (fixed order).
@@ -590,6 +652,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   const int nkb = (Kr + kBK - 1) / kBK;
   const int per = (nkb + (which ? a.Sk : a.Sq) - 1) / (which ? a.Sk : a.Sq);
   const int kb0 = sp * per, kb1 = min(nkb, kb0 + per);
+  // CTAs of different m-tiles share the X operand: rotate the k-block order per m-tile so they do not
+  // all fetch the same L2 lines at the same time (the sum order stays fixed per CTA => deterministic)
+  const int nk = kb1 - kb0;
+  const int rot = nk > 0 ? (int)((mt * 7u) % (unsigned)nk) : 0;
+#define ESR_KB(t) (kb0 + ((t) + rot >= nk ? (t) + rot - nk : (t) + rot))
   const uint32_t base = (smem_u32(ib_smem_raw) + 1023u) & ~1023u;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NS]), done_bar = smem_u32(&bars[2 * NS]);
 
@@ -615,7 +682,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int t = 0; t < nk; ++t) {
+        const int kb = ESR_KB(t);
         mbar_wait(empty0 + 8u * stage, phase ^ 1u);
         const uint32_t fb = full0 + 8u * stage;
         const uint32_t As = base + stage * kStageBytes, Bs = As + kKBlkBytes;
@@ -641,7 +709,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       const uint32_t idesc = which ? make_idesc(kTile, D, 1, 1) : make_idesc(kTile, D, 0, 1);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int t = 0; t < nk; ++t) {
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         const uint32_t As = base + stage * kStageBytes, Bs = As + kKBlkBytes;
@@ -649,7 +717,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         for (int k = 0; k < kBK / 16; ++k) {
           const uint64_t ad = which ? make_sdesc(As + k * 2048u, kAtomBytes, 1024u) : make_sdesc(As + k * 32u, 0u, 1024u);
           const uint64_t bd = make_sdesc(Bs + k * 2048u, kAtomBytes, 1024u);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, ad, bd, idesc, (t > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty0 + 8u * stage);
         if (++stage == NS) {
@@ -692,6 +760,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, kCols);
+#undef ESR_KB
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -819,30 +888,31 @@ int set_smem(F* fn, size_t bytes) {
 }
 
 template <int KB, int NS>
-int launch_scores(int mode, const CUtensorMap& tq, const CUtensorMap& tk, const ScoreArgs& sa, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)(1 + NS) * KB * kKBlkBytes + 1024;
+int launch_scores(int mode, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tg, const ScoreArgs& sa, dim3 grid,
+                  cudaStream_t st) {
+  const size_t smem = (size_t)(1 + NS) * KB * kKBlkBytes + 8 * 4096 + 1024;
   int rc;
   if (mode == 0) {
     if ((rc = set_smem(k_inbatch_scores<KB, NS, 0>, smem)) != ESR_OK) return rc;
-    k_inbatch_scores<KB, NS, 0><<<grid, kIbThreads, smem, st>>>(tq, tk, sa);
+    k_inbatch_scores<KB, NS, 0><<<grid, kIbThreads, smem, st>>>(tq, tk, tg, sa);
   } else if (mode == 1) {
     if ((rc = set_smem(k_inbatch_scores<KB, NS, 1>, smem)) != ESR_OK) return rc;
-    k_inbatch_scores<KB, NS, 1><<<grid, kIbThreads, smem, st>>>(tq, tk, sa);
+    k_inbatch_scores<KB, NS, 1><<<grid, kIbThreads, smem, st>>>(tq, tk, tg, sa);
   } else {
     if ((rc = set_smem(k_inbatch_scores<KB, NS, 2>, smem)) != ESR_OK) return rc;
-    k_inbatch_scores<KB, NS, 2><<<grid, kIbThreads, smem, st>>>(tq, tk, sa);
+    k_inbatch_scores<KB, NS, 2><<<grid, kIbThreads, smem, st>>>(tq, tk, tg, sa);
   }
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
 
-int launch_scores_d(int D, int mode, const CUtensorMap& tq, const CUtensorMap& tk, const ScoreArgs& sa, dim3 grid,
-                    cudaStream_t st) {
+int launch_scores_d(int D, int mode, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tg, const ScoreArgs& sa,
+                    dim3 grid, cudaStream_t st) {
   switch (D) {
-    case 64: return launch_scores<1, 4>(mode, tq, tk, sa, grid, st);
-    case 128: return launch_scores<2, 4>(mode, tq, tk, sa, grid, st);
-    case 192: return launch_scores<3, 3>(mode, tq, tk, sa, grid, st);
-    case 256: return launch_scores<4, 2>(mode, tq, tk, sa, grid, st);
+    case 64: return launch_scores<1, 4>(mode, tq, tk, tg, sa, grid, st);
+    case 128: return launch_scores<2, 4>(mode, tq, tk, tg, sa, grid, st);
+    case 192: return launch_scores<3, 3>(mode, tq, tk, tg, sa, grid, st);
+    case 256: return launch_scores<4, 2>(mode, tq, tk, tg, sa, grid, st);
     default: return ESR_EINVAL;
   }
 }
@@ -924,9 +994,13 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
   sa.ib0 = 0;
   sa.margin = cfg->margin;
   sa.scale = cfg->scale;
+  {
+    const char* dbg = getenv("ESR_IB_DEBUG");
+    sa.debug = dbg ? atoi(dbg) : 0;
+  }
   int rc;
   if (softmax) {  // row statistics of the whole batch first (no G traffic), then logsumexp
-    if ((rc = launch_scores_d(p.D, 1, tmQ, tmK, sa, dim3(p.n_ib, p.JS), st)) != ESR_OK) return rc;
+    if ((rc = launch_scores_d(p.D, 1, tmQ, tmK, tmQ /* unused in this mode */, sa, dim3(p.n_ib, p.JS), st)) != ESR_OK) return rc;
     k_inbatch_lse<<<(unsigned)ceil_div(p.Bq, 256), 256, 0, st>>>(w.stats, p.R, p.Bq, w.lse2);
     ESR_LAUNCH_CHECK();
   }
@@ -944,10 +1018,11 @@ extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const Es
     const int i0 = ib0 * kTile;
     const int rows = p.Bq - i0 < n_ic * kTile ? p.Bq - i0 : n_ic * kTile;
     sa.ib0 = ib0;
-    if ((rc = launch_scores_d(p.D, softmax ? 2 : 0, tmQ, tmK, sa, dim3(n_ic, p.JS), st)) != ESR_OK) return rc;
-    CUtensorMap tmGk, tmGmn;  // this chunk's rows only: rows beyond `rows` read as zero
-    if (!(make_tmap(&tmGk, w.G, p.Bk, rows, p.ldG, kBK, kTile) && make_tmap(&tmGmn, w.G, p.Bk, rows, p.ldG, 64, kBK)))
+    CUtensorMap tmGk, tmGmn, tmGst;  // this chunk's rows only: rows beyond `rows` read as zero / are not written
+    if (!(make_tmap(&tmGk, w.G, p.Bk, rows, p.ldG, kBK, kTile) && make_tmap(&tmGmn, w.G, p.Bk, rows, p.ldG, 64, kBK) &&
+          make_tmap(&tmGst, w.G, p.Bk, rows, p.ldG, 64, 32)))
       return ESR_ENOTSUP;
+    if ((rc = launch_scores_d(p.D, softmax ? 2 : 0, tmQ, tmK, tmGst, sa, dim3(n_ic, p.JS), st)) != ESR_OK) return rc;
     ba.i0 = i0;
     ba.rows = rows;
     ba.chunk = c;
