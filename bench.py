@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-uniform", action="store_true")
+    ap.add_argument("--no-inbatch", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, help="plan/staging buffers in flight (GloveTrainer)")
+    ap.add_argument("--row-blocks", type=int, default=-1, help="persistent row-pass grid (-1 = trainer default, 0 = 2 CTAs per SM)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: row exchange over NVLink peer memory (libesr kernels) or NCCL all-to-all")
     return ap.parse_args()
@@ -289,6 +292,50 @@ def rows_kernel_time(table, a, ids_dev, cnt_dev, steps):
     return tot / steps
 
 
+def ncu_traffic(stream, a):
+    """DRAM bytes per row-pass launch from the committed ncu capture of the same kernel / batch (None otherwise)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[stream]
+        if t["batch"] == a.batch and a.vocab == 1_000_000 and a.dim == 128:
+            return t["bytes"]
+    except Exception:
+        pass
+    return None
+
+
+def inbatch_leg(peaks):
+    """BASELINE configs[2] / configs[3] scoring step (B x B in-batch negatives on tcgen05): device-timed, inputs
+    resident.  flops = 6*B*B*D useful (one score pass + dQ + dK); softmax issues a second score pass."""
+    import torch
+    from esrecsys_b200.engine import InBatchScorer
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    out = {}
+    for name, B, D, loss in (("spotify_inbatch_hinge_B8192_D128", 8192, 128, "hinge"),
+                             ("spotify_inbatch_softmax_B8192_D128", 8192, 128, "softmax"),
+                             ("two_tower_inbatch_softmax_B4096_D256", 4096, 256, "softmax")):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        Q = torch.randn(B, D, device="cuda", generator=g) / D ** 0.25
+        K = torch.randn(B, D, device="cuda", generator=g) / D ** 0.25
+        sc = InBatchScorer(B, D, loss=loss)
+        for _ in range(5):
+            sc.run(Q, K)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 50
+        e0.record()
+        for _ in range(n):
+            sc.run(Q, K)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        tf = 6.0 * B * B * D / (ms * 1e-3) / 1e12
+        out[name] = {"ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3), "useful_tflops": tf, "bound": "tensor",
+                     "peak": peak, "frac": tf / peak, "dtype": "bf16 operands, f32 accumulate (tcgen05)",
+                     "kernels_per_step": 4 if loss == "hinge" else 6}
+        del sc
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -321,7 +368,7 @@ def run_ours(a):
     cnt_dev = [torch.from_numpy(counts[k]).cuda() for k in range(a.nbatch)]
     ids_pin = [torch.from_numpy(ids[k]).pin_memory() for k in range(a.nbatch)]
     cnt_pin = [torch.from_numpy(counts[k]).pin_memory() for k in range(a.nbatch)]
-    tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel)
+    tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel, depth=a.depth, row_blocks=None if a.row_blocks < 0 else a.row_blocks)
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -356,8 +403,9 @@ def run_ours(a):
         ab, U = alg_bytes(ids, D, B)
         ach = ab / (t_rows * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                            "traffic": None, "kernel": "k_glove_rows", "kernel_ms": t_rows, "alg_bytes_per_launch": ab,
-                            "unique_rows_per_step": U, "peak_source": peak_src, "stream": "zipf(1)"}
+                            "traffic": ncu_traffic("zipf", a), "kernel": "k_glove_rows_grp_async", "kernel_ms": t_rows,
+                            "alg_bytes_per_launch": ab, "unique_rows_per_step": U, "peak_source": peak_src,
+                            "stream": "zipf(1)"}
         if not a.no_uniform:
             uids, ucnt = synth.glove_batches(V, B, 4, a.seed + 99, uniform=True)
             u_dev = [torch.from_numpy(uids[k].reshape(-1)).cuda() for k in range(4)]
@@ -366,8 +414,11 @@ def run_ours(a):
             abu, Uu = alg_bytes(uids, D, B)
             achu = abu / (t_u * 1e-3) / 1e9
             line["roofline_uniform"] = {"bound": "hbm", "achieved": achu, "peak": hbm_peak, "unit": "GB/s",
-                                        "frac": achu / hbm_peak, "traffic": None, "kernel": "k_glove_rows", "kernel_ms": t_u,
+                                        "frac": achu / hbm_peak, "traffic": ncu_traffic("uniform", a),
+                                        "kernel": "k_glove_rows_grp_async", "kernel_ms": t_u,
                                         "alg_bytes_per_launch": abu, "unique_rows_per_step": Uu, "stream": "uniform"}
+        if not a.no_inbatch:
+            line["other_workloads"] = inbatch_leg(peaks)
         clocks.active = False
     line["clocks"] = clocks.summary()
     if rank == 0:

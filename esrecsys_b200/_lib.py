@@ -46,7 +46,7 @@ class EsrGloveCfg(C.Structure):
                 ("lr", C.c_float), ("eps", C.c_float), ("x_max", C.c_float), ("alpha", C.c_float),
                 ("chunk", C.c_int32), ("reserved", C.c_int32), ("emit_map", C.c_void_p),
                 ("emit_peers_dE", C.c_void_p), ("emit_peers_db", C.c_void_p), ("n_emit_peers", C.c_int32),
-                ("reserved2", C.c_int32)]
+                ("row_blocks", C.c_int32)]
 
 
 class EsrInbatchCfg(C.Structure):

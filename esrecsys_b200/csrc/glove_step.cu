@@ -52,9 +52,12 @@ struct GloveWs {
   float* parts;     // [nchunks][2]    partial scalar sums
   float* prep_blk;  // [prep_blocks][3]
   float* rows_blk;  // [row_blocks][2]
-  int32_t* wl_count;  // [2]
+  int32_t* wl_count;  // [4 + heavy_cap]: light / heavy list lengths, work counter, then one ticket per heavy segment
   int32_t* wl_light;  // [nchunks]
   int32_t* wl_heavy;  // [nchunks]
+  float* part2;       // [heavy_cap][kHeavySplit][D] second-level partial sums of the heavy segments
+  float* parts2;      // [heavy_cap][kHeavySplit]
+  int64_t heavy_cap;
   int64_t nchunks;
   int32_t prep_blocks;
   int32_t row_blocks;
@@ -69,6 +72,8 @@ int group_lanes(int D4) {
 }
 
 constexpr int kMinAutoChunk = 16;
+constexpr int kHeavyParts = 32;   // straddling segments with more partials than this are combined by several blocks
+constexpr int kHeavySplit = 8;    // blocks per heavy segment
 
 // chunk == 0: pick the chunk length that wastes the least of the last wave.  All resident groups
 // advance in lock step through `rounds` chunks, so the pass costs rounds * (chunk + start-up).
@@ -112,11 +117,38 @@ size_t carve_ws(void* base, int64_t B, int32_t D, int32_t chunk_in, GloveWs* w) 
   t.parts = c.take<float>(cap_chunks * 2);
   t.prep_blk = c.take<float>((size_t)t.prep_blocks * 3);
   t.rows_blk = c.take<float>((size_t)cap_row_blocks * 2);
-  t.wl_count = c.take<int32_t>(4);
+  t.heavy_cap = n / ((int64_t)kHeavyParts * kMinAutoChunk) + 2;  // a heavy segment holds > kHeavyParts * chunk slots
+  t.wl_count = c.take<int32_t>(4 + t.heavy_cap);
   t.wl_light = c.take<int32_t>(cap_chunks);
   t.wl_heavy = c.take<int32_t>(cap_chunks);
+  t.part2 = c.take<float>((size_t)t.heavy_cap * kHeavySplit * D);
+  t.parts2 = c.take<float>((size_t)t.heavy_cap * kHeavySplit);
   if (w) *w = t;
   return c.off;
+}
+
+// Fixed-order reduction of NV-wide block partials into scalars[off .. off+NV) (double accumulate).
+template <int NV>
+__device__ void reduce_partials(const float* __restrict__ blk, int nblk, float* __restrict__ out) {
+  __shared__ double sh[kCombineThreads * NV];
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] += (double)__ldcg(blk + b * NV + k);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) sh[threadIdx.x * NV + k] = acc[k];
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) sh[threadIdx.x * NV + k] += sh[(threadIdx.x + o) * NV + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = (float)sh[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,8 +160,9 @@ __global__ void __launch_bounds__(kThreads) k_glove_prep(const int32_t* __restri
                                                          const float* __restrict__ bias, const uint8_t* __restrict__ ver,
                                                          int64_t n, int64_t B, float x_max, float alpha,
                                                          int32_t* __restrict__ skv, SlotRec* __restrict__ rec,
-                                                         float* __restrict__ blk) {
+                                                         float* __restrict__ blk, float* __restrict__ scalars) {
   __shared__ float red[32 * 3];
+  __shared__ bool last_block;
   const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   float v[3] = {0.f, 0.f, 0.f};
   if (p < n) {
@@ -157,36 +190,16 @@ __global__ void __launch_bounds__(kThreads) k_glove_prep(const int32_t* __restri
     blk[blockIdx.x * 3 + 0] = v[0];
     blk[blockIdx.x * 3 + 1] = v[1];
     blk[blockIdx.x * 3 + 2] = v[2];
+    // the last block to arrive reduces every block's partials in index order (deterministic); the ticket
+    // lives in the unused tail of the scalars block, zeroed by the caller's memset
+    __threadfence();
+    last_block = atomicAdd(reinterpret_cast<unsigned*>(scalars + ESR_GLOVE_NSCAL - 1), 1u) == gridDim.x - 1;
   }
-}
-
-// Fixed-order reduction of NV-wide block partials into scalars[off .. off+NV) (double accumulate).
-template <int NV>
-__device__ void reduce_partials(const float* __restrict__ blk, int nblk, float* __restrict__ out) {
-  __shared__ double sh[kCombineThreads * NV];
-  double acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x)
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] += (double)blk[b * NV + k];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) sh[threadIdx.x * NV + k] = acc[k];
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o)
-#pragma unroll
-      for (int k = 0; k < NV; ++k) sh[threadIdx.x * NV + k] += sh[(threadIdx.x + o) * NV + k];
-    __syncthreads();
+  if (last_block) {
+    __threadfence();
+    reduce_partials<3>(blk, gridDim.x, scalars + ESR_SC_SUM_BS);
   }
-  if (threadIdx.x == 0)
-#pragma unroll
-    for (int k = 0; k < NV; ++k) out[k] = (float)sh[k];
-}
-
-__global__ void __launch_bounds__(kCombineThreads) k_glove_prep_reduce(const float* __restrict__ blk, int nblk,
-                                                                       float* __restrict__ scalars) {
-  reduce_partials<3>(blk, nblk, scalars + ESR_SC_SUM_BS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,6 +271,9 @@ struct RowsArgs {
   int32_t* work_counter;  // dynamic work distribution of the persistent row pass
   int32_t* wl_light;  // head chunks of straddling segments with <= kHeavyParts partials
   int32_t* wl_heavy;
+  int32_t* tickets;   // [heavy_cap] arrival counters of the heavy segments' blocks (zeroed with wl_count)
+  float* part2;
+  float* parts2;
   float* dE;
   const int32_t* emit_map;  // EMIT: gradient of unique row u goes to dE[emit_map[u]] (NULL: dE[u])
   EmitPeers peers;
@@ -272,7 +288,6 @@ struct RowsArgs {
   float lr, eps;
 };
 
-constexpr int kHeavyParts = 64;
 
 // Close a finished segment: Adagrad row write (UPDATE) or gradient emit (EMIT).
 template <int NK>
@@ -1058,13 +1073,19 @@ __global__ void __launch_bounds__(kCombineThreads) k_glove_combine(const RowsArg
     sum_parts<NK, UN>(a, c, 0, s.np, sum, bacc, lane);
     close_straddler<NK>(a, s, sum, bacc, lane);
   }
-  // heavy work list: one block per segment, warps take contiguous ranges of partials
+  // heavy work list: kHeavySplit blocks per segment, each sums a contiguous range of the partials (warps
+  // take contiguous sub-ranges) into a second-level partial; the LAST block to arrive adds those in
+  // range order and closes the segment -- the summation tree is fixed, whichever block that is.
+  __shared__ int ticket_sh;
   const int nh = a.wl_count[1];
-  for (int e = blockIdx.x; e < nh; e += gridDim.x) {
+  for (int task = blockIdx.x; task < nh * kHeavySplit; task += gridDim.x) {
+    const int e = task / kHeavySplit, sp = task % kHeavySplit;
     const int64_t c = a.wl_heavy[e];
     const Straddler s = straddler_of(a, c);
-    const int64_t per = ceil_div(s.np, (int64_t)kCombineWarps);
-    const int64_t m0 = wid * per, m1 = min(s.np, m0 + per);
+    const int64_t per_split = ceil_div(s.np, (int64_t)kHeavySplit);
+    const int64_t r0 = min(s.np, sp * per_split), r1 = min(s.np, r0 + per_split);
+    const int64_t per = ceil_div(r1 - r0, (int64_t)kCombineWarps);
+    const int64_t m0 = min(r1, r0 + wid * per), m1 = min(r1, m0 + per);
     Row<NK> sum;
     row_zero(sum);
     float ssum = 0.f;
@@ -1080,7 +1101,34 @@ __global__ void __launch_bounds__(kCombineThreads) k_glove_combine(const RowsArg
         for (int k = 0; k < NK; ++k) f4_add(sum.v[k], sh[w][k * 32 + lane]);
         bacc += shs[w];
       }
-      close_straddler<NK>(a, s, sum, bacc, lane);
+      float4* p2 = reinterpret_cast<float4*>(a.part2) + ((int64_t)e * kHeavySplit + sp) * a.D4;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int col = k * 32 + lane;
+        if (col < a.D4) __stcg(p2 + col, sum.v[k]);
+      }
+      if (lane == 0) {
+        __stcg(a.parts2 + (int64_t)e * kHeavySplit + sp, bacc);
+        __threadfence();
+        ticket_sh = atomicAdd(a.tickets + e, 1);
+      }
+      __syncwarp();
+      if (ticket_sh == kHeavySplit - 1) {
+        __threadfence();
+        Row<NK> tot;
+        row_zero(tot);
+        float btot = 0.f;
+        for (int q = 0; q < kHeavySplit; ++q) {
+          const float4* src = reinterpret_cast<const float4*>(a.part2) + ((int64_t)e * kHeavySplit + q) * a.D4;
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const int col = k * 32 + lane;
+            if (col < a.D4) f4_add(tot.v[k], __ldcg(src + col));
+          }
+          btot += __ldcg(a.parts2 + (int64_t)e * kHeavySplit + q);
+        }
+        close_straddler<NK>(a, s, tot, btot, lane);
+      }
     }
     __syncthreads();
   }
@@ -1194,6 +1242,9 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.work_counter = w.wl_count + 2;
   a.wl_light = w.wl_light;
   a.wl_heavy = w.wl_heavy;
+  a.tickets = w.wl_count + 4;
+  a.part2 = w.part2;
+  a.parts2 = w.parts2;
   a.nchunks = w.nchunks;
   a.scalars = scalars;
   a.bsum = w.bsum;
@@ -1237,21 +1288,23 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
   carve_ws(ws, cfg->B, t->D, cfg->chunk, &w);
   const int64_t n = plan->n_slots;
   k_glove_prep<<<w.prep_blocks, kThreads, 0, stream>>>(plan->sorted_keys, plan->perm, plan->partner, counts, t->bias,
-                                                       t->ver, n, cfg->B, cfg->x_max, cfg->alpha, w.skv, w.rec, w.prep_blk);
-  ESR_LAUNCH_CHECK();
-  k_glove_prep_reduce<<<1, kCombineThreads, 0, stream>>>(w.prep_blk, w.prep_blocks, scalars);
+                                                       t->ver, n, cfg->B, cfg->x_max, cfg->alpha, w.skv, w.rec, w.prep_blk,
+                                                       scalars);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
-                           bool use_async = false) {
+                           bool use_async = false, int grid_override = 0) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
-  if (use_async) row_blocks = (int)std::min<int64_t>(row_blocks, 2 * (int64_t)sm_count());  // persistent, work-stealing
+  if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
+    const int64_t cap = grid_override > 0 ? grid_override : 2 * (int64_t)sm_count();
+    row_blocks = (int)std::min<int64_t>(row_blocks, cap);
+  }
   if ((phases & 1) && use_async) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
     static size_t configured = 0;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && smem > configured) {
@@ -1262,7 +1315,7 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     k_glove_rows_grp_async<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if (phases & 1) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     constexpr size_t smem = (size_t)kWarps * GP * sizeof(GroupMeta);
     static bool configured = false;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && !configured) {
@@ -1283,7 +1336,7 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
 template <int NK, int S, int MINB>
 static int launch_rows(const RowsArgs& a, const GloveWs& w, float* scalars, bool tma, int phases, cudaStream_t stream) {
   int row_blocks = w.row_blocks;
-  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, 4 * sizeof(int32_t), stream));
+  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
   if (tma) {
     const size_t smem = (size_t)kWarps * kTmaStages * 3 * a.D4 * 16;
     static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per NK: largest dynamic smem opted in
@@ -1327,10 +1380,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     if (d4 <= 8) return launch_rows_grp<2, 4, 1>(a, w, scalars, phases, stream);
     if (d4 <= 16) return launch_rows_grp<4, 4, 1>(a, w, scalars, phases, stream);
     const bool as = cfg->reserved != 1;  // reserved == 1: keep rows in registers (A/B probe)
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as);
+    const int go = cfg->row_blocks;
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go);
   }
   switch (nk) {
     case 1:

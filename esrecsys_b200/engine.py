@@ -169,7 +169,8 @@ class GloveStep:
     phases over an IndexPlan (include/esr.h: esr_glove_prep/rows/finish)."""
 
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", eps=1e-7,
-                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto", dE=None, db=None):
+                 x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto", dE=None, db=None,
+                 row_blocks=0):
         self.table = table
         self.B = int(B)
         dev = table.device
@@ -182,6 +183,7 @@ class GloveStep:
         cfg.B_global = int(B_global if B_global is not None else B)
         cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
         cfg.chunk = chunk
+        cfg.row_blocks = int(row_blocks)
         self.cfg = cfg
         self.emit = bool(emit_grads)
         self.ws_bytes = int(L.lib().esr_glove_workspace_bytes(self.B, table.D, chunk))

@@ -14,6 +14,8 @@ bench.py.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -23,13 +25,20 @@ from .engine import EmbeddingTable, GloveStep, IndexPlan
 
 class GloveTrainer:
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", chunk=0, impl="auto",
-                 graphs=True, depth=2, loss_log=4096):
+                 graphs=True, depth=2, loss_log=4096, row_blocks=None):
         L.require_cuda()
+        if row_blocks is None:
+            # The persistent row pass fills every SM with 2 CTAs, which leaves no registers for the plan
+            # kernels of batch t+1 on the side stream (measured on B200: 170 us/step, plan serialised behind
+            # the row pass).  Leaving ~11 % of the CTA slots free lets them co-run: 155-161 us/step.
+            sm = C.c_int(0)
+            L.check(L.lib().esr_device_info(C.byref(sm), None, None), "esr_device_info")
+            row_blocks = max(1, (2 * sm.value * 8) // 9)
         self.table = table
         self.B = int(B)
         self.dev = table.device
         self.depth = int(depth)
-        self.step_fn = GloveStep(table, B, lr=lr, bias_mode=bias_mode, chunk=chunk, impl=impl)
+        self.step_fn = GloveStep(table, B, lr=lr, bias_mode=bias_mode, chunk=chunk, impl=impl, row_blocks=row_blocks)
         self.plans = [IndexPlan(2 * self.B, table.V, self.dev) for _ in range(self.depth)]
         self.ids = [torch.zeros(2 * self.B, dtype=torch.int32, device=self.dev) for _ in range(self.depth)]
         self.counts = [torch.ones(self.B, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
@@ -49,7 +58,7 @@ class GloveTrainer:
 
     # kernels one step launches (libesr only; the radix sort is cub code compiled into libesr)
     LAUNCHES_PLAN = 8    # iota, cub histogram + <=4 onesweep passes (key_bits<=32), head count, scan, head write
-    LAUNCHES_STEP = 5    # prep, prep_reduce, rows, combine, finish
+    LAUNCHES_STEP = 4    # prep (+ fused reduction), rows, combine, finish
 
     def _plan_body(self, k):
         self.plans[k].build(self.ids[k])

@@ -145,7 +145,7 @@ typedef struct EsrGloveCfg {
   void* const* emit_peers_dE;
   void* const* emit_peers_db;
   int32_t n_emit_peers;
-  int32_t reserved2;
+  int32_t row_blocks;  /* persistent row-pass grid; 0 => 2 CTAs per SM.  Fewer leaves SM room for the plan stream */
 } EsrGloveCfg;
 
 /* Scalars block (device float[ESR_GLOVE_NSCAL]) shared by the three phases.  After
