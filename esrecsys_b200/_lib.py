@@ -66,6 +66,8 @@ _SIGNATURES = {
     "esr_table_export_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P]),
     "esr_rowwise_dot_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     "esr_score_all_f32": (C.c_int, [C.POINTER(EsrTable), _P, C.c_int32, _P, _P]),
+    "esr_sort_cols_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "esr_sort_cols_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "esr_check_ids_i32": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "esr_plan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_plan_build_i32": (C.c_int, [C.POINTER(EsrPlan), _P, C.c_size_t, _P]),
@@ -102,6 +104,10 @@ _SIGNATURES = {
     "esr_gather_scalar_f32": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "esr_permute_rows_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "esr_segment_sum_rows_f32": (C.c_int, [C.POINTER(EsrPlan), C.c_int32, _P, _P, _P, _P, _P]),
+    "esr_decode_cooccur_b64": (C.c_int64, [C.c_char_p, C.c_size_t, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_size_t)]),
+    "esr_decode_tfrecord_int64": (C.c_int64, [_P, C.c_size_t, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(_P),
+                                              C.POINTER(C.c_int64), C.POINTER(_P), C.c_int64, C.POINTER(C.c_size_t)]),
     "esr_inbatch_workspace_bytes": (C.c_size_t, [C.POINTER(EsrInbatchCfg)]),
     "esr_inbatch_fwd_bwd_bf16": (C.c_int, [_P, _P, C.POINTER(EsrInbatchCfg), _P, _P, _P, _P, C.c_size_t, _P]),
     "esr_inbatch_ws_layout": (C.c_int, [C.POINTER(EsrInbatchCfg), C.POINTER(C.c_int64)]),

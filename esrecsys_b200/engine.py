@@ -280,6 +280,28 @@ def score_all(table: EmbeddingTable, queries):
     return out
 
 
+def sort_cols(scores, k=None, descending=False, want_values=False):
+    """Stable per-column ranking of a (V, T) score matrix -> int32 (k, T) row indices (and values).
+    ``descending=False, k=None`` is ``jnp.argsort(scores, axis=0)`` (find_knn); ``descending=True`` is
+    ``jax.lax.top_k`` per column."""
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.is_contiguous()
+    V, T = scores.shape
+    k = V if k is None else int(k)
+    ws_bytes = int(L.lib().esr_sort_cols_workspace_bytes(V))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
+    idx = torch.empty(k, T, dtype=torch.int32, device=scores.device)
+    val = torch.empty(k, T, dtype=torch.float32, device=scores.device) if want_values else None
+    L.check(L.lib().esr_sort_cols_f32(L.ptr(scores), V, T, 1 if descending else 0, k, L.ptr(idx), L.ptr(val), L.ptr(ws),
+                                      ws_bytes, L.stream_ptr()), "esr_sort_cols_f32")
+    return (idx, val) if want_values else idx
+
+
+def top_k(scores_1d, k):
+    """``jax.lax.top_k(scores, k)`` of a 1-D score vector -> (values, indices)."""
+    idx, val = sort_cols(scores_1d.reshape(-1, 1).contiguous(), k, True, True)
+    return val[:, 0], idx[:, 0]
+
+
 class InBatchScorer:
     """B x B in-batch-negative scoring + loss + gradients on the tensor cores
     (``esr_inbatch_fwd_bwd_bf16``; csrc/inbatch_scores.cu).  Generalises the triplet scoring of

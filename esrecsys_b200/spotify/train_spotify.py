@@ -1,0 +1,65 @@
+"""Hot-path functions of spotify/train_spotify.py with the same names and argument meaning:
+``train_step`` (:77-111), ``eval_step`` (:113-131), ``sample_negative`` (:139-150).
+
+``train_step`` runs the fused forward + backward of the reference loss for a pack of playlists
+(``SpotifyModel.loss_and_grads``) and applies the reference's optimizer through ``TrainState``;
+``eval_step`` scores every track against the 5 context rows on the device and ranks them with libesr.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import engine
+from ..train_state import TrainState
+from .models import SpotifyModel, _i32
+
+
+def train_step(state: TrainState, model: SpotifyModel, examples, regularization=10.0):
+    """train_spotify.py:77-111 for a list of playlist dicts (the reference passes one): returns (state, loss[P])."""
+    loss, grads = model.loss_and_grads(state.params, examples, regularization)
+    return state.apply_gradients(grads=grads), loss
+
+
+def eval_scores(model: SpotifyModel, params, y, all_albums, all_artists):
+    """``result[1]`` of eval_step (:114-119): affinity of every track of the corpus to the playlist context,
+    ``max_k(track . ctx_k) + 0.1 isin(album, album_ctx) + 0.1 isin(artist, artist_ctx)`` (spotify/models.py:78-80)."""
+    dev = params["album_embed"]["embedding"].device
+    ctx = model.get_embeddings(params, y["album_context"], y["artist_context"])            # (5, 2F)
+    cand = model.get_embeddings(params, all_albums, all_artists)                           # (N, 2F)
+    scores = engine.score_all(engine.EmbeddingTable.wrap(cand.contiguous()), ctx.contiguous())    # (N, 5), one table scan
+    aff = scores.max(dim=1).values
+    alb = torch.as_tensor(np.asarray(all_albums)).to(dev)
+    art = torch.as_tensor(np.asarray(all_artists)).to(dev)
+    aff = aff + 0.1 * torch.isin(alb, torch.as_tensor(np.asarray(y["album_context"])).to(dev)).float()
+    aff = aff + 0.1 * torch.isin(art, torch.as_tensor(np.asarray(y["artist_context"])).to(dev)).float()
+    return aff
+
+
+def eval_step(model: SpotifyModel, params, y, all_tracks, all_albums, all_artists, k=500):
+    """train_spotify.py:113-131: recall of the next tracks / artists among the top-k tracks.  Returns
+    (metrics f32[2], top_k_indices)."""
+    aff = eval_scores(model, params, y, all_albums, all_artists)
+    _, top = engine.top_k(aff, k)                                                           # jax.lax.top_k
+    dev = aff.device
+    top_l = top.long()
+    top_tracks = torch.as_tensor(np.asarray(all_tracks)).to(dev)[top_l]
+    top_artists = torch.as_tensor(np.asarray(all_artists)).to(dev)[top_l]
+    nt = torch.as_tensor(np.asarray(y["next_track"])).to(dev)
+    na = torch.as_tensor(np.asarray(y["next_artist"])).to(dev)
+    t = torch.isin(top_tracks, nt).sum().float() / nt.numel()
+    a = torch.isin(top_artists, na).sum().float() / na.numel()
+    return torch.stack([t, a]), top
+
+
+def sample_negative(x, generator: torch.Generator, num_negatives, all_tracks, all_albums, all_artists):
+    """train_spotify.py:139-150: uniform negatives, ``randint(0, N - 1)`` -- the upper bound is EXCLUSIVE in
+    jax.random.randint, so the last track is never drawn (kept).  The stream is torch's, not threefry: parity
+    harnesses pass the negatives in as inputs."""
+    n = len(all_tracks)
+    idx = torch.randint(0, n - 1, (num_negatives,), generator=generator).numpy()
+    out = dict(x)
+    out["neg_track"] = np.asarray(all_tracks)[idx]
+    out["neg_album"] = np.asarray(all_albums)[idx]
+    out["neg_artist"] = np.asarray(all_artists)[idx]
+    return out

@@ -55,8 +55,22 @@ def update_model(state: TrainState, grads):
 def find_knn(model: Glove, params, token):
     """train_cooccurence.py:91-97: scores (V,T) and the ascending argsort over axis 0."""
     scores = model.apply({"params": params}, token, method=Glove.score_all)
-    indices = torch.argsort(scores, dim=0, stable=True)
+    indices = engine.sort_cols(scores)          # stable ascending argsort over axis 0, as jnp.argsort
     return scores, indices
+
+
+def dump_knn(model: Glove, params, tokens, token_dictionary=None, k=10):
+    """train_cooccurence.py:114-126: the k nearest neighbours of each query token, read from the tail of the
+    ascending argsort.  Returns ``[(query, [(neighbour, score), ...]), ...]`` (the reference logs them)."""
+    scores, indices = find_knn(model, params, tokens)
+    name = (lambda t: token_dictionary.get_token_from_embedding_index(t)) if token_dictionary is not None else int
+    V = scores.shape[0]
+    tail = indices[V - k:].flip(0).cpu().numpy()                    # (k, T): indices[-j-1][i]
+    sc = scores.cpu().numpy()
+    out = []
+    for i, token in enumerate(np.asarray(tokens).reshape(-1)):
+        out.append((name(int(token)), [(name(int(tail[j, i])), float(sc[tail[j, i], i])) for j in range(k)]))
+    return out
 
 
 def train_epoch(state, steps_per_epoch, train_it):

@@ -88,6 +88,14 @@ int esr_rowwise_dot_f32(const float* x, const float* y, int64_t B, int32_t D, fl
 /* scores[v, t] = table[v] . queries[t], (V,T) row-major, T <= 64: Glove.score_all (wikipedia/models.py:40-55),
  * the product scan of find_top_k (pinterest/make_recommendations.py:57).  Streams the table once. */
 int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float* scores, esr_stream_t stream);
+/* Per-query ranking of a (V,T) row-major score matrix (the output of esr_score_all_f32): for every column t the
+ * first k entries of the stable sort of the column, out_idx[r*T + t] = row of rank r (out_val likewise, optional).
+ * descending == 0, k == V : jnp.argsort(scores, axis=0) of find_knn (wikipedia/train_cooccurence.py:91-97);
+ * descending != 0         : jax.lax.top_k (spotify/train_spotify.py:120, pinterest/make_recommendations.py:64),
+ * ties in index order in both cases. */
+size_t esr_sort_cols_workspace_bytes(int64_t V);
+int esr_sort_cols_f32(const float* scores, int64_t V, int32_t T, int32_t descending, int64_t k, int32_t* out_idx,
+                      float* out_val, void* ws, size_t ws_bytes, esr_stream_t stream);
 /* Debug validator: *n_bad (device int32) = number of ids outside [0, V). */
 int esr_check_ids_i32(const int32_t* ids, int64_t n, int64_t V, int32_t* n_bad, esr_stream_t stream);
 
@@ -322,6 +330,23 @@ int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const flo
                                int32_t n_ranks, const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
                                int64_t map_stride, int32_t* desc /* scratch [recv_cap * n_ranks] */, float lr, float eps,
                                esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Native decoders of the reference's record formats (HOST pointers).  Re-entrant,
+ * allocation-free; a negative return is an ESR_E* code.
+ * ------------------------------------------------------------------------------------------ */
+/* Text of a *.cooccur.pb.b64 part after bz2 decompression: one base64 line per CooccurrenceRow
+ * {1: index, 2: packed other_index, 3: packed float count}.  Writes the (i, j, count) triples in the order
+ * CooccurrenceGenerator.get_item yields them (wikipedia/cooccurrence_matrix.py:62-83) and returns their number;
+ * stops before a row that would exceed cap or at an incomplete last line; *consumed = bytes fully decoded. */
+int64_t esr_decode_cooccur_b64(const char* text, size_t n_bytes, int32_t* out_i, int32_t* out_j, float* out_count,
+                               int64_t cap, int64_t* n_rows, size_t* consumed);
+/* TFRecord stream of tf.train.Example with int64_list features (spotify/input_pipeline.py:23-37,
+ * spotify/make_training.py:102-112).  For key k the values of record r are vals[k][offs[k][r] .. offs[k][r+1]);
+ * offs[k] has max_records + 1 entries.  Returns the number of records decoded; CRCs are not verified. */
+int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes, int32_t n_keys, const char* const* keys,
+                                  int64_t* const* vals, const int64_t* val_cap, int64_t* const* offs,
+                                  int64_t max_records, size_t* consumed);
 
 #ifdef __cplusplus
 }
