@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kThreads) k_peer_pull_ids(PeerPtrs counts, Pee
       src_meta[s * 3 + 2] = dsp[s];
     } else {
       src_meta[n_ranks * 3] = min((int64_t)off[n_ranks], recv_cap);  // total received
+      src_meta[n_ranks * 3 + 1] = 0;                                 // owner entries (counted by k_peer_resolve)
     }
   }
   const int64_t total = min((int64_t)off[n_ranks], recv_cap);
@@ -133,11 +134,15 @@ __global__ void __launch_bounds__(kThreads) k_peer_clear_map(const int32_t* __re
 // not own their row get all -1.  Splitting this off keeps the heavy kernel below free of dependent
 // 4-byte lookups, so its row loads are issued back to back.
 __global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const int32_t* __restrict__ recv_ids,
-                                                           const int32_t* __restrict__ src_meta,
+                                                           int32_t* __restrict__ src_meta,
                                                            const int32_t* __restrict__ slot_map, int64_t map_stride,
-                                                           int32_t* __restrict__ desc) {
+                                                           int32_t* __restrict__ desc, int32_t* __restrict__ own_list) {
   const int64_t total = src_meta[n_ranks * 3];
-  for (int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x; k < total; k += (int64_t)gridDim.x * kThreads) {
+  const int64_t span = (int64_t)gridDim.x * kThreads;
+  for (int64_t k0 = blockIdx.x * (int64_t)kThreads; k0 < total; k0 += span) {
+    const int64_t k = k0 + threadIdx.x;
+    bool own = false;
+    if (k < total) {
     int s = 0;
     while (s + 1 < n_ranks && k >= src_meta[(s + 1) * 3]) ++s;
     const int32_t x = recv_ids[k];
@@ -151,80 +156,91 @@ __global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const in
 #pragma unroll
     for (int q = 0; q < ESR_MAX_PEERS; ++q)
       if (q < n_ranks) desc[k * n_ranks + q] = (first && q >= s && pos[q] >= 0) ? src_meta[q * 3 + 0] + pos[q] : -1;
+    own = first;
+    }
+    // compact the entries that own their row (warp-aggregated append; the order of the list only decides which
+    // group processes which row, never a summation order)
+    const unsigned m = __ballot_sync(FULL, own);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(src_meta + n_ranks * 3 + 1, __popc(m));
+      base = __shfl_sync(FULL, base, __ffs(m) - 1);
+      if (own) own_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)k;
+    }
   }
 }
 
-// One group of TPR lanes per entry, EB entries per iteration: sum the row's gradients over the sources
-// in source order (from my inbox, where the sources' row passes scattered them), then optax.adagrad on
-// the local shard row.  Every load of the EB
-// entries (descriptors, bias scalars, then rows) is issued before its first use.
-template <int TPR, int EB>
-__global__ void __launch_bounds__(kThreads) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
-                                                                 const float* __restrict__ inbox_db, int n_ranks,
-                                                                 const int32_t* __restrict__ recv_ids,
-                                                                 const int32_t* __restrict__ src_meta,
-                                                                 const int32_t* __restrict__ desc, int D4,
-                                                                 float* __restrict__ rows, float* __restrict__ acc,
-                                                                 float* __restrict__ bias, float* __restrict__ bias_acc,
-                                                                 float lr, float eps) {
+// One group of TPR lanes per OWNER entry (compacted list), EB entries per iteration: sum the row's gradients
+// over the sources in source order (from my inbox, where the sources' row passes scattered them), then
+// optax.adagrad on the local shard row.  NR = number of sources rounded up to a power of two (compile time,
+// so the per-source loops carry no dead code); every load of the EB entries is issued before its first use.
+// (The first version looped over ESR_MAX_PEERS with predicates: 128 registers, 2 CTAs per SM, 2 TB/s.)
+template <int TPR, int NR, int EB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
+                                                                       const float* __restrict__ inbox_db, int n_ranks,
+                                                                       const int32_t* __restrict__ recv_ids,
+                                                                       const int32_t* __restrict__ src_meta,
+                                                                       const int32_t* __restrict__ desc,
+                                                                       const int32_t* __restrict__ own_list, int D4,
+                                                                       float* __restrict__ rows, float* __restrict__ acc,
+                                                                       float* __restrict__ bias, float* __restrict__ bias_acc,
+                                                                       float lr, float eps) {
   const int lane = threadIdx.x % TPR;
-  const int64_t total = src_meta[n_ranks * 3];
+  const int64_t total = src_meta[n_ranks * 3 + 1];
   const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
-  for (int64_t k0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; k0 < total; k0 += groups * EB) {
-    int gi[EB][ESR_MAX_PEERS];
-    int32_t x[EB];
-    bool any[EB];
+  for (int64_t i0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; i0 < total; i0 += groups * EB) {
+    int gi[EB][NR];
+    int64_t x[EB];
+    bool on[EB];
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
-      const int64_t k = k0 + e * groups;
-      any[e] = false;
-      x[e] = 0;
+      const int64_t i = i0 + e * groups;
+      on[e] = i < total;
+      const int64_t k = on[e] ? own_list[i] : 0;
+      x[e] = on[e] ? recv_ids[k] : 0;
 #pragma unroll
-      for (int q = 0; q < ESR_MAX_PEERS; ++q) {
-        gi[e][q] = (k < total && q < n_ranks) ? desc[k * n_ranks + q] : -1;
-        any[e] = any[e] || gi[e][q] >= 0;
-      }
-      if (any[e]) x[e] = recv_ids[k];
+      for (int q = 0; q < NR; ++q) gi[e][q] = (on[e] && q < n_ranks) ? desc[k * n_ranks + q] : -1;
     }
     // bias scalars (lane 0) -- loaded up front so their latency overlaps the row traffic
     float bp[EB], ba[EB], bg[EB];
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
       bp[e] = ba[e] = bg[e] = 0.f;
-      if (any[e] && lane == 0) {
+      if (on[e] && lane == 0) {
         bp[e] = bias[x[e]];
         ba[e] = bias_acc[x[e]];
 #pragma unroll
-        for (int q = 0; q < ESR_MAX_PEERS; ++q)
-          if (q < n_ranks && gi[e][q] >= 0) bg[e] += inbox_db[gi[e][q]];
+        for (int q = 0; q < NR; ++q)
+          if (gi[e][q] >= 0) bg[e] += inbox_db[gi[e][q]];
       }
     }
     for (int c = lane; c < D4; c += TPR) {
-      float4 g[EB], pv[EB], av[EB];
+      float4 g[EB][NR], pv[EB], av[EB];
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
-        g[e] = f4_zero();
-        if (any[e]) {
-          pv[e] = reinterpret_cast<const float4*>(rows)[(int64_t)x[e] * D4 + c];
-          av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + (int64_t)x[e] * D4 + c);
-#pragma unroll
-          for (int q = 0; q < ESR_MAX_PEERS; ++q)
-            if (q < n_ranks && gi[e][q] >= 0)
-              f4_add(g[e], ld_stream(inbox_dE + (int64_t)gi[e][q] * D4 + c));
+        if (on[e]) {
+          pv[e] = reinterpret_cast<const float4*>(rows)[x[e] * D4 + c];
+          av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + x[e] * D4 + c);
         }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) g[e][q] = gi[e][q] >= 0 ? ld_stream(inbox_dE + (int64_t)gi[e][q] * D4 + c) : f4_zero();
       }
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
-        if (any[e]) {
-          adagrad4(pv[e], av[e], g[e], lr, eps);
-          reinterpret_cast<float4*>(rows)[(int64_t)x[e] * D4 + c] = pv[e];
-          st_stream(reinterpret_cast<float4*>(acc) + (int64_t)x[e] * D4 + c, av[e]);
+        if (on[e]) {
+          float4 s = g[e][0];
+#pragma unroll
+          for (int q = 1; q < NR; ++q) f4_add(s, g[e][q]);   // source order: a missing source adds +0.0
+          adagrad4(pv[e], av[e], s, lr, eps);
+          reinterpret_cast<float4*>(rows)[x[e] * D4 + c] = pv[e];
+          st_stream(reinterpret_cast<float4*>(acc) + x[e] * D4 + c, av[e]);
         }
       }
     }
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
-      if (any[e] && lane == 0) {
+      if (on[e] && lane == 0) {
         adagrad1(bp[e], ba[e], bg[e], lr, eps);
         bias[x[e]] = bp[e];
         bias_acc[x[e]] = ba[e];
@@ -303,20 +319,34 @@ extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void*
 
 extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
                                           const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
-                                          int64_t map_stride, int32_t* desc, float lr, float eps, esr_stream_t stream_) {
+                                          int64_t map_stride, int32_t* desc, int64_t recv_cap, float lr, float eps,
+                                          esr_stream_t stream_) {
   ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
   ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
-  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0);
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && recv_cap > 0);
   ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D4 = shard->D / 4;
-  k_peer_resolve<<<4 * sm_count(), kThreads, 0, stream>>>(n_ranks, recv_ids, src_meta, slot_map, map_stride, desc);
+  int32_t* own_list = desc + recv_cap * n_ranks;
+  k_peer_resolve<<<4 * sm_count(), kThreads, 0, stream>>>(n_ranks, recv_ids, const_cast<int32_t*>(src_meta), slot_map,
+                                                          map_stride, desc, own_list);
   ESR_LAUNCH_CHECK();
   const int tpr = tpr_for(D4);
   const int grid = 8 * sm_count();
-  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 2><<<grid, kThreads, 0, stream>>>(
-                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, D4,
-                            shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)));
+#define ESR_MERGE(NR, EB, MINB)                                                                                          \
+  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, NR, EB, MINB><<<grid, kThreads, 0, stream>>>(                          \
+                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, own_list, \
+                            D4, shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)))
+  if (n_ranks == 1) {
+    ESR_MERGE(1, 4, 3);
+  } else if (n_ranks == 2) {
+    ESR_MERGE(2, 4, 2);
+  } else if (n_ranks <= 4) {
+    ESR_MERGE(4, 2, 3);
+  } else {
+    ESR_MERGE(8, 2, 2);
+  }
+#undef ESR_MERGE
   ESR_LAUNCH_CHECK();
   k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
   ESR_LAUNCH_CHECK();

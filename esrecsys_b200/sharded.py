@@ -289,7 +289,7 @@ class PeerShardedGloveTrainer:
         self.src_meta = torch.zeros(3 * 8 + 4, **i32)
         self.map_stride = V_max
         self.slot_map = torch.full((self.n, V_max), -1, **i32)
-        self.desc = torch.empty(self.recv_cap * self.n, **i32)
+        self.desc = torch.empty(self.recv_cap * (self.n + 1), **i32)
         self.s_side = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
@@ -354,7 +354,7 @@ class PeerShardedGloveTrainer:
         L.check(lib.esr_peer_merge_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
                                                L.ptr(self.recv_ids),
                                                L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride, L.ptr(self.desc),
-                                               self.lr, 1e-7, sp), "esr_peer_merge_adagrad_f32")
+                                               self.recv_cap, self.lr, 1e-7, sp), "esr_peer_merge_adagrad_f32")
         self.barrier()                                          # every owner has applied its updates
         self.ev_done[k].record(main)
         slot = self.t % self.loss_log.numel()

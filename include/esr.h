@@ -311,7 +311,8 @@ int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bi
                         float* out_bias, esr_stream_t stream);
 /* Owner `me`: from every source rank's published esr_route_plan_i32 outputs (send_counts[n],
  * send_local[]) copy the owner-local ids destined to me into recv_ids (source-major), write
- * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[3n] = total,
+ * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[3n] = total
+ * (src_meta[3n+1] is the merge's owner-entry counter; src_meta holds 3n + 4 ints),
  * and slot_map[s*map_stride + x] = position of row x in source s's list (slot_map is all -1 on entry
  * and is restored to -1 by esr_peer_merge_adagrad_f32). */
 /* Source side, after every rank published its route plan: emit_map[u] = owner << 27 | (offset of my
@@ -328,8 +329,8 @@ int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* pee
  * optax.adagrad to the shard in place.  All loads are local. */
 int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db,
                                int32_t n_ranks, const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
-                               int64_t map_stride, int32_t* desc /* scratch [recv_cap * n_ranks] */, float lr, float eps,
-                               esr_stream_t stream);
+                               int64_t map_stride, int32_t* desc /* scratch [recv_cap * (n_ranks + 1)] */, int64_t recv_cap,
+                               float lr, float eps, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Native decoders of the reference's record formats (HOST pointers).  Re-entrant,

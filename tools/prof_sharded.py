@@ -54,7 +54,7 @@ def main():
         L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, tr.rank, tr.recv_cap, L.ptr(tr.recv_ids),
                                           L.ptr(tr.src_meta), L.ptr(tr.slot_map), tr.map_stride, sp)); ev[i].record(); i += 1
         L.check(lib.esr_peer_merge_adagrad_f32(C.byref(tr.shard.struct()), L.ptr(tr.inbox_dE), L.ptr(tr.inbox_db), n, L.ptr(tr.recv_ids),
-                                               L.ptr(tr.src_meta), L.ptr(tr.slot_map), tr.map_stride, L.ptr(tr.desc), tr.lr, 1e-7, sp)); ev[i].record(); i += 1
+                                               L.ptr(tr.src_meta), L.ptr(tr.slot_map), tr.map_stride, L.ptr(tr.desc), tr.recv_cap, tr.lr, 1e-7, sp)); ev[i].record(); i += 1
         tr.barrier(); ev[i].record(); i += 1
         torch.cuda.synchronize()
         if it >= 3:
