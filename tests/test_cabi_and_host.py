@@ -115,3 +115,20 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_inbatch_cfg_layout_and_workspace_query():
+    """EsrInbatchCfg matches the header (u32, i32, 3 x i64, 2 x i32, 3 x f32, i32) and the workspace query is pure."""
+    from esrecsys_b200 import _lib
+    assert C.sizeof(_lib.EsrInbatchCfg) == 8 + 24 + 8 + 12 + 4
+    assert _lib.EsrInbatchCfg.D.offset == 32 and _lib.EsrInbatchCfg.b_norm.offset == 48
+    h = _lib.lib()
+    cfg = _lib.EsrInbatchCfg()
+    cfg.struct_size = C.sizeof(_lib.EsrInbatchCfg)
+    cfg.loss_kind, cfg.Bq, cfg.Bk, cfg.D, cfg.margin, cfg.scale, cfg.b_norm = 0, 8192, 8192, 128, 1.0, 1.0, 8192.0
+    full = h.esr_inbatch_workspace_bytes(C.byref(cfg))
+    assert full > 8192 * 8192 * 2                      # holds the bf16 dL/dS matrix
+    cfg.chunk_rows = 1024
+    assert 0 < h.esr_inbatch_workspace_bytes(C.byref(cfg)) < full
+    cfg.D = 100
+    assert h.esr_inbatch_workspace_bytes(C.byref(cfg)) == 0     # unsupported width is refused, not rounded
