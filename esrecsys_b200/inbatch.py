@@ -133,3 +133,72 @@ class TwoTowerInBatch:
         self.us.apply(scene_ids, dxs.contiguous())
         self.up.apply(product_ids, dxp.contiguous())
         return loss
+
+
+class ShardedSharedTableInBatch:
+    """configs[2] across the GPUs of one box ("table row-sharded 1 -> 8 B200 with index all-to-all"): the table is
+    sharded cyclically (owner = row % n, as the GloVe path), every rank holds B_local (query, item) pairs, and the
+    negatives of a query are the items of ALL ranks:
+
+      1. index plan of the local 2*B_local ids; unique rows fetched from their owners      RowExchange.fetch (ids / rows all-to-all)
+      2. Q, K_local = fetched rows in batch order                                          esr_permute_rows_f32
+      3. all-gather of K over the ranks                                                    NCCL
+      4. scores of the local queries against every item, loss, dQ, partial dK              esr_inbatch_fwd_bwd_bf16
+         (Bq = B_local, Bk = n * B_local, diag_off = rank * B_local, b_norm = n * B_local)
+      5. reduce-scatter of dK, all-reduce of the loss                                       NCCL
+      6. per-row sum of the 2*B_local gradient rows, gradient all-to-all, owners' Adagrad   RowExchange.push
+
+    One global step equals ``oracle.inbatch.shared_table_step`` on the rank-major concatenation of the batches."""
+
+    def __init__(self, V, D, B_local, lr=0.05, loss="hinge", margin=1.0, scale=1.0, group=None, device=None):
+        import torch.distributed as dist
+        from .sharded import LibesrOps, RowExchange, shard_rows
+        L.require_cuda()
+        self.dist, self.group = dist, group
+        self.n, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.V, self.D, self.B, self.lr = int(V), int(D), int(B_local), float(lr)
+        self.shard = engine.EmbeddingTable(shard_rows(V, self.rank, self.n), D, self.dev, sparse=False, adagrad=True)
+        self.ops = LibesrOps(self.dev)
+        self.xchg = RowExchange(self.ops, self.shard, group)
+        n_slots = 2 * self.B
+        self.plan = engine.IndexPlan(n_slots, V, self.dev, with_partner=False)
+        Bg = self.B * self.n
+        self.scorer = engine.InBatchScorer(self.B, D, Bk=Bg, loss=loss, diag_off=self.rank * self.B, margin=margin,
+                                           scale=scale, b_norm=Bg, device=self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.X = torch.empty(n_slots, D, **f32)
+        self.K_all = torch.empty(Bg, D, **f32)
+        self.dX = torch.empty(n_slots, D, **f32)
+        self.scorer.dQ = self.dX[:self.B]
+        self.gsum = torch.empty(n_slots, D, **f32)
+        self.zeros_b = torch.zeros(n_slots, **f32)
+        self.remap = torch.empty(n_slots, dtype=torch.int32, device=self.dev)
+
+    def load_dense(self, E):
+        idx = torch.arange(self.rank, self.V, self.n)
+        self.shard.rows0.copy_(torch.as_tensor(E)[idx].to(self.dev))
+
+    def gather_dense(self):
+        E = torch.zeros(self.V, self.D, device=self.dev)
+        E[torch.arange(self.rank, self.V, self.n, device=self.dev)] = self.shard.rows0
+        self.dist.all_reduce(E, group=self.group)
+        return E
+
+    def step(self, ids):
+        """ids: int32 (2, B_local) global rows [queries ; items].  Returns the GLOBAL loss (device scalar)."""
+        dist, B, D = self.dist, self.B, self.D
+        flat = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
+        plan = self.plan.build(flat)
+        rows, _ = self.xchg.fetch(plan.uniq, plan.n_uniq)
+        plan.remap_ids(self.remap)
+        self.ops.permute_rows(rows, self.remap, 2 * B, False, self.X)           # X[s] = row of slot s
+        dist.all_gather_into_tensor(self.K_all, self.X[B:], group=self.group)
+        loss, _, dK = self.scorer.run(self.X[:B], self.K_all)
+        dist.reduce_scatter_tensor(self.dX[B:], dK, group=self.group)
+        loss = loss.clone()
+        dist.all_reduce(loss, group=self.group)
+        L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), D, L.ptr(self.dX), None, L.ptr(self.gsum), None,
+                                                 L.stream_ptr()), "esr_segment_sum_rows_f32")
+        self.xchg.push(self.gsum, self.zeros_b, self.lr)
+        return loss[0]

@@ -134,3 +134,57 @@ def test_row_exchange_gloo(world):
     for p in procs:
         p.join(30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _inbatch_worker(rank, world, port, kind, q):
+    """The sharded in-batch decomposition (esrecsys_b200/inbatch.py, ShardedSharedTableInBatch) with gloo collectives:
+    every rank scores its B_local queries against the all-gathered items (diag_off = rank * B_local, b_norm = global B);
+    concatenated dQ, reduce-scattered dK and all-reduced loss must equal the single global step of the oracle."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import inbatch as oib
+        B, D = 24, 16
+        Bg = B * world
+        rng = np.random.default_rng(3)
+        Q = oib.bf16_round(rng.standard_normal((Bg, D)).astype(np.float32))
+        K = oib.bf16_round(rng.standard_normal((Bg, D)).astype(np.float32))
+        lo, hi = rank * B, (rank + 1) * B
+        K_all = torch.empty(Bg, D)
+        dist.all_gather_into_tensor(K_all, torch.from_numpy(K[lo:hi].copy()))
+        assert np.array_equal(K_all.numpy(), K)
+        fn = oib.hinge if kind == "hinge" else oib.softmax
+        kw = dict(margin=0.5) if kind == "hinge" else {}
+        loss, dQ, dK_part, _ = fn(Q[lo:hi], K_all.numpy(), off=rank * B, scale=0.25, b_norm=Bg, **kw)
+        dK_loc = torch.empty(B, D)
+        dist.reduce_scatter_tensor(dK_loc, torch.from_numpy(dK_part))
+        lt = torch.tensor([float(loss)], dtype=torch.float64)
+        dist.all_reduce(lt)
+        gl, gdQ, gdK, _ = fn(Q, K, off=0, scale=0.25, b_norm=Bg, **kw)
+        assert abs(lt.item() - gl) < 1e-5 * max(1.0, abs(gl))
+        np.testing.assert_allclose(dQ, gdQ[lo:hi], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(dK_loc.numpy(), gdK[lo:hi], rtol=1e-5, atol=1e-6)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("kind", ["hinge", "softmax"])
+def test_sharded_inbatch_decomposition_gloo(kind):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100) + (0 if kind == "hinge" else 1)
+    procs = [ctx.Process(target=_inbatch_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res

@@ -84,3 +84,53 @@ def test_route_plan_bit_exact():
         assert np.array_equal(counts.cpu().numpy(), oc)
         assert np.array_equal(order[:U].cpu().numpy(), oo)
         assert np.array_equal(send_local[:U].cpu().numpy(), osl)
+
+
+def _inbatch_worker(rank, world, port, V, D, B_loc, steps, kind, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from esrecsys_b200 import synth
+        from esrecsys_b200.inbatch import ShardedSharedTableInBatch
+        from oracle import inbatch as oib
+        rng = np.random.default_rng(11)
+        E = (rng.standard_normal((V, D)) / D ** 0.25).astype(np.float32)
+        qs, ks = synth.pair_batches(V, V, B_loc * world, steps, 5)      # global batches, rank-major slices
+        tr = ShardedSharedTableInBatch(V, D, B_loc, lr=0.05, loss=kind)
+        tr.load_dense(E)
+        Eo, acc = E.copy(), np.full_like(E, 0.1)
+        lo, hi = rank * B_loc, (rank + 1) * B_loc
+        for s in range(steps):
+            ids = torch.from_numpy(np.stack([qs[s][lo:hi], ks[s][lo:hi]])).cuda()
+            got = float(tr.step(ids).item())
+            want = oib.shared_table_step(Eo, acc, qs[s], ks[s], 0.05, kind)
+            assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (s, got, want)
+        Eg = tr.gather_dense().cpu().numpy()
+        bad = np.abs(Eg - Eo) > 1e-5 + 1e-5 * np.abs(Eo)
+        assert bad.mean() < 2e-3 and np.abs(Eg - Eo).max() < 1e-3, (bad.mean(), np.abs(Eg - Eo).max())
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("kind", ["hinge", "softmax"])
+def test_sharded_inbatch_matches_single_table_oracle(kind):
+    """configs[2] sharded: n ranks with B_local pairs each == one in-batch step over the concatenated batch."""
+    world = max(1, min(4, torch.cuda.device_count()))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40) + (0 if kind == "hinge" else 1)
+    procs = [ctx.Process(target=_inbatch_worker, args=(r, world, port, 4000, 128, 256, 3, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] == "ok" for r in res), res
