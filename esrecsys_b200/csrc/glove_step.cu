@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kPrepItems = 4;
 constexpr int kCombineThreads = 512;
 constexpr int kCombineWarps = kCombineThreads / 32;
 constexpr int32_t kRowMask = 0x3fffffff;
@@ -107,7 +108,7 @@ size_t carve_ws(void* base, int64_t B, int32_t D, int32_t chunk_in, GloveWs* w) 
   t.nchunks = ceil_div(n, chunk);
   // capacity: with chunk == 0 the chunk length is chosen per device, so size for the smallest one
   const int64_t cap_chunks = chunk_in <= 0 ? ceil_div(n, kMinAutoChunk) : t.nchunks;
-  t.prep_blocks = (int32_t)ceil_div(n, kThreads);
+  t.prep_blocks = (int32_t)ceil_div(n, kThreads * kPrepItems);
   t.row_blocks = (int32_t)ceil_div(t.nchunks, kWarps);
   const int64_t cap_row_blocks = ceil_div(cap_chunks, kWarps);
   t.skv = c.take<int32_t>(n);
@@ -163,26 +164,56 @@ __global__ void __launch_bounds__(kThreads) k_glove_prep(const int32_t* __restri
                                                          float* __restrict__ blk, float* __restrict__ scalars) {
   __shared__ float red[32 * 3];
   __shared__ bool last_block;
-  const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  // kPrepItems slots per thread, every load of a stage issued before the first use: the kernel is a chain of
+  // dependent gathers (perm -> counts, row -> bias / version), so its time is (latency x stages), not bytes.
+  const int64_t p0 = blockIdx.x * (int64_t)(kThreads * kPrepItems) + threadIdx.x;
   float v[3] = {0.f, 0.f, 0.f};
-  if (p < n) {
-    const int32_t row = sk[p], q = partner[p];
-    const int64_t s = perm[p];
-    const bool role_i = s < B;
-    const float x = counts[role_i ? s : s - B];
-    SlotRec r;
-    r.w = powf(fminf(1.f, x / x_max), alpha);
-    r.t = log10f(1.f + x);
-    // b[i] + b[j]: fp add commutes, so both roles of a pair hold the same bits
-    r.bs = role_i ? bias[row] + bias[q] : bias[q] + bias[row];
-    const int32_t vr = ver ? ver[row] : 0, vq = ver ? ver[q] : 0;
-    r.code = (int32_t)((uint32_t)q | (role_i ? (uint32_t)kRoleBit : 0u) | ((uint32_t)vq << 31));
-    rec[p] = r;
-    skv[p] = (int32_t)((uint32_t)row | ((uint32_t)vr << 31));
-    if (role_i) {
-      v[0] = r.bs;
-      v[1] = r.bs * r.bs;
-      v[2] = r.w;
+  int32_t row[kPrepItems], q[kPrepItems], s[kPrepItems];
+#pragma unroll
+  for (int k = 0; k < kPrepItems; ++k) {
+    const int64_t p = p0 + (int64_t)k * kThreads;
+    row[k] = q[k] = s[k] = 0;
+    if (p < n) {
+      row[k] = sk[p];
+      q[k] = partner[p];
+      s[k] = perm[p];
+    }
+  }
+  float x[kPrepItems], br[kPrepItems], bq[kPrepItems];
+  int32_t vr[kPrepItems], vq[kPrepItems];
+#pragma unroll
+  for (int k = 0; k < kPrepItems; ++k) {
+    const int64_t p = p0 + (int64_t)k * kThreads;
+    x[k] = br[k] = bq[k] = 0.f;
+    vr[k] = vq[k] = 0;
+    if (p < n) {
+      x[k] = counts[s[k] < B ? s[k] : s[k] - B];
+      br[k] = bias[row[k]];
+      bq[k] = bias[q[k]];
+      if (ver) {
+        vr[k] = ver[row[k]];
+        vq[k] = ver[q[k]];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kPrepItems; ++k) {
+    const int64_t p = p0 + (int64_t)k * kThreads;
+    if (p < n) {
+      const bool role_i = s[k] < B;
+      SlotRec r;
+      r.w = powf(fminf(1.f, x[k] / x_max), alpha);
+      r.t = log10f(1.f + x[k]);
+      // b[i] + b[j]: fp add commutes, so both roles of a pair hold the same bits
+      r.bs = br[k] + bq[k];
+      r.code = (int32_t)((uint32_t)q[k] | (role_i ? (uint32_t)kRoleBit : 0u) | ((uint32_t)vq[k] << 31));
+      rec[p] = r;
+      skv[p] = (int32_t)((uint32_t)row[k] | ((uint32_t)vr[k] << 31));
+      if (role_i) {
+        v[0] += r.bs;
+        v[1] = fmaf(r.bs, r.bs, v[1]);
+        v[2] += r.w;
+      }
     }
   }
   block_sum<3>(v, red);
@@ -690,7 +721,36 @@ __device__ __forceinline__ void grow_from_smem(Row<NV>& r, const float4* sp, int
   }
 }
 
-template <int G, int NV, int MINB>
+// FULLD: D4 == G * NV, every lane column exists -> no per-column bounds checks in the hot loop
+template <int G, int NV, bool FULLD>
+__device__ __forceinline__ void grow_copy_async_f(uint32_t dst, const float4* __restrict__ src, int gl, int D4, bool keep) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    if (FULLD || c < D4) cp_async16(dst + 16u * c, src + c, keep);
+  }
+}
+template <int G, int NV, bool FULLD>
+__device__ __forceinline__ void grow_from_smem_f(Row<NV>& r, const float4* sp, int gl, int D4) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    r.v[k] = (FULLD || c < D4) ? sp[c] : f4_zero();
+  }
+}
+template <int G, int NV, bool FULLD>
+__device__ __forceinline__ void grow_store_f(const Row<NV>& r, float4* __restrict__ p, int gl, int D4, bool stream) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * G + gl;
+    if (FULLD || c < D4) {
+      if (stream) st_stream(p + c, r.v[k]);
+      else p[c] = r.v[k];
+    }
+  }
+}
+
+template <int G, int NV, int MINB, bool FULLD>
 __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const RowsArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ float red[32 * 2];
@@ -740,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
     if (s < cnt) {
       const int32_t code = gm.rec[s].code;
       const uint32_t q = (uint32_t)(code & kRowMask);
-      grow_copy_async<G, NV>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl,
+      grow_copy_async_f<G, NV, FULLD>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl,
                              a.D4, true);
     }
   };
@@ -752,9 +812,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       const bool head = k1 != k0, end = k1 != k2;
       const uint32_t row = (uint32_t)(k1 & kRowMask);
       if (s == 0 || head)
-        grow_copy_async<G, NV>(bufs_u32 + 3u * RB, ((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, true);
+        grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 3u * RB, ((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, true);
       if (!a.emit && end && (head || started_if_not_head))
-        grow_copy_async<G, NV>(bufs_u32 + 4u * RB, accp + (uint64_t)row * D4, gl, a.D4, false);
+        grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 4u * RB, accp + (uint64_t)row * D4, gl, a.D4, false);
     }
   };
 
@@ -776,28 +836,26 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   for (int s = 0; s < a.chunk; ++s) {
     const bool active = s < cnt;
     cp_async_wait1();  // partner(s), self(s), acc(s) have landed; partner(s+1) may still be in flight
-    Row<NV> P, A;
-    row_zero(P);
+    Row<NV> P, A;   // P, A, rec are only consumed when the slot is active (the group_sum must still run warp-wide)
     bool is_head = false, is_end = false;
     int32_t key_cur = kNoKey;
     SlotRec rec;
-    rec.code = 0; rec.w = 0.f; rec.t = 0.f; rec.bs = 0.f;
     if (active) {
       const int32_t k0 = gm.keys[s], k2 = gm.keys[2 + s];
       key_cur = gm.keys[1 + s];
       rec = gm.rec[s];
       is_head = key_cur != k0;
       is_end = key_cur != k2;
-      grow_from_smem<G, NV>(P, reinterpret_cast<const float4*>(bufs + (size_t)(s % 3) * RB), gl, a.D4);
+      grow_from_smem_f<G, NV, FULLD>(P, reinterpret_cast<const float4*>(bufs + (size_t)(s % 3) * RB), gl, a.D4);
       if (s == 0 || is_head) {
-        grow_from_smem<G, NV>(cur, reinterpret_cast<const float4*>(bufs + 3 * (size_t)RB), gl, a.D4);
+        grow_from_smem_f<G, NV, FULLD>(cur, reinterpret_cast<const float4*>(bufs + 3 * (size_t)RB), gl, a.D4);
         row_zero(grad);
         bacc = 0.f;
         started_here = is_head;
         if (is_head && s > 0) ++u;
       }
       if (!a.emit && is_end && started_here)
-        grow_from_smem<G, NV>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
+        grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
     }
     // every buffer read above is private to the lane that filled it: refill without a barrier
     issue_self_acc(s + 1, started_here && !is_end);
@@ -828,19 +886,19 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
             base = a.peers.dE[e >> kEmitShift];
             e &= (1u << kEmitShift) - 1u;
           }
-          grow_store<G, NV>(grad, reinterpret_cast<float4*>(base) + e * D4, gl, a.D4, true);
+          grow_store_f<G, NV, FULLD>(grad, reinterpret_cast<float4*>(base) + e * D4, gl, a.D4, true);
         } else {
           const uint32_t row = (uint32_t)(key_cur & kRowMask);
           const int v = (key_cur >> 31) & 1;
 #pragma unroll
           for (int k = 0; k < NV; ++k) adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
-          grow_store<G, NV>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
-          grow_store<G, NV>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
+          grow_store_f<G, NV, FULLD>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
+          grow_store_f<G, NV, FULLD>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
         }
         if (gl == 0) a.bsum[u] = bacc;
       } else if (is_end || s == cnt - 1) {
         const int slot = (!is_end && started_here) ? 1 : 0;
-        grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.part) + (uint64_t)(c * 2 + slot) * D4, gl, a.D4, false);
+        grow_store_f<G, NV, FULLD>(grad, reinterpret_cast<float4*>(a.part) + (uint64_t)(c * 2 + slot) * D4, gl, a.D4, false);
         if (gl == 0) {
           a.parts[c * 2 + slot] = bacc;
           if (slot == 1) {
@@ -1308,11 +1366,14 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
     static size_t configured = 0;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && smem > configured) {
-      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       configured = smem;
     }
-    k_glove_rows_grp_async<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
+    if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
+    else k_glove_rows_grp_async<G, NV, 2, false><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if (phases & 1) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
