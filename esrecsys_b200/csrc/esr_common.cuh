@@ -114,6 +114,50 @@ __device__ __forceinline__ void f4_add(float4& acc, float4 v) {
   acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: fma.rn.f32x2 ...): each half is an ordinary IEEE op, so a packed
+// sequence is bit-identical to the same scalar sequence; it halves the issue slots of the row pass, which is
+// issue-bound on duplicate-heavy streams.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // d += a * b
+  asm("{\n .reg .b64 ra, rb, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%0, %1};\n"
+      " fma.rn.f32x2 rc, ra, rb, rc;\n mov.b64 {%0, %1}, rc;\n}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // d = a * b
+  asm("{\n .reg .b64 ra, rb, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mul.rn.f32x2 rc, ra, rb;\n mov.b64 {%0, %1}, rc;\n}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // d = a + b
+  asm("{\n .reg .b64 ra, rb, rc;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n add.rn.f32x2 rc, ra, rb;\n mov.b64 {%0, %1}, rc;\n}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// dot of two float4 pairs into a 2-lane accumulator (acc0 gets x,z products, acc1 gets y,w)
+__device__ __forceinline__ void f4_dot2(float& acc0, float& acc1, float4 a, float4 b) {
+  ffma2(acc0, acc1, a.x, a.y, b.x, b.y);
+  ffma2(acc0, acc1, a.z, a.w, b.z, b.w);
+}
+__device__ __forceinline__ void f4_fma2(float4& acc, float s, float4 v) {  // same bits as f4_fma
+  ffma2(acc.x, acc.y, s, s, v.x, v.y);
+  ffma2(acc.z, acc.w, s, s, v.z, v.w);
+}
+// optax.adagrad on two elements; same bits as two adagrad1 calls when eps > 0 (a == 0 then implies g == 0 and the
+// update is exactly 0 either way, so the a > 0 guard of adagrad1 is only needed for eps == 0)
+__device__ __forceinline__ void adagrad2(float& p0, float& p1, float& a0, float& a1, float g0, float g1, float lr, float eps) {
+  ffma2(a0, a1, g0, g1, g0, g1);
+  float t0, t1;
+  fadd2(t0, t1, a0, a1, eps, eps);
+  const float i0 = rsqrtf(t0), i1 = rsqrtf(t1);
+  float s0, s1;
+  fmul2(s0, s1, -lr, -lr, g0, g1);
+  ffma2(p0, p1, s0, s1, i0, i1);
+}
+__device__ __forceinline__ void adagrad4_packed(float4& p, float4& a, float4 g, float lr, float eps) {
+  adagrad2(p.x, p.y, a.x, a.y, g.x, g.y, lr, eps);
+  adagrad2(p.z, p.w, a.z, a.w, g.z, g.w, lr, eps);
+}
+
 // optax.adagrad: a += g^2 ; p -= lr * g * rsqrt(a + eps)   (0 where a == 0)
 __device__ __forceinline__ void adagrad1(float& p, float& a, float g, float lr, float eps) {
   a = fmaf(g, g, a);

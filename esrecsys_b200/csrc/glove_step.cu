@@ -863,10 +863,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
     issue_partner(s + 2);
     cp_async_commit();
 
-    float d = 0.f;
+    float d0 = 0.f, d1 = 0.f;  // packed pair accumulators (FFMA2): the same tree in both roles of a pair
 #pragma unroll
-    for (int k = 0; k < NV; ++k) d += f4_dot(cur.v[k], P.v[k]);
-    const float dot = group_sum<G>(d);
+    for (int k = 0; k < NV; ++k) f4_dot2(d0, d1, cur.v[k], P.v[k]);
+    const float dot = group_sum<G>(d0 + d1);
     if (active) {
       const float res = rec.t - dot;
       const float rr = a.per_pair ? res - rec.bs : res;
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
         sums[1] = fmaf(rec.w * rr, rr, sums[1]);
       }
 #pragma unroll
-      for (int k = 0; k < NV; ++k) f4_fma(grad.v[k], g, P.v[k]);
+      for (int k = 0; k < NV; ++k) f4_fma2(grad.v[k], g, P.v[k]);
       bacc += a.per_pair ? g : rec.bs;
       if (is_end && started_here) {
         if (a.emit) {
@@ -891,7 +891,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
           const uint32_t row = (uint32_t)(key_cur & kRowMask);
           const int v = (key_cur >> 31) & 1;
 #pragma unroll
-          for (int k = 0; k < NV; ++k) adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+          for (int k = 0; k < NV; ++k) {
+            if (a.eps > 0.f) adagrad4_packed(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+            else adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+          }
           grow_store_f<G, NV, FULLD>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
           grow_store_f<G, NV, FULLD>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
         }
@@ -936,15 +939,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Bounded spin: a lost arrival traps (a launch error the host sees) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-  } while (!ok);
+    if (!ok && spin > (1u << 24)) __trap();
+  }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -1047,6 +1052,208 @@ __global__ void __launch_bounds__(kThreads, tma_min_blocks(NK)) k_glove_rows_tma
     }
   }
   store_block_sums(a, sums, red, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2, group variant with a per-group FIFO of bulk copies (ESR_IMPL_AUTO + cfg.reserved == 2; A/B candidate
+// for the default).  Same work split as k_glove_rows_grp_async, different staging: every row a chunk needs
+// (per slot, in order: self row at a segment head, accumulator row at a segment end, partner row) goes through
+// ONE ring of kFifoBufs generic row buffers per group, filled by cp.async.bulk (one instruction per 512-byte row,
+// issued by the group's first lane, completion on a per-buffer mbarrier).  The producer side runs ahead as far as
+// the ring allows (up to kFifoAhead slots), so a group that only needs partner rows (most slots of a Zipf
+// stream) keeps 4 rows in flight instead of 1-2: the async variant's fixed {self, acc, partner} buffers left
+// ~70 % of the staged bytes idle at its wait point (measured: 2800 clk per slot-step, latency-bound).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFifoBufs = 5;
+constexpr int kFifoAhead = 4;
+
+template <int G, int NV, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_fifo(const RowsArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  __shared__ float red[32 * 2];
+  constexpr int GP = 32 / G;
+  constexpr int NB = kFifoBufs;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, grp = lane / G;
+  const int gidx = (threadIdx.x >> 5) * GP + grp;
+  constexpr int kGroups = kWarps * GP;
+  GroupMeta& gm = reinterpret_cast<GroupMeta*>(dyn_raw)[gidx];
+  const uint32_t D4 = (uint32_t)a.D4;
+  const uint32_t RB = D4 * 16u;
+  unsigned char* bufs = dyn_raw + (size_t)kGroups * sizeof(GroupMeta) + (size_t)gidx * NB * RB;
+  const uint32_t bufs_u32 = smem_u32(bufs);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_raw + (size_t)kGroups * sizeof(GroupMeta) + (size_t)kGroups * NB * RB) + gidx * NB;
+  const uint32_t bar0 = smem_u32(bars);
+  if (gl == 0) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  uint64_t pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  uint32_t phase = 0;  // bit b = parity the next wait on buffer b expects
+  const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
+  const float* const rows0 = a.rows[0];
+  const float* const rows1 = a.rows[1];
+  float sums[2] = {0.f, 0.f};
+  const int64_t nitems = (a.nchunks + GP - 1) / GP;
+  for (;;) {
+    int64_t item = 0;
+    if (lane == 0) item = atomicAdd(a.work_counter, 1);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= nitems) break;
+    const int64_t c = a.nchunks - 1 - (item * GP + grp);
+    const int64_t p0 = c * a.chunk;
+    const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+    __syncwarp();  // the previous item's readers are done with gm
+    for (int s = gl; s < cnt; s += G) {
+      gm.keys[1 + s] = a.skv[p0 + s];
+      gm.rec[s] = a.rec[p0 + s];
+    }
+    if (gl == 0 && cnt > 0) {
+      gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
+      gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+      gm.keys[2 + cnt] = kNoKey;
+      gm.keys[3 + cnt] = kNoKey;
+    }
+    __syncwarp();
+    // index of the first true head of the chunk: slots before it continue a segment started in an earlier chunk
+    int first_head = cnt;
+    for (int s = 0; s < cnt; ++s)
+      if (gm.keys[1 + s] != gm.keys[s]) {
+        first_head = s;
+        break;
+      }
+
+    // ---- producer side: rows of slot t into the ring, FIFO order {self, acc, partner} ----
+    int pb = 0, cb = 0, issued = 0;  // buffers issued / consumed (this chunk), slots issued
+    auto slot_needs = [&](int t, bool& need_self, bool& need_acc) {
+      const int32_t k0 = gm.keys[t], k1 = gm.keys[1 + t], k2 = gm.keys[2 + t];
+      need_self = (t == 0) || (k1 != k0);
+      need_acc = !a.emit && (k1 != k2) && t >= first_head;
+    };
+    auto put = [&](const float* src, bool stream) {
+      const int b = pb % NB;
+      if (gl == 0) {
+        mbar_expect_tx(bar0 + 8u * b, RB);
+        if (stream) bulk_g2s_hint(bufs_u32 + (uint32_t)b * RB, src, RB, bar0 + 8u * b, pol_stream);
+        else bulk_g2s(bufs_u32 + (uint32_t)b * RB, src, RB, bar0 + 8u * b);
+      }
+      ++pb;
+    };
+    auto top_up = [&](int s) {
+      while (issued < cnt && issued <= s + kFifoAhead) {
+        bool ns, na;
+        slot_needs(issued, ns, na);
+        if (pb - cb + 1 + (ns ? 1 : 0) + (na ? 1 : 0) > NB) break;
+        const int32_t k1 = gm.keys[1 + issued];
+        const uint32_t row = (uint32_t)(k1 & kRowMask);
+        if (ns) put(((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * a.D4 * 4, false);
+        if (na) put(a.acc + (uint64_t)row * a.D4 * 4, true);
+        const int32_t code = gm.rec[issued].code;
+        put(((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)(uint32_t)(code & kRowMask) * a.D4 * 4, false);
+        ++issued;
+      }
+    };
+    // ---- consumer side: next buffer of the ring -> registers ----
+    auto take = [&](Row<NV>& r) {
+      const int b = cb % NB;
+      mbar_wait(bar0 + 8u * b, (phase >> b) & 1u);
+      phase ^= 1u << b;
+      grow_from_smem<G, NV>(r, reinterpret_cast<const float4*>(bufs + (size_t)b * RB), gl, a.D4);
+      ++cb;
+    };
+
+    Row<NV> cur, grad;
+    row_zero(cur);
+    row_zero(grad);
+    float bacc = 0.f;
+    bool started_here = false;
+    int64_t u = cnt > 0 ? a.useg[p0] : 0;
+    for (int s = 0; s < a.chunk; ++s) {
+      const bool active = s < cnt;
+      __syncwarp();  // every lane has read the buffers released in the previous slot: they may be refilled
+      if (active) top_up(s);
+      Row<NV> P, A;
+      row_zero(P);
+      bool is_head = false, is_end = false;
+      int32_t key_cur = kNoKey;
+      SlotRec rec;
+      rec.code = 0; rec.w = 0.f; rec.t = 0.f; rec.bs = 0.f;
+      if (active) {
+        bool ns, na;
+        slot_needs(s, ns, na);
+        key_cur = gm.keys[1 + s];
+        rec = gm.rec[s];
+        is_head = key_cur != gm.keys[s];
+        is_end = key_cur != gm.keys[2 + s];
+        if (ns) {
+          take(cur);
+          row_zero(grad);
+          bacc = 0.f;
+          started_here = is_head;
+          if (is_head && s > 0) ++u;
+        }
+        if (na) take(A);
+        take(P);
+      }
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) d += f4_dot(cur.v[k], P.v[k]);
+      const float dot = group_sum<G>(d);
+      if (active) {
+        const float res = rec.t - dot;
+        const float rr = a.per_pair ? res - rec.bs : res;
+        const float g = a.c2B * rec.w * (a.per_pair ? rr : res - mbs);
+        if (rec.code & kRoleBit) {
+          sums[0] = fmaf(rec.w, res, sums[0]);
+          sums[1] = fmaf(rec.w * rr, rr, sums[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) f4_fma(grad.v[k], g, P.v[k]);
+        bacc += a.per_pair ? g : rec.bs;
+        if (is_end && started_here) {
+          if (a.emit) {
+            uint64_t e = a.emit_map ? (uint64_t)a.emit_map[u] : (uint64_t)u;
+            float* base = a.dE;
+            if (a.peers.on) {
+              base = a.peers.dE[e >> kEmitShift];
+              e &= (1u << kEmitShift) - 1u;
+            }
+            grow_store<G, NV>(grad, reinterpret_cast<float4*>(base) + e * D4, gl, a.D4, true);
+          } else {
+            const uint32_t row = (uint32_t)(key_cur & kRowMask);
+            const int v = (key_cur >> 31) & 1;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) adagrad4(cur.v[k], A.v[k], grad.v[k], a.lr, a.eps);
+            grow_store<G, NV>(cur, reinterpret_cast<float4*>(a.wrows[1 - v]) + (uint64_t)row * D4, gl, a.D4, true);
+            grow_store<G, NV>(A, reinterpret_cast<float4*>(a.acc) + (uint64_t)row * D4, gl, a.D4, true);
+          }
+          if (gl == 0) a.bsum[u] = bacc;
+        } else if (is_end || s == cnt - 1) {
+          const int slot = (!is_end && started_here) ? 1 : 0;
+          grow_store<G, NV>(grad, reinterpret_cast<float4*>(a.part) + (uint64_t)(c * 2 + slot) * D4, gl, a.D4, false);
+          if (gl == 0) {
+            a.parts[c * 2 + slot] = bacc;
+            if (slot == 1) {
+              const int64_t np = (a.seg_off[u + 1] - 1) / a.chunk - c + 1;
+              const int heavy = np > kHeavyParts;
+              const int e = atomicAdd(a.wl_count + heavy, 1);
+              (heavy ? a.wl_heavy : a.wl_light)[e] = (int32_t)c;
+            }
+          }
+        }
+      }
+    }
+  }  // work loop
+  float v[2] = {gl == 0 ? sums[0] : 0.f, gl == 0 ? sums[1] : 0.f};
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) {
+    a.rows_blk[blockIdx.x * 2 + 0] = v[0];
+    a.rows_blk[blockIdx.x * 2 + 1] = v[1];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1354,14 +1561,24 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
-                           bool use_async = false, int grid_override = 0) {
+                           bool use_async = false, int grid_override = 0, bool fifo = false) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
   if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
     const int64_t cap = grid_override > 0 ? grid_override : 2 * (int64_t)sm_count();
     row_blocks = (int)std::min<int64_t>(row_blocks, cap);
   }
-  if ((phases & 1) && use_async) {
+  if ((phases & 1) && use_async && fifo) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
+    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + kFifoBufs * ((size_t)a.D4 * 16 + 8));
+    static size_t configured_fifo = 0;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && smem > configured_fifo) {
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_fifo<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_fifo = smem;
+    }
+    k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
+    ESR_LAUNCH_CHECK();
+  } else if ((phases & 1) && use_async) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
     static size_t configured = 0;  // per <G, NV> instantiation
@@ -1442,10 +1659,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     if (d4 <= 16) return launch_rows_grp<4, 4, 1>(a, w, scalars, phases, stream);
     const bool as = cfg->reserved != 1;  // reserved == 1: keep rows in registers (A/B probe)
     const int go = cfg->row_blocks;
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go);
+    const bool ff = cfg->reserved == 2;  // reserved == 2: bulk-copy FIFO staging (A/B probe)
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff);
   }
   switch (nk) {
     case 1:

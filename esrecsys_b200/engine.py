@@ -170,7 +170,7 @@ class GloveStep:
 
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", eps=1e-7,
                  x_max=100.0, alpha=0.75, chunk=0, emit_grads=False, B_global=None, impl="auto", dE=None, db=None,
-                 row_blocks=0):
+                 row_blocks=0, variant=0):
         self.table = table
         self.B = int(B)
         dev = table.device
@@ -178,12 +178,15 @@ class GloveStep:
         cfg.struct_size = C.sizeof(L.EsrGloveCfg)
         cfg.bias_mode = L.BIAS_MODES[bias_mode]
         cfg.rows_mode = L.ROWS_EMIT_GRADS if emit_grads else L.ROWS_UPDATE
+        if impl == "fifo":          # the group row pass with bulk-copy FIFO staging (A/B candidate for the default)
+            impl, variant = "auto", 2
         cfg.impl = impl if isinstance(impl, int) else {"auto": L.IMPL_AUTO, "ldg": L.IMPL_LDG, "tma": L.IMPL_TMA}[impl]
         cfg.B = self.B
         cfg.B_global = int(B_global if B_global is not None else B)
         cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
         cfg.chunk = chunk
         cfg.row_blocks = int(row_blocks)
+        cfg.reserved = int(variant)     # row-pass staging A/B: 0 cp.async (default), 1 registers, 2 bulk-copy FIFO
         self.cfg = cfg
         self.emit = bool(emit_grads)
         self.ws_bytes = int(L.lib().esr_glove_workspace_bytes(self.B, table.D, chunk))

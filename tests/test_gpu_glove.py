@@ -103,7 +103,7 @@ def _emit(E, b, ids, counts, bias_mode, chunk=0, impl="auto"):
     return sc, step.dE[:U].cpu().numpy(), step.db[:U].cpu().numpy(), plan
 
 
-@pytest.mark.parametrize("impl", ["auto", "ldg", "tma"])
+@pytest.mark.parametrize("impl", ["auto", "ldg", "tma", "fifo"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B,chunk", [
     (10000, 64, 2048, 0),      # BASELINE config 1 shape
@@ -145,7 +145,7 @@ def test_grads_i_equals_j_and_literal_loss():
     np.testing.assert_allclose(sc[5], lit, rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("impl", ["auto", "ldg", "tma"])
+@pytest.mark.parametrize("impl", ["auto", "ldg", "tma", "fifo"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B,uniform", [(10000, 64, 2048, False), (300, 128, 1024, False), (50000, 128, 8192, True),
                                            (20, 256, 4096, False)])

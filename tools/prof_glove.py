@@ -27,12 +27,13 @@ def main():
     ap.add_argument("--nbatch", type=int, default=8)
     ap.add_argument("--bias_mode", default="reference_broadcast")
     ap.add_argument("--impl", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
     a = ap.parse_args()
     ids, counts = synth.glove_batches(a.V, a.B, a.nbatch, 0, a.uniform)
     U = np.mean([np.unique(ids[k]).size for k in range(a.nbatch)])
     t = engine.EmbeddingTable(a.V, a.D)
     t.rows0.normal_(0, 1.0 / np.sqrt(a.D))
-    step = engine.GloveStep(t, a.B, bias_mode=a.bias_mode, chunk=a.chunk, impl=a.impl)
+    step = engine.GloveStep(t, a.B, bias_mode=a.bias_mode, chunk=a.chunk, impl=a.impl, variant=a.variant)
     plan = engine.IndexPlan(2 * a.B, a.V)
     d_ids = [torch.from_numpy(ids[k].reshape(-1)).cuda() for k in range(a.nbatch)]
     d_cnt = [torch.from_numpy(counts[k]).cuda() for k in range(a.nbatch)]
@@ -59,7 +60,7 @@ def main():
     ms = {n: acc[n] / a.steps for n in names}
     R = a.D * 4
     alg = U * R * 4 + U * 16 + a.B * 12
-    out = dict(impl=a.impl, V=a.V, D=a.D, B=a.B, uniform=a.uniform, chunk=a.chunk, U=U, ms=ms, total_ms=sum(ms.values()),
+    out = dict(impl=a.impl, variant=a.variant, V=a.V, D=a.D, B=a.B, uniform=a.uniform, chunk=a.chunk, U=U, ms=ms, total_ms=sum(ms.values()),
                rows_GBs=alg / (ms["rows"] * 1e-3) / 1e9, step_GBs=alg / (sum(ms.values()) * 1e-3) / 1e9,
                pairs_per_s=a.B / (sum(ms.values()) * 1e-3), loss=float(step.scalars[5].item()))
     print(json.dumps(out))
