@@ -68,6 +68,7 @@ _SIGNATURES = {
     "esr_score_all_f32": (C.c_int, [C.POINTER(EsrTable), _P, C.c_int32, _P, _P]),
     "esr_sort_cols_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_sort_cols_f32": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
+    "esr_sample_uniform_i32": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
     "esr_check_ids_i32": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "esr_plan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_plan_build_i32": (C.c_int, [C.POINTER(EsrPlan), _P, C.c_size_t, _P]),

@@ -375,3 +375,37 @@ extern "C" int esr_score_all_f32(const EsrTable* t, const float* queries, int32_
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// On-device negative sampling.  Replaces sample_negative's
+// jax.random.randint(subkey, [num_negatives], 0, N - 1) (spotify/train_spotify.py:139-150; the upper bound is
+// EXCLUSIVE, so index N-1 is never drawn -- kept) and the pre-sampled negative of pinterest/train_shop_the_look.py:72-91.
+// The stream is our own counter-based generator (splitmix64 of (seed, step, k)), not threefry: parity harnesses
+// treat negatives as inputs; oracle.index.sample_uniform restates it bit for bit.
+// ---------------------------------------------------------------------------------------------
+namespace esr {
+namespace {
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(kThreads) k_sample_uniform(uint64_t seed, uint64_t step, int64_t n, uint32_t hi,
+                                                             int32_t* __restrict__ out) {
+  const int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t r = splitmix64(splitmix64(seed ^ (step * 0xD1342543DE82EF95ull)) + (uint64_t)k);
+  out[k] = (int32_t)(((r >> 32) * (uint64_t)hi) >> 32);  // multiply-shift: unbiased to 2^-32
+}
+}  // namespace
+}  // namespace esr
+
+extern "C" int esr_sample_uniform_i32(uint64_t seed, uint64_t step, int64_t n, int64_t hi, int32_t* out, esr_stream_t stream_) {
+  ESR_REQUIRE(n >= 0 && hi > 0 && hi <= 0x7fffffffll && (out != nullptr || n == 0));
+  if (n == 0) return ESR_OK;
+  esr::k_sample_uniform<<<(unsigned)esr::ceil_div(n, esr::kThreads), esr::kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      seed, step, n, (uint32_t)hi, out);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}

@@ -283,6 +283,16 @@ def score_all(table: EmbeddingTable, queries):
     return out
 
 
+def sample_uniform(seed, step, n, hi, device=None, out=None):
+    """n uniform int32 in [0, hi) on the device (counter-based, reproducible from (seed, step))."""
+    dev = _dev(device)
+    if out is None:
+        out = torch.empty(int(n), dtype=torch.int32, device=dev)
+    L.check(L.lib().esr_sample_uniform_i32(int(seed), int(step), int(n), int(hi), L.ptr(out), L.stream_ptr()),
+            "esr_sample_uniform_i32")
+    return out
+
+
 def sort_cols(scores, k=None, descending=False, want_values=False):
     """Stable per-column ranking of a (V, T) score matrix -> int32 (k, T) row indices (and values).
     ``descending=False, k=None`` is ``jnp.argsort(scores, axis=0)`` (find_knn); ``descending=True`` is

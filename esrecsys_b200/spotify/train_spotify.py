@@ -63,3 +63,13 @@ def sample_negative(x, generator: torch.Generator, num_negatives, all_tracks, al
     out["neg_album"] = np.asarray(all_albums)[idx]
     out["neg_artist"] = np.asarray(all_artists)[idx]
     return out
+
+
+def sample_negative_device(x, seed, step, num_negatives, all_tracks_d, all_albums_d, all_artists_d):
+    """sample_negative with the draw and the three gathers on the GPU: ``all_*_d`` are device
+    tensors of the corpus arrays; returns ``x`` plus device ``neg_track / neg_album / neg_artist``."""
+    n = all_tracks_d.numel()
+    idx = engine.sample_uniform(seed, step, num_negatives, n - 1, all_tracks_d.device).long()
+    out = dict(x)
+    out["neg_track"], out["neg_album"], out["neg_artist"] = all_tracks_d[idx], all_albums_d[idx], all_artists_d[idx]
+    return out

@@ -96,6 +96,10 @@ int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float*
 size_t esr_sort_cols_workspace_bytes(int64_t V);
 int esr_sort_cols_f32(const float* scores, int64_t V, int32_t T, int32_t descending, int64_t k, int32_t* out_idx,
                       float* out_val, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* out[k] = uniform integer in [0, hi), k < n, from a counter-based stream keyed by (seed, step, k): the on-device
+ * replacement of sample_negative's jax.random.randint(key, [n], 0, N - 1) (spotify/train_spotify.py:139-150; pass
+ * hi = N - 1: the reference's upper bound is exclusive).  Bit-exact contract: oracle.index.sample_uniform. */
+int esr_sample_uniform_i32(uint64_t seed, uint64_t step, int64_t n, int64_t hi, int32_t* out, esr_stream_t stream);
 /* Debug validator: *n_bad (device int32) = number of ids outside [0, V). */
 int esr_check_ids_i32(const int32_t* ids, int64_t n, int64_t V, int32_t* n_bad, esr_stream_t stream);
 

@@ -104,3 +104,23 @@ def route_plan(uniq: np.ndarray, n_ranks: int):
 def exchange_counts(all_send_counts: np.ndarray):
     """Simulate the count all-to-all: ``recv_counts[r][s] = send_counts[s][r]``."""
     return np.ascontiguousarray(np.asarray(all_send_counts, np.int32).T)
+
+
+def _splitmix64(x):
+    m = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & m
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & m
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m
+    return x ^ (x >> 31)
+
+
+def sample_uniform(seed, step, n, hi):
+    """Bit-exact restatement of esr_sample_uniform_i32 (csrc/table_ops.cu): our own counter-based stream that
+    replaces jax.random.randint in sample_negative (spotify/train_spotify.py:139-150) -- not threefry."""
+    m = (1 << 64) - 1
+    base = _splitmix64((seed ^ ((step * 0xD1342543DE82EF95) & m)) & m)
+    out = np.empty(n, np.int32)
+    for k in range(n):
+        r = _splitmix64((base + k) & m)
+        out[k] = ((r >> 32) * hi) >> 32
+    return out

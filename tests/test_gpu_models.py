@@ -232,3 +232,15 @@ def test_pinterest_find_top_k_matches_oracle():
     oval, oidx = ostl.find_top_k(s, P, 10)
     assert np.array_equal(_np(idx), oidx)
     np.testing.assert_allclose(_np(val), oval, rtol=RTOL, atol=ATOL)
+
+
+def test_device_negative_sampler_bit_exact_and_uniform():
+    from esrecsys_b200 import engine
+    from oracle import index as oidx
+    got = engine.sample_uniform(7, 3, 1000, 2262291).cpu().numpy()
+    assert np.array_equal(got, oidx.sample_uniform(7, 3, 1000, 2262291))
+    assert not np.array_equal(got, engine.sample_uniform(7, 4, 1000, 2262291).cpu().numpy())     # new step, new draw
+    big = engine.sample_uniform(1, 0, 1 << 20, 64).cpu().numpy()
+    assert big.min() == 0 and big.max() == 63                                                    # upper bound exclusive
+    cnt = np.bincount(big, minlength=64)
+    assert np.abs(cnt - (1 << 14)).max() < 6 * np.sqrt(1 << 14)                                  # flat to 6 sigma
