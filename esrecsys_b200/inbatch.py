@@ -202,3 +202,88 @@ class ShardedSharedTableInBatch:
                                                  L.stream_ptr()), "esr_segment_sum_rows_f32")
         self.xchg.push(self.gsum, self.zeros_b, self.lr)
         return loss[0]
+
+
+class ShardedTwoTowerInBatch:
+    """configs[3] across the GPUs of one box: scene-id and product-id tables row-sharded cyclically, the two MLP
+    towers replicated (their gradients all-reduced -- SURVEY.md 8(e)), B_local pairs per rank, in-batch negatives over
+    the items of ALL ranks (all-gather of the product-tower outputs, reduce-scatter of their gradients).  One global
+    step equals ``oracle.inbatch.two_tower_step`` on the rank-major concatenation of the batches."""
+
+    def __init__(self, Vs, Vp, D, B_local, hidden=None, out=None, lr=0.05, tower_lr=1e-3, loss="softmax", margin=1.0,
+                 scale=1.0, seed=0, group=None, device=None):
+        import torch.distributed as dist
+        from .sharded import LibesrOps, RowExchange, shard_rows
+        L.require_cuda()
+        self.dist, self.group = dist, group
+        self.n, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.Vs, self.Vp, self.D, self.B, self.lr = int(Vs), int(Vp), int(D), int(B_local), float(lr)
+        H, O = int(hidden or D), int(out or D)
+        mk = lambda V: engine.EmbeddingTable(shard_rows(V, self.rank, self.n), D, self.dev, sparse=False, adagrad=True)
+        self.shard_s, self.shard_p = mk(Vs), mk(Vp)
+        self.ops = LibesrOps(self.dev)
+        self.xs, self.xp = RowExchange(self.ops, self.shard_s, group), RowExchange(self.ops, self.shard_p, group)
+        self.plan_s = engine.IndexPlan(self.B, Vs, self.dev, with_partner=False)
+        self.plan_p = engine.IndexPlan(self.B, Vp, self.dev, with_partner=False)
+        gen = torch.Generator(device="cpu").manual_seed(seed)           # same seed on every rank: replicated towers
+        self.scene_tower = MLPTower(D, H, O, gen, self.dev, tower_lr)
+        self.product_tower = MLPTower(D, H, O, gen, self.dev, tower_lr)
+        Bg = self.B * self.n
+        self.scorer = engine.InBatchScorer(self.B, O, Bk=Bg, loss=loss, diag_off=self.rank * self.B, margin=margin,
+                                           scale=scale, b_norm=Bg, device=self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.Xs, self.Xp = torch.empty(self.B, D, **f32), torch.empty(self.B, D, **f32)
+        self.K_all = torch.empty(Bg, O, **f32)
+        self.dk_loc = torch.empty(self.B, O, **f32)
+        self.gs, self.gp = torch.empty(self.B, D, **f32), torch.empty(self.B, D, **f32)
+        self.zeros_b = torch.zeros(self.B, **f32)
+        self.remap = torch.empty(self.B, dtype=torch.int32, device=self.dev)
+
+    def load_dense(self, Es, Ep):
+        self.shard_s.rows0.copy_(torch.as_tensor(Es)[torch.arange(self.rank, self.Vs, self.n)].to(self.dev))
+        self.shard_p.rows0.copy_(torch.as_tensor(Ep)[torch.arange(self.rank, self.Vp, self.n)].to(self.dev))
+
+    def gather_dense(self):
+        out = []
+        for V, sh in ((self.Vs, self.shard_s), (self.Vp, self.shard_p)):
+            E = torch.zeros(V, self.D, device=self.dev)
+            E[torch.arange(self.rank, V, self.n, device=self.dev)] = sh.rows0
+            self.dist.all_reduce(E, group=self.group)
+            out.append(E)
+        return out
+
+    def _fetch(self, plan, xchg, ids, X):
+        plan.build(ids)
+        rows, _ = xchg.fetch(plan.uniq, plan.n_uniq)
+        plan.remap_ids(self.remap)
+        self.ops.permute_rows(rows, self.remap, self.B, False, X)
+
+    def _push(self, plan, xchg, dX, gsum):
+        L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), self.D, L.ptr(dX), None, L.ptr(gsum), None, L.stream_ptr()),
+                "esr_segment_sum_rows_f32")
+        xchg.push(gsum, self.zeros_b, self.lr)
+
+    def step(self, scene_ids, product_ids):
+        """int32 (B_local,) global ids each.  Returns the GLOBAL loss (device scalar)."""
+        dist = self.dist
+        s_ids = scene_ids.to(self.dev, torch.int32).contiguous()
+        p_ids = product_ids.to(self.dev, torch.int32).contiguous()
+        self._fetch(self.plan_s, self.xs, s_ids, self.Xs)
+        self._fetch(self.plan_p, self.xp, p_ids, self.Xp)
+        q = self.scene_tower.forward(self.Xs)
+        k = self.product_tower.forward(self.Xp)
+        dist.all_gather_into_tensor(self.K_all, k.contiguous(), group=self.group)
+        loss, dq, dK = self.scorer.run(q.contiguous(), self.K_all)
+        dist.reduce_scatter_tensor(self.dk_loc, dK, group=self.group)
+        loss = loss.clone()
+        dist.all_reduce(loss, group=self.group)
+        dxs = self.scene_tower.backward(dq)
+        dxp = self.product_tower.backward(self.dk_loc)
+        for tower in (self.scene_tower, self.product_tower):       # replicated dense params: sum of the ranks' gradients
+            for g in tower.g.values():
+                dist.all_reduce(g, group=self.group)
+            tower.update()
+        self._push(self.plan_s, self.xs, dxs.contiguous(), self.gs)
+        self._push(self.plan_p, self.xp, dxp.contiguous(), self.gp)
+        return loss[0]

@@ -34,7 +34,8 @@ def _run(Q, K, **kw):
 
 
 SHAPES = [(128, 128, 128, 0), (256, 256, 64, 0), (384, 384, 128, 0), (200, 200, 128, 0), (1024, 1024, 256, 0),
-          (128, 512, 128, 256), (333, 777, 192, 100), (2048, 2048, 128, 0)]
+          (128, 512, 128, 256), (333, 777, 192, 100), (2048, 2048, 128, 0),
+          (1, 1, 64, 0), (2, 7, 128, 3), (130, 129, 256, 0)]       # single pair; tiny ragged; one tile + 1-2 rows
 
 
 @pytest.mark.parametrize("Bq,Bk,D,off", SHAPES)
@@ -43,7 +44,8 @@ def test_hinge_parity(Bq, Bk, D, off):
     loss, dQ, dK, G, diag, cnt, _ = _run(Q, K, loss="hinge", diag_off=off)
     S, Qh, Kh = oib.scores(Q, K)
     pj = np.arange(Bq) + off
-    np.testing.assert_allclose(diag, S[np.arange(Bq), pj], rtol=1e-5, atol=1e-5)
+    has = pj < Bk                                     # queries whose positive lies outside the item batch score 0
+    np.testing.assert_allclose(diag[has], S[np.arange(Bq)[has], pj[has]], rtol=1e-5, atol=1e-5)
     mask, h = oib.hinge_mask(S, off)
     gm = G > 0.5
     assert set(np.unique(G)) <= {0.0, 1.0}

@@ -134,3 +134,68 @@ def test_sharded_inbatch_matches_single_table_oracle(kind):
     for p in procs:
         p.join(60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _two_tower_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from esrecsys_b200 import synth
+        from esrecsys_b200.inbatch import ShardedTwoTowerInBatch
+        from oracle import inbatch as oib
+        V, D, B_loc, steps = 3000, 64, 128, 3
+        rng = np.random.default_rng(12)
+        Es = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+        Ep = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+        tr = ShardedTwoTowerInBatch(V, V, D, B_loc, lr=0.05, tower_lr=1e-3, loss="softmax", scale=4.0, seed=3)
+        tr.load_dense(Es, Ep)
+        ps = {k: v.cpu().numpy().copy() for k, v in tr.scene_tower.p.items()}
+        pp = {k: v.cpu().numpy().copy() for k, v in tr.product_tower.p.items()}
+        mk = lambda p: dict(count=0, mu={k: np.zeros_like(v) for k, v in p.items()}, nu={k: np.zeros_like(v) for k, v in p.items()})
+        os_, op_ = mk(ps), mk(pp)
+        Eso, Epo = Es.copy(), Ep.copy()
+        accs, accp = np.full_like(Es, 0.1), np.full_like(Ep, 0.1)
+        s_ids, p_ids = synth.pair_batches(V, V, B_loc * world, steps, 9)
+        lo, hi = rank * B_loc, (rank + 1) * B_loc
+        for s in range(steps):
+            got = float(tr.step(torch.from_numpy(s_ids[s][lo:hi]).cuda(), torch.from_numpy(p_ids[s][lo:hi]).cuda()).item())
+            want = oib.two_tower_step(Eso, accs, Epo, accp, ps, pp, os_, op_, s_ids[s], p_ids[s], 0.05, 1e-3, "softmax", 1.0, 4.0)
+            assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (s, got, want)
+        Egs, Egp = tr.gather_dense()
+        np.testing.assert_allclose(Egs.cpu().numpy(), Eso, rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(Egp.cpu().numpy(), Epo, rtol=1e-3, atol=2e-4)
+        # optax.adam moves a parameter by ~lr * sign(g) in the first steps whatever |g| is, so an element whose gradient
+        # cancels to ~0 (bias sums) can differ by up to 2 * lr per step between two fp32 summation orders (here: the
+        # all-reduce of per-rank partial sums vs one global sum).  Weights: tight; biases: bounded by that envelope and
+        # mostly equal.
+        for k in ps:
+            for got, want in ((tr.scene_tower.p[k].cpu().numpy(), ps[k]), (tr.product_tower.p[k].cpu().numpy(), pp[k])):
+                if k.startswith("W"):
+                    bad = np.abs(got - want) > 2e-4 + 1e-3 * np.abs(want)
+                    assert bad.mean() < 5e-3, (k, bad.mean())
+                assert np.abs(got - want).max() <= 2.2 * steps * 1e-3, (k, np.abs(got - want).max())
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_two_tower_matches_oracle():
+    """configs[3] sharded: row-sharded id tables, replicated MLP towers (all-reduced grads), global in-batch softmax."""
+    world = max(1, min(4, torch.cuda.device_count()))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29990 + (os.getpid() % 9)
+    procs = [ctx.Process(target=_two_tower_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] == "ok" for r in res), res
