@@ -317,9 +317,24 @@ extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void*
   return ESR_OK;
 }
 
-extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+// Owner side, step 1 (ids only -- can run on a side stream while the row pass is still producing gradients):
+// per received entry, where every source keeps that row's gradient (desc), and the compacted list of the entries
+// that own their row (own_list = desc + recv_cap * n_ranks, counter in src_meta[3n + 1]).
+extern "C" int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_meta, const int32_t* slot_map,
+                                    int64_t map_stride, int32_t* desc, int64_t recv_cap, esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && desc &&
+              recv_cap > 0);
+  k_peer_resolve<<<4 * sm_count(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(n_ranks, recv_ids, src_meta, slot_map,
+                                                                                     map_stride, desc, desc + recv_cap * n_ranks);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+// Owner side, step 2 (after every rank's gradients have landed): merge in source order + optax.adagrad, then restore
+// slot_map to -1.
+extern "C" int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
                                           const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
-                                          int64_t map_stride, int32_t* desc, int64_t recv_cap, float lr, float eps,
+                                          int64_t map_stride, const int32_t* desc, int64_t recv_cap, float lr, float eps,
                                           esr_stream_t stream_) {
   ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
   ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
@@ -327,10 +342,7 @@ extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE
   ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D4 = shard->D / 4;
-  int32_t* own_list = desc + recv_cap * n_ranks;
-  k_peer_resolve<<<4 * sm_count(), kThreads, 0, stream>>>(n_ranks, recv_ids, const_cast<int32_t*>(src_meta), slot_map,
-                                                          map_stride, desc, own_list);
-  ESR_LAUNCH_CHECK();
+  const int32_t* own_list = desc + recv_cap * n_ranks;
   const int tpr = tpr_for(D4);
   const int grid = 8 * sm_count();
 #define ESR_MERGE(NR, EB, MINB)                                                                                          \
@@ -351,6 +363,17 @@ extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE
   k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
+}
+
+extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+                                          const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
+                                          int64_t map_stride, int32_t* desc, int64_t recv_cap, float lr, float eps,
+                                          esr_stream_t stream_) {
+  const int rc = esr_peer_resolve_i32(n_ranks, recv_ids, const_cast<int32_t*>(src_meta), slot_map, map_stride, desc, recv_cap,
+                                      stream_);
+  if (rc != ESR_OK) return rc;
+  return esr_peer_apply_adagrad_f32(shard, inbox_dE, inbox_db, n_ranks, recv_ids, src_meta, slot_map, map_stride, desc,
+                                    recv_cap, lr, eps, stream_);
 }
 
 // emit_map[u] = owner << 27 | (offset of my bucket in owner's inbox + position inside the bucket)

@@ -219,16 +219,20 @@ class PeerShardedGloveTrainer:
     (csrc/peer_ops.cu) on buffers from torch's symmetric-memory rendezvous: no NCCL all-to-all, no id
     exchange, no host-known sizes, no host synchronisation inside the step.
 
-      side stream : index plan + route plan of batch t+1 (published in symmetric memory, double-buffered)
-      main stream : peer gather of the unique rows (NVLink loads) -> compact plan -> prep
-                    -> all-reduce(3 floats) -> emit plan -> row pass, whose gradient rows are STORED
+      side stream : index plan + route plan (published in symmetric memory, double-buffered) + compact plan of batch t+1
+      main stream : peer gather of the unique rows (NVLink loads) -> prep -> all-reduce(3 floats) -> owners pull the
+                    id lists and resolve who sends what -> emit plan -> row pass, whose gradient rows are STORED
                     STRAIGHT INTO THE OWNERS' INBOXES over NVLink -> all-reduce(2) -> finish -> barrier
-                    -> owners pull the id lists, merge their inbox locally, Adagrad -> barrier
+                    -> owners merge their inbox locally, Adagrad -> barrier
+    ``graphs=True`` captures both halves into CUDA graphs per parity after two eager steps (the eager step is ~25 host
+    calls and partly host-bound).  EXPERIMENTAL and off by default: in round 1 the replay of the captured
+    NCCL all-reduce + symmetric-memory barrier sequence dead-locked in the 2-GPU bench (killed by its timeout).
     """
 
     DEPTH = 2
 
-    def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0):
+    def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
+                 graphs=False):
         import torch.distributed._symmetric_memory as symm_mem
         L.require_cuda()
         self.group = group if group is not None else dist.group.WORLD
@@ -275,10 +279,20 @@ class PeerShardedGloveTrainer:
         self.ops = LibesrOps(self.dev)
         self.plans = [IndexPlan(n_slots, V, self.dev) for _ in range(self.DEPTH)]
         self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
-        self.cplan = IndexPlan(n_slots, n_slots, self.dev)
+        # the plan re-expressed in unique-row indices depends on the ids only: built on the side stream, per parity;
+        # perm / useg / seg_off / n_uniq are shared with the original plan
+        self.cplans = [IndexPlan(n_slots, n_slots, self.dev) for _ in range(self.DEPTH)]
+        for cp, pl in zip(self.cplans, self.plans):
+            cp.s.n_slots = n_slots
+            cp.s.perm, cp.s.useg, cp.s.seg_off, cp.s.n_uniq = pl.s.perm, pl.s.useg, pl.s.seg_off, pl.s.n_uniq
+        self.cplan = self.cplans[0]
         self.scratch = torch.empty(n_slots, **i32)
+        sm = C.c_int(0)
+        L.check(L.lib().esr_device_info(C.byref(sm), None, None), "esr_device_info")
+        # 8/9 of the persistent row pass's CTA slots: the side / owner streams' id kernels co-run with it
         self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
-                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db)
+                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db,
+                                 row_blocks=max(1, (2 * sm.value * 8) // 9))
         cfg = self.step_fn.cfg
         cfg.emit_map = L.ptr(self.emit_map)
         cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
@@ -294,6 +308,12 @@ class PeerShardedGloveTrainer:
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self._keep = [None] * self.DEPTH
+        # static staging of the batch: the step's kernels (and, once captured, its CUDA graphs) always read these
+        self.st_ids = [torch.ones(n_slots, **i32) for _ in range(self.DEPTH)]
+        self.st_counts = [torch.ones(self.B, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
+        self.use_graphs = bool(graphs)
+        self.g_plan = [None] * self.DEPTH
+        self.g_step = [None] * self.DEPTH
         self.t = 0
         self.loss = None
         self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
@@ -302,6 +322,67 @@ class PeerShardedGloveTrainer:
 
     def barrier(self):
         self._hdls[0].barrier()
+
+    # -- the two halves of a step; every call enqueues on the CURRENT stream ------------------------------------
+    def _plan_body(self, k):
+        """Everything that depends on the ids only (side stream): index plan, owner routing (published for the
+        peers), the plan re-expressed in unique-row indices."""
+        plan, pub, cplan = self.plans[k], self.pub[k], self.cplans[k]
+        plan.build(self.st_ids[k])
+        self.ops.route_plan(plan.uniq, plan.n_uniq, self.n, out=(pub["order"], pub["send_local"], pub["counts"],
+                                                                 pub["inv_order"]))
+        cplan.s.n_slots = plan.n_slots
+        L.check(L.lib().esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner),
+                                             L.ptr(cplan.uniq), L.ptr(self.scratch), L.stream_ptr()), "esr_plan_compact_i32")
+
+    def _step_body(self, k):
+        lib, n = L.lib(), self.n
+        plan, pub, cplan, st = self.plans[k], self.pub[k], self.cplans[k], self.step_fn
+        sp = L.stream_ptr()
+        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
+                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
+        st.prep(cplan, self.st_counts[k])
+        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: all fetches done, all route plans published
+        L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
+                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
+                                          sp), "esr_peer_pull_ids_i32")
+        L.check(lib.esr_peer_resolve_i32(n, L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
+                                         self.map_stride, L.ptr(self.desc), self.recv_cap, sp), "esr_peer_resolve_i32")
+        L.check(lib.esr_peer_emit_plan_i32(pub["p_counts"], n, self.rank, L.ptr(plan.uniq), L.ptr(plan.n_uniq),
+                                           plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
+                                           L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
+        st.rows(cplan)                                          # gradient rows go straight to the owners' inboxes
+        dist.all_reduce(st.scalars[3:5], group=self.group)
+        st.finish(cplan)
+        self.barrier()                                          # every rank's gradients have landed in the inboxes
+        L.check(lib.esr_peer_apply_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
+                                               L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
+                                               self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, sp),
+                "esr_peer_apply_adagrad_f32")
+        self.barrier()                                          # every owner has applied its updates
+
+    def _capture(self):
+        """Capture the two halves per parity into CUDA graphs (the eager step is ~25 host calls: at 0.5 ms per step the
+        host was the bound).  Collective: every rank captures the same sequence.  Falls back to eager launches if the
+        runtime refuses to capture a collective."""
+        try:
+            torch.cuda.synchronize(self.dev)
+            cap = torch.cuda.Stream(self.dev)
+            for k in range(self.DEPTH):
+                gp = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gp, stream=cap, capture_error_mode="thread_local"):
+                    self._plan_body(k)
+                gs = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gs, stream=cap, capture_error_mode="thread_local"):
+                    self._step_body(k)
+                self.g_plan[k], self.g_step[k] = gp, gs
+            torch.cuda.synchronize(self.dev)
+        except Exception as e:  # pragma: no cover
+            import warnings
+            warnings.warn("sharded step: CUDA-graph capture failed (%s); staying on eager launches" % e)
+            self.g_plan = [None] * self.DEPTH
+            self.g_step = [None] * self.DEPTH
+            self.use_graphs = False
 
     def load_dense(self, E, b):
         idx = torch.arange(self.rank, self.V, self.n)
@@ -313,52 +394,32 @@ class PeerShardedGloveTrainer:
     def step(self, ids, counts):
         """ids: int32 (2, B_local) global rows (host pinned or device); counts: f32 (B_local,).
         Enqueues one step; returns the GLOBAL loss as a device scalar."""
-        lib = L.lib()
-        n, k = self.n, self.t % self.DEPTH
-        plan, pub, cplan, st = self.plans[k], self.pub[k], self.cplan, self.step_fn
+        k = self.t % self.DEPTH
         main = torch.cuda.current_stream(self.dev)
         side = self.s_side
-        # ---- side stream: everything that depends on the ids only ----
+        if self.use_graphs and self.g_step[0] is None and self.t == 2 * self.DEPTH:
+            self._capture()                    # after two eager steps per parity (lazy NCCL / allocator state is warm)
+        # ---- side stream: stage the batch, then everything that depends on the ids only ----
         side.wait_stream(main)                 # inputs may have been produced on the caller's stream
         side.wait_event(self.ev_done[k])       # peers are done with publish set k (barrier of step t-2 passed)
         with torch.cuda.stream(side):
-            d_ids = ids.to(self.dev, non_blocking=True).reshape(-1).contiguous()
-            d_counts = counts.to(self.dev, non_blocking=True)
-            self._keep[k] = (d_ids, d_counts, ids, counts)
-            plan.build(d_ids)
-            self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"],
-                                                                pub["inv_order"]))
+            self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
+            self.st_counts[k].copy_(counts, non_blocking=True)
+            self._keep[k] = (ids, counts)
+            if self.g_plan[k] is not None:
+                self.g_plan[k].replay()
+            else:
+                self._plan_body(k)
             self.ev_plan[k].record(side)
         main.wait_event(self.ev_plan[k])
         # ---- main stream ----
-        sp = L.stream_ptr(main)
-        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
-                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
-        L.check(lib.esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner), L.ptr(cplan.uniq),
-                                         L.ptr(self.scratch), sp), "esr_plan_compact_i32")
-        cs = cplan.s
-        cs.n_slots = plan.n_slots
-        cs.perm, cs.useg, cs.seg_off, cs.n_uniq = plan.s.perm, plan.s.useg, plan.s.seg_off, plan.s.n_uniq
-        st.prep(cplan, d_counts)
-        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: all fetches done, all route plans published
-        L.check(lib.esr_peer_emit_plan_i32(pub["p_counts"], n, self.rank, L.ptr(plan.uniq), L.ptr(plan.n_uniq),
-                                           plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
-                                           L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
-        st.rows(cplan)                                          # gradient rows go straight to the owners' inboxes
-        dist.all_reduce(st.scalars[3:5], group=self.group)
-        st.finish(cplan)
-        self.barrier()                                          # every rank's gradients have landed in the inboxes
-        L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
-                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
-                                          sp), "esr_peer_pull_ids_i32")
-        L.check(lib.esr_peer_merge_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
-                                               L.ptr(self.recv_ids),
-                                               L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride, L.ptr(self.desc),
-                                               self.recv_cap, self.lr, 1e-7, sp), "esr_peer_merge_adagrad_f32")
-        self.barrier()                                          # every owner has applied its updates
+        if self.g_step[k] is not None:
+            self.g_step[k].replay()
+        else:
+            self._step_body(k)
         self.ev_done[k].record(main)
         slot = self.t % self.loss_log.numel()
-        self.loss_log[slot: slot + 1].copy_(st.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
+        self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
         self.loss = self.loss_log[slot]
         self.t += 1
         return self.loss

@@ -353,6 +353,14 @@ int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes, int32_t n
                                   int64_t* const* vals, const int64_t* val_cap, int64_t* const* offs,
                                   int64_t max_records, size_t* consumed);
 
+/* The two halves of esr_peer_merge_adagrad_f32: resolve depends on the ids only (side stream, overlaps the row
+ * pass); apply needs the gradients (after the device barrier). */
+int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_meta, const int32_t* slot_map,
+                         int64_t map_stride, int32_t* desc, int64_t recv_cap, esr_stream_t stream);
+int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+                               const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map, int64_t map_stride,
+                               const int32_t* desc, int64_t recv_cap, float lr, float eps, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
