@@ -287,12 +287,10 @@ class PeerShardedGloveTrainer:
             cp.s.perm, cp.s.useg, cp.s.seg_off, cp.s.n_uniq = pl.s.perm, pl.s.useg, pl.s.seg_off, pl.s.n_uniq
         self.cplan = self.cplans[0]
         self.scratch = torch.empty(n_slots, **i32)
-        sm = C.c_int(0)
-        L.check(L.lib().esr_device_info(C.byref(sm), None, None), "esr_device_info")
-        # 8/9 of the persistent row pass's CTA slots: the side / owner streams' id kernels co-run with it
+        # full persistent grid: leaving CTA slots free (as the single-GPU trainer does for its plan stream) measured
+        # 2 % slower here -- the id kernels of this path are short and run between the phases anyway
         self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
-                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db,
-                                 row_blocks=max(1, (2 * sm.value * 8) // 9))
+                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db)
         cfg = self.step_fn.cfg
         cfg.emit_map = L.ptr(self.emit_map)
         cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
