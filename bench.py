@@ -260,7 +260,7 @@ def run_sharded(a, rank, world, local):
                        "5-float all-reduce" if a.exchange == "peer" else "NCCL all-to-all of ids / rows / gradients")},
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": a.steps * 40, "final_loss": float(tr.loss.item()),
+        "gpu_launches": a.steps * tr.LAUNCHES_PER_STEP, "final_loss": float(tr.loss.item()),
         "clocks": clocks.summary(),
     }
     if rank == 0:
