@@ -52,3 +52,33 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def token_dictionary_golden():
+    """tests/golden/token.tstat.pb.b64.bz2 written with the reference's TokenDictionary.save + nlp_pb2.TokenStat, and the
+    answers the reference's TokenDictionary gives for it (token_dictionary.py:58-119)."""
+    import json
+    import token_dictionary as ref_td          # /root/reference/wikipedia/token_dictionary.py
+    words = ["the", "of", "and", "naïve", "zürich", "data-set", "x"] + ["w%03d" % i for i in range(40)]
+    stats = []
+    for i, w in enumerate(words):
+        ts = nlp_pb.TokenStat()
+        ts.token, ts.frequency, ts.doc_frequency, ts.index = w, 1000 - i, 500 - i, i
+        if i % 5 == 0:
+            ts.url = "https://example.org/%d" % i
+        stats.append(ts)
+    path = os.path.join(HERE, "token.tstat.pb.b64.bz2")
+    ref_td.TokenDictionary.save(stats, path)
+    td = ref_td.TokenDictionary(path)
+    probe = ["the", "zürich", "unknownword", "abc", "Supercalifragilistic", "x"]
+    ans = {"size": td.get_dictionary_size(), "embedding_size": td.get_embedding_dictionary_size(),
+           "max_doc_frequency": td.get_max_doc_frequency(),
+           "embedding_index": {w: td.get_embedding_index(w) for w in probe},
+           "tokenize": td.simple_tokenize("The quick, brown fox: jumps/over [the] lazy_dog!"),
+           "from_embedding_index": {str(i): td.get_token_from_embedding_index(i) for i in (1, 5, 47, 48, 70000)}}
+    json.dump(ans, open(os.path.join(HERE, "token_dictionary_expected.json"), "w"), ensure_ascii=False, indent=1)
+    print("token dictionary:", ans["size"], "tokens")
+
+
+if __name__ == "__main__":
+    token_dictionary_golden()

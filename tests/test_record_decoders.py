@@ -114,3 +114,23 @@ def test_tfrecord_truncated_and_negative_values(tmp_path):
     open(path, "wb").write(blob + blob[:-3])
     with pytest.raises(L.EsrError):
         sip.decode_file(path, keys=("a", "b"))
+
+
+def test_token_dictionary_matches_reference_golden():
+    """tests/golden/token.tstat.pb.b64.bz2 was written by the REFERENCE's TokenDictionary.save and the expected answers by
+    the reference's TokenDictionary itself (tests/golden/make_record_golden.py)."""
+    import json
+    from esrecsys_b200.wikipedia.token_dictionary import TokenDictionary, encode_token_stat, parse_token_stat
+    want = json.load(open(os.path.join(G, "token_dictionary_expected.json")))
+    td = TokenDictionary(os.path.join(G, "token.tstat.pb.b64.bz2"))
+    assert td.get_dictionary_size() == want["size"] and td.get_embedding_dictionary_size() == want["embedding_size"]
+    assert td.get_max_doc_frequency() == want["max_doc_frequency"]
+    for w, idx in want["embedding_index"].items():
+        assert td.get_embedding_index(w) == idx, w
+    assert td.simple_tokenize("The quick, brown fox: jumps/over [the] lazy_dog!") == want["tokenize"]
+    for i, name in want["from_embedding_index"].items():
+        assert td.get_token_from_embedding_index(int(i)) == name
+    assert td.get_token_from_embedding_index(0) == "NULL" and td.get_doc_frequency(3) == 497
+    # writer round trip (proto3: zero / empty fields are omitted)
+    msg = encode_token_stat(token="naïve", url="", frequency=7, doc_frequency=0, index=3)
+    assert parse_token_stat(msg) == {"token": "naïve", "url": "", "frequency": 7, "doc_frequency": 0, "index": 3}
