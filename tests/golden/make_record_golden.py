@@ -82,3 +82,24 @@ def token_dictionary_golden():
 
 if __name__ == "__main__":
     token_dictionary_golden()
+
+
+def generator_golden():
+    """The first batches the REFERENCE's CooccurrenceGenerator.get_batch yields for cooccur_rows.pb.b64.bz2
+    (wikipedia/cooccurrence_matrix.py:58-107).  The module imports tensorflow at the top only for get_dataset
+    (:108-115); a stub module object stands in for it here -- get_batch itself is pure Python + nlp_pb2 + NumPy."""
+    import types
+    sys.modules.setdefault("tensorflow", types.ModuleType("tensorflow"))
+    import cooccurrence_matrix as ref_cm       # /root/reference/wikipedia/cooccurrence_matrix.py
+    gen = ref_cm.CooccurrenceGenerator(os.path.join(HERE, "cooccur_rows.pb.b64.bz2"))
+    it = gen.get_batch(100)
+    out = {}
+    for b in range(3):
+        x, y = next(it)
+        out["x0_%d" % b], out["x1_%d" % b], out["y_%d" % b] = x[0], x[1], y
+    np.savez_compressed(os.path.join(HERE, "cooccur_batches_expected.npz"), **out)
+    print("generator batches:", out["x0_0"].dtype, out["y_0"].dtype, out["x0_0"].shape)
+
+
+if __name__ == "__main__":
+    generator_golden()

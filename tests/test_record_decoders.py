@@ -134,3 +134,15 @@ def test_token_dictionary_matches_reference_golden():
     # writer round trip (proto3: zero / empty fields are omitted)
     msg = encode_token_stat(token="naïve", url="", frequency=7, doc_frequency=0, index=3)
     assert parse_token_stat(msg) == {"token": "naïve", "url": "", "frequency": 7, "doc_frequency": 0, "index": 3}
+
+
+def test_generator_batches_match_reference_generator():
+    """Batches of esrecsys_b200's CooccurrenceGenerator.get_batch == the batches the reference's own generator yields
+    for the same file (tests/golden/cooccur_batches_expected.npz, produced by running the reference class)."""
+    want = np.load(os.path.join(G, "cooccur_batches_expected.npz"))
+    it = cm.CooccurrenceGenerator(os.path.join(G, "cooccur_rows.pb.b64.bz2")).get_batch(100)
+    for b in range(3):
+        (t1, t2), y = next(it)
+        assert t1.dtype == want["x0_%d" % b].dtype and y.dtype == want["y_%d" % b].dtype
+        assert np.array_equal(t1, want["x0_%d" % b]) and np.array_equal(t2, want["x1_%d" % b])
+        assert np.array_equal(y.view(np.uint32), want["y_%d" % b].view(np.uint32))
