@@ -82,3 +82,20 @@ def train_epoch(state, steps_per_epoch, train_it):
         state = update_model(state, grads)
         epoch_loss.append(loss)
     return state, float(torch.stack(epoch_loss).mean().item())
+
+
+def save_state(state, step, checkpoint_dir):
+    """train_cooccurence.py:129-134: ``checkpoint-%05d.flax`` holding ``flax.serialization.to_bytes(state)``."""
+    import os
+    from .. import checkpoint
+    filename = os.path.join(checkpoint_dir, "checkpoint-%05d.flax" % step)
+    with open(filename, "wb") as f:
+        f.write(checkpoint.to_bytes(state))
+    return filename
+
+
+def resume_state(state, resume_checkpoint):
+    """train_cooccurence.py:173-177: ``flax.serialization.from_bytes(state, contents)``."""
+    from .. import checkpoint
+    with open(resume_checkpoint, "rb") as f:
+        return checkpoint.from_bytes(state, f.read())

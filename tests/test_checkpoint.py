@@ -87,3 +87,14 @@ def test_sharded_manifest(tmp_path):
         ck.save_sharded(str(tmp_path), 5, r, world, {"rows": E[r::world], "bias": E[r::world, 0]}, V, D)
     out = ck.load_sharded_dense(str(tmp_path), 5)
     assert np.array_equal(out["rows"], E) and np.array_equal(out["bias"], E[:, 0])
+
+
+def test_train_cooccurence_save_and_resume_names(tmp_path):
+    from esrecsys_b200.wikipedia.train_cooccurence import resume_state, save_state
+    st = _state(O.adam(1e-3))
+    st.step = 7
+    path = save_state(st, 7, str(tmp_path))
+    assert os.path.basename(path) == "checkpoint-00007.flax"
+    other = _state(O.adam(1e-3), seed=3)
+    assert resume_state(other, path).step == 7
+    assert torch.equal(other.params["_bias"]["embedding"], st.params["_bias"]["embedding"])
