@@ -10,11 +10,15 @@ through jax/flax/optax (absent from this image):
 * ``oracle.index``   -- our own integer bookkeeping contract (stable slot sort, segments,
                         cyclic owner routing); bit-exact target for the CUDA path
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
-jax/flax/optax cannot be imported here, so the oracle cannot be checked against
-the reference's own outputs. It is validated instead against an independent
-float64 torch-autograd transcription of each forward (tests/test_oracle_*.py)
-and hand-computed micro cases.
+PINNING: the reference ships no tests, golden vectors or fixtures, and jax / flax /
+optax cannot be installed here.  The oracle is pinned (to 1e-12, tests/test_ref_golden.py)
+against vectors produced by EXECUTING the reference's own unmodified source files on
+a torch-float64 stand-in for the jax / flax / optax surface they call
+(tests/golden/make_ref_golden.py, tests/golden/refshim/): every statement of the
+reference on the path is pinned; the third-party rules underneath (jax VJPs, optax
+formulas) are restated in that stand-in, not executed -- in that sense parity with
+real jax stays UNPINNED.  Also validated against an independent float64
+torch-autograd transcription (tests/golden/make_golden.py) and hand-computed cases.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this package. The product

@@ -16,10 +16,12 @@ Restates, in NumPy:
 ``bias_mode="reference_broadcast"`` is what the reference computes;
 ``bias_mode="per_pair"`` is textbook GloVe.
 
-PARITY UNPINNED: jax/flax (jax 0.3.25, flax 0.5.2 -- wikipedia/requirements.txt:18-20)
-are not importable here and the reference holds no golden vectors.  The closed
-form below is pinned against (1) the literal (B,B) evaluation in this file and
-(2) torch float64 autograd of that literal forward (tests/test_oracle_glove.py).
+PINNING: jax/flax (jax 0.3.25, flax 0.5.2 -- wikipedia/requirements.txt:18-20) are not
+installable here and the reference holds no golden vectors.  The closed form below is
+pinned against (1) the reference's own models.py / train_cooccurence.py executed on the
+jax/flax/optax stand-in of tests/golden/refshim (tests/golden/ref_glove_*.npz, 1e-12),
+(2) the literal (B,B) evaluation in this file and (3) torch float64 autograd of that
+literal forward (tests/test_oracle_glove.py).  Real-jax parity stays unpinned.
 """
 from __future__ import annotations
 
