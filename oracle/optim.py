@@ -13,10 +13,13 @@ wikipedia/train_cooccurence.py:101, spotify/train_spotify.py:110.
 ``optax.adagrad`` is the north-star sparse rule (BASELINE.json); the reference
 never calls it.
 
-Restated from the published optax algorithms.  Parity
-unpinned: no reference golden vectors exist; tests/test_oracle_optim.py checks
-these against torch.optim (Adam / SGD momentum / Adagrad) which implement the
-same published rules.
+Restated from the published optax algorithms.  Parity with
+real optax is unpinned (not installable here, no reference golden vectors):
+tests/test_oracle_optim.py checks these against torch.optim (Adam / SGD momentum /
+Adagrad), which implement the same published rules, and tests/test_ref_golden.py
+against three-step trajectories driven by the reference's own update_model /
+train_step (whose optax calls resolve to an independent restatement under
+tests/golden/refshim/optax).
 """
 from __future__ import annotations
 

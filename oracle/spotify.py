@@ -14,9 +14,12 @@ Restates, in NumPy:
   (every row's trace decays and moves every step).
 * ``eval_step`` scoring + top-k    spotify/train_spotify.py:113-131.
 
-PARITY UNPINNED: jax 0.4.10 / flax 0.6.9 / optax 0.1.5 (spotify/requirements.txt:17,30,53)
-are not importable here; no reference golden vectors exist.  Pinned against torch
-float64 autograd of a literal forward transcription (tests/test_oracle_spotify.py).
+PINNING: jax 0.4.10 / flax 0.6.9 / optax 0.1.5 (spotify/requirements.txt:17,30,53) are not
+installable here; no reference golden vectors exist.  Pinned (1e-12) against the reference's
+own spotify/models.py + train_spotify.py executed on the jax/flax/optax stand-in of
+tests/golden/refshim (tests/golden/ref_spotify.npz, tests/test_ref_golden.py) and against torch
+float64 autograd of a literal forward transcription (tests/test_oracle_spotify.py).  The jax
+VJP / optax rules themselves are restated there, so real-jax parity stays unpinned.
 """
 from __future__ import annotations
 

@@ -18,9 +18,12 @@ torch autograd only).
 The in-batch generalisations (``inbatch_hinge``, ``inbatch_softmax``; SURVEY.md
 App. A.4) have NO reference counterpart at all.
 
-PARITY UNPINNED: jax 0.3.25 / flax 0.5.2 / optax 0.1.2 (pinterest/requirements.txt:5-8)
-are not importable here; no reference golden vectors exist.  Pinned against torch
-float64 autograd (tests/test_oracle_stl.py).
+PINNING: jax 0.3.25 / flax 0.5.2 / optax 0.1.2 (pinterest/requirements.txt:5-8) are not
+installable here; no reference golden vectors exist.  Pinned (1e-12) against the reference's own
+pinterest/models.py (STLModel, CNN towers swapped for ID towers) + train_shop_the_look.py +
+make_recommendations.py executed on the jax/flax/optax stand-in of tests/golden/refshim
+(tests/golden/ref_stl.npz, tests/test_ref_golden.py) and against torch float64 autograd
+(tests/test_oracle_stl.py).  Real-jax parity stays unpinned.
 """
 from __future__ import annotations
 
