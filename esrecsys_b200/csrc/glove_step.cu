@@ -750,7 +750,11 @@ __device__ __forceinline__ void grow_store_f(const Row<NV>& r, float4* __restric
   }
 }
 
-template <int G, int NV, int MINB, bool FULLD>
+// ACCREG (cfg.reserved == 3, experimental, not the default): the accumulator row -- read exactly once per step -- does not
+// go through cp.async.cg (normal L2 priority) but through ld.global.cs into registers one slot ahead (SASS LDG.E.EF:
+// evict-first in L2), so it stops displacing table rows that a later slot re-reads as a partner.  Same arithmetic,
+// bit-identical results.  (The L2::cache_hint form of cp.async faults on B200: profiles/r1_summary.md 3c.)
+template <int G, int NV, int MINB, bool FULLD, bool ACCREG = false>
 __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const RowsArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ float red[32 * 2];
@@ -813,8 +817,23 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       const uint32_t row = (uint32_t)(k1 & kRowMask);
       if (s == 0 || head)
         grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 3u * RB, ((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, true);
-      if (!a.emit && end && (head || started_if_not_head))
+      if (!ACCREG && !a.emit && end && (head || started_if_not_head))
         grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 4u * RB, accp + (uint64_t)row * D4, gl, a.D4, false);
+    }
+  };
+  Row<NV> An;  // ACCREG: accumulator row of the next slot, in flight in registers
+  row_zero(An);
+  auto acc_to_regs = [&](int s, bool started_if_not_head) {
+    if (ACCREG && s < cnt && !a.emit) {
+      const int32_t k0 = gm.keys[s], k1 = gm.keys[1 + s], k2 = gm.keys[2 + s];
+      if (k1 != k2 && (k1 != k0 || started_if_not_head)) {
+        const float4* src = accp + (uint64_t)(uint32_t)(k1 & kRowMask) * D4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int c = k * G + gl;
+          if (FULLD || c < (int)D4) An.v[k] = ld_stream(src + c);
+        }
+      }
     }
   };
 
@@ -826,6 +845,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   int64_t u = cnt > 0 ? a.useg[p0] : 0;
   // prologue: {self, acc of slot 0} {partner 0} {nothing} {partner 1}
   issue_self_acc(0, false);
+  acc_to_regs(0, false);
   cp_async_commit();
   issue_partner(0);
   cp_async_commit();
@@ -854,11 +874,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
         started_here = is_head;
         if (is_head && s > 0) ++u;
       }
-      if (!a.emit && is_end && started_here)
-        grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
+      if (!a.emit && is_end && started_here) {
+        if (ACCREG) A = An;
+        else grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
+      }
     }
     // every buffer read above is private to the lane that filled it: refill without a barrier
     issue_self_acc(s + 1, started_here && !is_end);
+    acc_to_regs(s + 1, started_here && !is_end);
     cp_async_commit();
     issue_partner(s + 2);
     cp_async_commit();
@@ -1561,7 +1584,7 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
-                           bool use_async = false, int grid_override = 0, bool fifo = false) {
+                           bool use_async = false, int grid_override = 0, bool fifo = false, bool accreg = false) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
   if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
@@ -1587,9 +1610,12 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
                                     (int)smem));
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
       configured = smem;
     }
-    if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
+    if (a.D4 == G * NV && accreg) k_glove_rows_grp_async<G, NV, 2, true, true><<<row_blocks, kThreads, smem, stream>>>(a);
+    else if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
     else k_glove_rows_grp_async<G, NV, 2, false><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if (phases & 1) {
@@ -1660,10 +1686,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     const bool as = cfg->reserved != 1;  // reserved == 1: keep rows in registers (A/B probe)
     const int go = cfg->row_blocks;
     const bool ff = cfg->reserved == 2;  // reserved == 2: bulk-copy FIFO staging (A/B probe)
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff);
+    const bool ar = cfg->reserved == 3;  // reserved == 3: accumulator rows via ld.global.cs registers (experimental)
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar);
   }
   switch (nk) {
     case 1:
