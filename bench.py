@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--row-blocks", type=int, default=-1, help="persistent row-pass grid (-1 = trainer default, 0 = 2 CTAs per SM)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: row exchange over NVLink peer memory (libesr kernels) or NCCL all-to-all")
+    ap.add_argument("--fast-sync", action="store_true",
+                    help="N>1 peer path, experimental: libesr peer all-reduce / barrier kernels instead of NCCL + symm-mem barrier")
+    ap.add_argument("--step-graphs", action="store_true", help="N>1 peer path, experimental: CUDA-graph the sharded step")
     return ap.parse_args()
 
 
@@ -234,7 +237,10 @@ def run_sharded(a, rank, world, local):
     from esrecsys_b200.sharded import PeerShardedGloveTrainer, ShardedGloveTrainer
     V, D, B = a.vocab, a.dim, a.batch
     torch.manual_seed(a.seed)
-    tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr)
+    kw = {}
+    if a.exchange == "peer" and (a.fast_sync or a.step_graphs):      # experimental switches of the peer path (off by default)
+        kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs}
+    tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr, **kw)
     tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
     ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
     dev_b = [(torch.from_numpy(ids[k]).cuda(), torch.from_numpy(counts[k]).cuda()) for k in range(a.nbatch)]

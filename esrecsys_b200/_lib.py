@@ -99,6 +99,8 @@ _SIGNATURES = {
     "esr_peer_pull_ids_i32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_int64, _P]),
     "esr_peer_merge_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                              C.c_float, C.c_float, _P]),
+    "esr_peer_sync_bytes": (C.c_size_t, []),
+    "esr_peer_allreduce_f32": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     "esr_peer_resolve_i32": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P]),
     "esr_peer_apply_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                              C.c_float, C.c_float, _P]),

@@ -376,6 +376,94 @@ extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE
                                     recv_cap, lr, eps, stream_);
 }
 
+// ---------------------------------------------------------------------------------------------
+// esr_peer_allreduce_f32: all-reduce of a handful of floats (or, with count == 0, a pure barrier) over symmetric peer
+// memory -- the step's two batch-sum reductions and its phase barriers as ONE plain kernel each, so the sharded step
+// holds no NCCL call and stays CUDA-graph capturable, and a synchronisation costs one NVLink round trip.
+// Every rank owns a sync block of kSyncRing x ESR_MAX_PEERS slots of 8 words: [0..5] payload, [7] sequence flag.
+// Call k (k = 1, 2, ...; the counter lives on the device so a replayed graph advances it):
+//   publish : lane r < n stores my payload, then (release, system scope) the flag k into slot [k % ring][me] of rank r;
+//   wait    : lane s < n polls slot [k % ring][s] of MY block until its flag is k (acquire, system scope);
+//   reduce  : lane c < count adds the n payloads in rank order -> bit-identical sums on every rank.
+// A rank can run at most one call ahead of the slowest one (it cannot leave call k before everyone published k), so a
+// ring of 2 would do; 4 is used.  The poll is bounded by wall time: a lost peer traps instead of hanging the GPU.
+// EXPERIMENTAL in round 1 (written after the GPU budget was spent): PeerShardedGloveTrainer(fast_sync=True).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSyncRing = 4;
+constexpr int kSyncWords = 8;
+constexpr int kSyncMaxCount = 6;
+constexpr unsigned long long kSyncTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) k_peer_allreduce(PeerPtrs sync, int n, int me, const float* in, float* out, int count,
+                                                       uint32_t* seq_counter) {
+  const int lane = threadIdx.x;
+  const uint32_t seq = *seq_counter + 1u;
+  const int ring = (int)(seq % kSyncRing);
+  float mine[kSyncMaxCount];
+#pragma unroll
+  for (int c = 0; c < kSyncMaxCount; ++c) mine[c] = c < count ? in[c] : 0.f;
+  if (lane < n) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(const_cast<void*>(sync.p[lane])) + ((size_t)ring * ESR_MAX_PEERS + me) * kSyncWords;
+#pragma unroll
+    for (int c = 0; c < kSyncMaxCount; ++c)
+      if (c < count) st_relaxed_sys(dst + c, __float_as_uint(mine[c]));
+    st_release_sys(dst + 7, seq);  // release: the payload stores above are visible before the flag
+  }
+  const uint32_t* my = reinterpret_cast<const uint32_t*>(sync.p[me]) + (size_t)ring * ESR_MAX_PEERS * kSyncWords;
+  if (lane < n) {
+    const uint32_t* flag = my + (size_t)lane * kSyncWords + 7;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) != seq) {
+      if (global_ns() - t0 > kSyncTimeoutNs) __trap();
+      __nanosleep(40);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (lane < count) {
+    float sum = 0.f;
+    for (int r = 0; r < n; ++r) sum += __uint_as_float(ld_relaxed_sys(my + (size_t)r * kSyncWords + lane));
+    out[lane] = sum;
+  }
+  __syncwarp();
+  if (lane == 0) *seq_counter = seq;
+}
+
+extern "C" size_t esr_peer_sync_bytes(void) { return (size_t)kSyncRing * ESR_MAX_PEERS * kSyncWords * sizeof(uint32_t); }
+
+extern "C" int esr_peer_allreduce_f32(void* const* peer_sync, int32_t n_ranks, int32_t me, const float* in, float* out,
+                                      int32_t count, uint32_t* seq_counter, esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && count >= 0 && count <= kSyncMaxCount);
+  ESR_REQUIRE(seq_counter != nullptr && (count == 0 || (in != nullptr && out != nullptr)));
+  PeerPtrs ps;
+  ESR_REQUIRE(load_ptrs(&ps, reinterpret_cast<const void* const*>(peer_sync), n_ranks));
+  k_peer_allreduce<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(ps, n_ranks, me, in, out, count, seq_counter);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
 // emit_map[u] = owner << 27 | (offset of my bucket in owner's inbox + position inside the bucket)
 __global__ void __launch_bounds__(kThreads) k_peer_emit_plan(PeerPtrs counts, int n_ranks, int me, Cyclic cyc,
                                                              const int32_t* __restrict__ uniq,

@@ -239,7 +239,7 @@ class PeerShardedGloveTrainer:
     LAUNCHES_PER_STEP = 25
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
-                 graphs=False):
+                 graphs=False, fast_sync=False):
         import torch.distributed._symmetric_memory as symm_mem
         L.require_cuda()
         self.group = group if group is not None else dist.group.WORLD
@@ -322,11 +322,32 @@ class PeerShardedGloveTrainer:
         self.t = 0
         self.loss = None
         self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        # fast_sync (EXPERIMENTAL, off): the two batch-sum all-reduces and the two phase barriers of a step as libesr
+        # peer-memory kernels (esr_peer_allreduce_f32) instead of NCCL + the symmetric-memory barrier -- one NVLink
+        # round trip each, and no library collective left inside the step, so the whole step can be graph-captured
+        self.fast_sync = bool(fast_sync)
+        if self.fast_sync:
+            words = int(L.lib().esr_peer_sync_bytes()) // 4
+            self.sync, self.p_sync = symm((words,), torch.int32)
+            self.sync.zero_()
+            self.sync_seq = torch.zeros(1, **i32)
         torch.cuda.current_stream().synchronize()
-        self.barrier()
+        self._hdls[0].barrier()
 
     def barrier(self):
-        self._hdls[0].barrier()
+        if self.fast_sync:
+            L.check(L.lib().esr_peer_allreduce_f32(self.p_sync, self.n, self.rank, None, None, 0, L.ptr(self.sync_seq),
+                                                   L.stream_ptr()), "esr_peer_allreduce_f32")
+        else:
+            self._hdls[0].barrier()
+
+    def _all_reduce(self, view):
+        """Sum of a few floats over the ranks, in place."""
+        if self.fast_sync:
+            L.check(L.lib().esr_peer_allreduce_f32(self.p_sync, self.n, self.rank, L.ptr(view), L.ptr(view), view.numel(),
+                                                   L.ptr(self.sync_seq), L.stream_ptr()), "esr_peer_allreduce_f32")
+        else:
+            dist.all_reduce(view, group=self.group)
 
     # -- the two halves of a step; every call enqueues on the CURRENT stream ------------------------------------
     def _plan_body(self, k):
@@ -347,7 +368,7 @@ class PeerShardedGloveTrainer:
         L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
                                         self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
         st.prep(cplan, self.st_counts[k])
-        dist.all_reduce(st.scalars[0:3], group=self.group)      # also orders: all fetches done, all route plans published
+        self._all_reduce(st.scalars[0:3])                       # also orders: all fetches done, all route plans published
         L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
                                           L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
                                           sp), "esr_peer_pull_ids_i32")
@@ -357,7 +378,7 @@ class PeerShardedGloveTrainer:
                                            plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
                                            L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
         st.rows(cplan)                                          # gradient rows go straight to the owners' inboxes
-        dist.all_reduce(st.scalars[3:5], group=self.group)
+        self._all_reduce(st.scalars[3:5])
         st.finish(cplan)
         self.barrier()                                          # every rank's gradients have landed in the inboxes
         L.check(lib.esr_peer_apply_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,

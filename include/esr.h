@@ -336,6 +336,16 @@ int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const flo
                                int64_t map_stride, int32_t* desc /* scratch [recv_cap * (n_ranks + 1)] */, int64_t recv_cap,
                                float lr, float eps, esr_stream_t stream);
 
+/* All-reduce (sum) of count <= 6 floats across the ranks -- count == 0: a device barrier -- over symmetric peer memory,
+ * as one single-warp kernel (no NCCL, CUDA-graph capturable): the batch-sum reductions SURVEY.md 8(e)(3) and the phase
+ * barriers of the sharded step.  peer_sync[r] = rank r's sync block (esr_peer_sync_bytes() bytes, zeroed once before the
+ * first call, same rendezvous as the other peer buffers); seq_counter = device uint32, zeroed once, advanced by every
+ * call (every rank must make the same calls in the same order).  Sums are formed in rank order: bit-identical on every
+ * rank.  in == out is allowed.  A peer that never arrives traps after 20 s instead of hanging the device. */
+size_t esr_peer_sync_bytes(void);
+int esr_peer_allreduce_f32(void* const* peer_sync, int32_t n_ranks, int32_t me, const float* in, float* out,
+                           int32_t count, uint32_t* seq_counter, esr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Native decoders of the reference's record formats (HOST pointers).  Re-entrant,
  * allocation-free; a negative return is an ESR_E* code.

@@ -30,7 +30,8 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
         E, b = synth.init_glove_tables(V, D, 0)
         b = (np.random.default_rng(5).standard_normal(V) * 0.05).astype(np.float32)
         ids, counts = synth.glove_batches(V, B_loc * world, steps, 1)     # global batches
-        tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode)
+        kw = {"fast_sync": True} if peer == "fast" else {}        # libesr peer all-reduce / barrier kernels (experimental)
+        tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode, **kw)
         tr.load_dense(E, b)
         Eo, bo = E.copy(), b.copy()
         aE, ab = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC), np.full_like(bo, oopt.ADAGRAD_INIT_ACC)
@@ -51,7 +52,8 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("peer", [False, True], ids=["nccl_a2a", "peer_memory"])
+@pytest.mark.parametrize("peer", [False, True] + (["fast"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []),
+                         ids=["nccl_a2a", "peer_memory"] + (["peer_fast_sync"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []))
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B_loc", [(5000, 64, 1024), (300, 128, 512)])
 def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode, peer):
