@@ -30,7 +30,22 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
     if (!(cond)) return ESR_EINVAL; \
   } while (0)
 
-int sm_count();  // cached per process (device of first call)
+int sm_count();  // of the current device (cached per device)
+
+// Largest dynamic shared-memory opt-in already made for ONE kernel, per device (cudaFuncSetAttribute is a per-device
+// setting; a process normally drives one GPU, but nothing here relies on it):
+//   static SmemOptIn seen;  if (smem > 48 * 1024 && seen.raise(smem)) cudaFuncSetAttribute(kernel, ..., smem);
+struct SmemOptIn {
+  static constexpr int kMaxDevices = 64;
+  size_t v[kMaxDevices] = {};
+  bool raise(size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;  // unknown: always opt in
+    if (smem <= v[dev]) return false;
+    v[dev] = smem;
+    return true;
+  }
+};
 
 #ifdef __CUDACC__
 #define ESR_HD __host__ __device__

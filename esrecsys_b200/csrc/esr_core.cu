@@ -15,12 +15,12 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[64] = {};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 

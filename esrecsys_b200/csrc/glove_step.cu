@@ -1594,25 +1594,22 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
   if ((phases & 1) && use_async && fifo) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + kFifoBufs * ((size_t)a.D4 * 16 + 8));
-    static size_t configured_fifo = 0;  // per <G, NV> instantiation
-    if (smem > 48 * 1024 && smem > configured_fifo) {
+    static SmemOptIn configured_fifo;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && configured_fifo.raise(smem))
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_fifo<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_fifo = smem;
-    }
     k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
-    static size_t configured = 0;  // per <G, NV> instantiation
-    if (smem > 48 * 1024 && smem > configured) {
+    static SmemOptIn configured;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && configured.raise(smem)) {
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      configured = smem;
     }
     if (a.D4 == G * NV && accreg) k_glove_rows_grp_async<G, NV, 2, true, true><<<row_blocks, kThreads, smem, stream>>>(a);
     else if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
@@ -1621,12 +1618,10 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
   } else if (phases & 1) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     constexpr size_t smem = (size_t)kWarps * GP * sizeof(GroupMeta);
-    static bool configured = false;  // per <G, NV> instantiation
-    if (smem > 48 * 1024 && !configured) {
+    static SmemOptIn configured;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && configured.raise(smem))
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
     k_glove_rows_grp<G, NV, (NV <= 2 ? 3 : 2)><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   }
@@ -1643,11 +1638,9 @@ static int launch_rows(const RowsArgs& a, const GloveWs& w, float* scalars, bool
   if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
   if (tma) {
     const size_t smem = (size_t)kWarps * kTmaStages * 3 * a.D4 * 16;
-    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per NK: largest dynamic smem opted in
-    if (smem > configured[NK]) {
+    static SmemOptIn configured;  // per NK instantiation: largest dynamic smem opted in
+    if (configured.raise(smem))
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_tma<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[NK] = smem;
-    }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(tma_min_blocks(NK), (size_t)(220 * 1024) / (smem + 1024)));
     row_blocks = (int)std::min<int64_t>(w.row_blocks, (int64_t)sm_count() * per_sm);
     if (phases & 1) k_glove_rows_tma<NK><<<row_blocks, kThreads, smem, stream>>>(a);

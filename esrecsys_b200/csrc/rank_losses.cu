@@ -366,11 +366,8 @@ extern "C" int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, con
               neg_album && neg_artist && loss && dXa && dXr && album_rows && artist_rows);
   const size_t smem = spotify_smem(nc, max_m, o, F);
   if (smem > 220 * 1024) return ESR_ENOTSUP;  // playlist too long for one CTA's shared memory
-  static size_t configured = 0;
-  if (smem > configured) {
-    ESR_CUDA(cudaFuncSetAttribute(k_spotify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemOptIn configured;
+  if (configured.raise(smem)) ESR_CUDA(cudaFuncSetAttribute(k_spotify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SpotifyArgs a;
   a.A = album_table; a.R = artist_table; a.VA = VA; a.F = F; a.nc = nc; a.o = o;
   a.album_ctx = album_ctx; a.artist_ctx = artist_ctx; a.next_album = next_album; a.next_artist = next_artist;

@@ -363,11 +363,9 @@ extern "C" int esr_score_all_f32(const EsrTable* t, const float* queries, int32_
   if (t->V == 0) return ESR_OK;
   const size_t smem = (size_t)T * t->D * sizeof(float);
   if (smem > 200 * 1024) return ESR_ENOTSUP;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static SmemOptIn configured;
+  if (smem > 48 * 1024 && configured.raise(smem))
     ESR_CUDA(cudaFuncSetAttribute(k_score_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   const int64_t want = ceil_div(t->V, kThreads / 32);
   const int64_t cap = (int64_t)sm_count() * 8;
   k_score_all<<<(unsigned)(want < cap ? want : cap), kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
