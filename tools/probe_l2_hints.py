@@ -1,17 +1,18 @@
-"""Developer probe: A/B of the L2 eviction-priority hints on the row pass's cp.async copies (GloveStep variant 3 / 4,
-csrc/glove_step.cu k_glove_rows_grp_async<..., HINT>) against the default (variant 0).
+"""Developer probe: A/B of row-pass staging variants (GloveStep(variant=...)) against the default (variant 0).
 
-    python tools/probe_l2_hints.py [--steps 20] [--B 262144]        # parent: one child process per variant
-    python tools/probe_l2_hints.py --variant 3                      # child
+    python tools/probe_l2_hints.py --variants 0,3 [--steps 20] [--B 262144]   # parent: one child process per variant
+    python tools/probe_l2_hints.py --variant 3                                # child
 
-STATUS (round 1): both hinted variants fault with "an illegal instruction was encountered" on B200
-(profiles/r1_l2_hints_probe.json), so they are NOT in the library; the kernel change this probe drives is kept as
-profiles/r1_l2_hint_probe.patch (git apply it, rebuild, then run this).  Variant 0 alone is a quick row-pass timer.
+Variant 3 = `accreg` (accumulator rows through ld.global.cs registers, evict-first in L2; in the library, experimental).
+HISTORY (round 1): the first use of this probe tested L2::cache_hint descriptors on the cp.async copies -- at that
+time numbered variants 3 / 4 -- and both faulted with "an illegal instruction was encountered" on B200
+(profiles/r1_l2_hints_probe.json).  That kernel change is NOT in the library; it is kept as
+profiles/r1_l2_hint_probe.patch (a diff against commit 1644865's csrc/glove_step.cu).
 
 Each child trains the same seeded table on the same Zipf and uniform batches, prints the row-pass time (CUDA
-events, 256 MB L2 flush between steps) and a bit-pattern checksum of the final table / accumulator / bias.  The hints
-do not touch the arithmetic, so the checksums must equal variant 0's -- that is the parity check.  One process per
-variant so that a faulting variant cannot take the others' numbers with it.  Not a benchmark of record.
+events, 256 MB L2 flush between steps) and a bit-pattern checksum of the final table / accumulator / bias.  The
+variants do not touch the arithmetic, so the checksums must equal variant 0's -- that is the parity check.  One process
+per variant so that a faulting variant cannot take the others' numbers with it.  Not a benchmark of record.
 """
 import argparse
 import json
@@ -69,7 +70,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--nbatch", type=int, default=4)
     ap.add_argument("--variant", type=int, default=-1)
-    ap.add_argument("--variants", default="0,3,4")
+    ap.add_argument("--variants", default="0,3")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "l2_hints.json"))
     a = ap.parse_args()
     if a.variant >= 0:
