@@ -3,7 +3,7 @@ it needs /root/reference).  Same mechanism as make_ref_golden.py -- the referenc
 tests/golden/refshim -- but instead of writing fixtures it draws many random shapes / id patterns per trainer and compares
 the oracle (float64) with what the reference's functions return, case by case.
 
-    python tests/golden/ref_live_check.py wikipedia|spotify|pinterest [n_cases] [seed]
+    python tests/golden/ref_live_check.py wikipedia|spotify|pinterest|records [n_cases] [seed]
 
 Prints "OK <n>" or raises.  One trainer per process: the three directories reuse the module names `models`,
 `input_pipeline`."""
@@ -193,8 +193,53 @@ def pinterest(n, seed):
     print("OK", n)
 
 
+def records(n, seed):
+    """Wire formats: random CooccurrenceRow / TokenStat messages serialised by the reference's own generated protobuf
+    module (wikipedia/nlp_pb2.py) and parsed back by it exactly as cooccurrence_matrix.py:69-83 / token_dictionary.py
+    do, against the native decoder (esr_decode_cooccur_b64, host code) and the host TokenStat parser.  Bit-exact."""
+    mk._enter("wikipedia")
+    import base64
+    import numpy as np
+    import nlp_pb2 as nlp_pb
+    from esrecsys_b200.wikipedia import cooccurrence_matrix as cm
+    from esrecsys_b200.wikipedia import token_dictionary as td
+    rng = np.random.default_rng(seed)
+    for case in range(n):
+        lines, ii, jj, cc = [], [], [], []
+        for r in range(int(rng.integers(1, 40))):
+            row = nlp_pb.CooccurrenceRow()
+            row.index = int(rng.choice([0, 1, 127, 128, 16383, 16384, 2 ** 31 - 1, int(rng.integers(0, 2 ** 31))]))
+            k = int(rng.choice([0, 1, 2, 63, 64, 200]))
+            row.other_index.extend(int(v) for v in rng.integers(0, 2 ** 31, k))
+            vals = rng.lognormal(0, 3, k).astype(np.float32)
+            if k:
+                vals[rng.integers(0, k)] = np.float32(rng.choice([0.0, 1e-42, 3.4e38, 1.0 / 3]))
+            row.count.extend(float(v) for v in vals)
+            lines.append(base64.b64encode(row.SerializeToString()))
+            back = nlp_pb.CooccurrenceRow()
+            back.ParseFromString(base64.b64decode(lines[-1]))
+            for t in range(len(back.other_index)):
+                ii.append(back.index); jj.append(back.other_index[t]); cc.append(back.count[t])
+        text = b"".join(ln + b"\n" for ln in lines)
+        i, j, c, used = cm.decode_text(text)
+        assert used == len(text)
+        assert np.array_equal(i, np.asarray(ii, np.int64).astype(np.int32)) and np.array_equal(j, np.asarray(jj, np.int64).astype(np.int32))
+        assert np.array_equal(c.view(np.uint32), np.asarray(cc, np.float32).view(np.uint32))
+        assert cm.encode_row(5, [int(v) for v in jj[:7]], [float(v) for v in cc[:7]]) == nlp_pb.CooccurrenceRow(
+            index=5, other_index=[int(v) for v in jj[:7]], count=[float(v) for v in cc[:7]]).SerializeToString()
+        ts = nlp_pb.TokenStat(token="".join(chr(int(v)) for v in rng.choice([97, 233, 0x4e2d, 0x1F600, 45], int(rng.integers(0, 9)))),
+                              url="u%d" % case if case % 3 else "", frequency=int(rng.integers(0, 2 ** 40)),
+                              doc_frequency=int(rng.integers(0, 2 ** 20)), index=int(rng.integers(0, 2 ** 31)))
+        raw = ts.SerializeToString()
+        got = td.parse_token_stat(raw)
+        assert got == {"token": ts.token, "url": ts.url, "frequency": ts.frequency, "doc_frequency": ts.doc_frequency,
+                       "index": ts.index}, (got, ts)
+        assert td.encode_token_stat(ts.token, ts.url, ts.frequency, ts.doc_frequency, ts.index) == raw
+    print("OK", n)
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    {"wikipedia": wikipedia, "spotify": spotify, "pinterest": pinterest}[which](n, seed)
+    {"wikipedia": wikipedia, "spotify": spotify, "pinterest": pinterest, "records": records}[which](n, seed)

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "wikipedia")
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("trainer,seed", [("wikipedia", 1), ("spotify", 2), ("pinterest", 3)])
+@pytest.mark.parametrize("trainer,seed", [("wikipedia", 1), ("spotify", 2), ("pinterest", 3), ("records", 4)])
 def test_oracle_matches_reference_source_on_random_cases(trainer, seed):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "ref_live_check.py"), trainer, "20", str(seed)],
                        capture_output=True, text=True, timeout=280)
