@@ -1,7 +1,7 @@
 """Golden vectors produced by EXECUTING the reference's own source files (tests/golden/ref_*.npz).
 
     python tests/golden/make_ref_golden.py            # all three trainers, one subprocess each
-    python tests/golden/make_ref_golden.py wikipedia  # or spotify / pinterest
+    python tests/golden/make_ref_golden.py wikipedia  # or wikipedia_e2e / spotify / pinterest
 
 Runs HERE only (needs /root/reference, which does not exist on the GPU box); the vectors are committed.
 
@@ -123,6 +123,78 @@ def wikipedia():
         name = "ref_glove_V%d_D%d_B%d.npz" % (V, D, B)
         np.savez_compressed(os.path.join(HERE, name), **out)
         print("wrote", name, "losses", out["loss_adam"])
+
+
+def wikipedia_e2e():
+    """The body of train_cooccurence.main (:136-192) on a small corpus FILE, with the reference's own pieces end to end:
+    TokenDictionary -> CooccurrenceGenerator.get_batch -> Glove -> TrainState(optax.adam) -> [dump_knn, train_epoch] x
+    epochs.  (main itself needs wandb.init and tf.data; get_dataset (:108-115) only wraps get_batch into a tf Dataset.)
+    Writes the corpus part (tests/golden/e2e_cooccur/part-00000.bz2) and ref_glove_e2e.npz."""
+    _enter("wikipedia")
+    import base64
+    import bz2
+    import numpy as np
+    import jax
+    import jax.numpy as jnp
+    import optax
+    from flax.training import train_state
+    import nlp_pb2 as nlp_pb
+    import train_cooccurence as tc
+    from cooccurrence_matrix import CooccurrenceGenerator
+    from models import Glove
+    from token_dictionary import TokenDictionary
+
+    logged = []
+    tc.logging.info = lambda fmt, *a: logged.append(fmt % a)
+    D, B, epochs, steps_per_epoch, lr, seed = 8, 64, 2, 3, 0.05, 7
+    td = TokenDictionary(os.path.join(HERE, "token.tstat.pb.b64.bz2"))
+    num_tokens = td.get_embedding_dictionary_size()                               # :148
+    terms = "the,of,zürich,w010,w033"
+    debug_tokens = jnp.asarray(np.array([td.get_embedding_index(w) for w in terms.split(",")], np.int32))   # :150-154
+
+    # corpus: rows as make_cooccurrence.py:83-100 emits them (index > every other_index, fractional counts)
+    rng = np.random.default_rng(seed)
+    part_dir = os.path.join(HERE, "e2e_cooccur")
+    os.makedirs(part_dir, exist_ok=True)
+    with bz2.open(os.path.join(part_dir, "part-00000.bz2"), "wb") as f:
+        for index in range(2, 48):
+            row = nlp_pb.CooccurrenceRow()
+            row.index = index
+            k = int(rng.integers(4, 18))
+            others = rng.integers(1, index, k)
+            row.other_index.extend(int(v) for v in others)
+            row.count.extend(float(np.float32(v)) for v in np.clip(rng.lognormal(0.5, 1.6, k), 1.0 / 9, 400.0))
+            f.write(base64.b64encode(row.SerializeToString()) + b"\n")
+
+    model = Glove(num_embeddings=num_tokens, features=D)                             # :156
+    train_data = CooccurrenceGenerator(os.path.join(part_dir, "part-?????.bz2"))     # :158
+    train_iterator = train_data.get_batch(B, 0)                                      # what get_dataset wraps (:160)
+    x, _ = next(train_iterator)                                                      # :164 (consumes the first batch)
+    tree = model.init(jax.random.PRNGKey(seed), x)                                   # :165
+    assert tuple(tree["params"]["_token_embedding"]["embedding"].shape) == (num_tokens, D)
+    E = (np.random.default_rng(seed).standard_normal((num_tokens, D)) / np.sqrt(D)).astype(np.float32)
+    params = {"_token_embedding": {"embedding": jnp.asarray(E)}, "_bias": {"embedding": jnp.asarray(np.zeros((num_tokens, 1)))}}
+    state = train_state.TrainState.create(apply_fn=model.apply, params=params, tx=optax.adam(lr))     # :166-167
+    out = dict(D=np.int64(D), B=np.int64(B), epochs=np.int64(epochs), steps_per_epoch=np.int64(steps_per_epoch),
+               lr=np.float64(lr), seed=np.int64(seed), num_tokens=np.int64(num_tokens), terms=np.array(terms),
+               debug_tokens=_np(debug_tokens).astype(np.int32), E_checksum=np.float64(E.astype(np.float64).sum()),
+               first_batch_x=np.stack(x), train_loss=[])
+    for step in range(epochs):                                                       # :174
+        del logged[:]
+        tc.dump_knn(model, state.params, debug_tokens, td)                          # :178
+        out["knn_lines_%d" % step] = np.array(logged)
+        state, train_loss = tc.train_epoch(state, steps_per_epoch, train_iterator)  # :179
+        out["train_loss"].append(float(train_loss))
+    del logged[:]
+    tc.dump_knn(model, state.params, debug_tokens, td)
+    out["knn_lines_%d" % epochs] = np.array(logged)
+    out["train_loss"] = np.asarray(out["train_loss"])
+    Ef = _np(state.params["_token_embedding"]["embedding"])
+    assert np.array_equal(Ef[64:], E[64:].astype(np.float64))                        # rows beyond the corpus never move
+    out["E_final_head"], out["b_final_head"] = Ef[:64], _np(state.params["_bias"]["embedding"])[:64, 0]
+    np.savez_compressed(os.path.join(HERE, "ref_glove_e2e.npz"), **out)
+    print("wrote ref_glove_e2e.npz train_loss", out["train_loss"], "V", num_tokens)
+    print(out["knn_lines_%d" % epochs][0])
 
 
 # ------------------------------------------------------------------------------------------------ spotify
@@ -292,9 +364,9 @@ def pinterest():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wikipedia", "spotify", "pinterest"]
+    which = sys.argv[1:] or ["wikipedia", "wikipedia_e2e", "spotify", "pinterest"]
     if len(which) == 1:
-        {"wikipedia": wikipedia, "spotify": spotify, "pinterest": pinterest}[which[0]]()
+        {"wikipedia": wikipedia, "wikipedia_e2e": wikipedia_e2e, "spotify": spotify, "pinterest": pinterest}[which[0]]()
     else:                                               # module names collide across the three directories
         for w in which:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), w])
