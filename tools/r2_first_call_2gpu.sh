@@ -1,0 +1,15 @@
+#!/bin/bash
+# First multi-GPU call of round 2:   gpurun --gpus 2 --timeout 900 -- 'bash tools/r2_first_call_2gpu.sh'
+# libesr peer all-reduce / barrier kernels (fast_sync) and, on top of them, CUDA-graph capture of the sharded step.
+mkdir -p gpurun_out
+N=${N:-2}
+ESR_TEST_EXPERIMENTAL=1 timeout 500 python -m pytest tests/test_gpu_sharded.py -q -x -k "fast_sync" > gpurun_out/r2_fast_sync_tests.log 2>&1
+run() {  # name, extra flags
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+      bench.py --gpus $N --steps 100 --warmup 10 --no-cpu --no-inbatch --no-uniform $2 > gpurun_out/r2_bench_${N}gpu_$1.json 2> gpurun_out/r2_bench_${N}gpu_$1.err
+}
+run default ""
+run fast_sync "--fast-sync"
+run fast_sync_graphs "--fast-sync --step-graphs"
+tail -3 gpurun_out/r2_fast_sync_tests.log
+for f in gpurun_out/r2_bench_${N}gpu_*.json; do echo $f; head -c 400 $f; echo; done
