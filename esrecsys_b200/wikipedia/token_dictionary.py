@@ -69,82 +69,104 @@ def encode_token_stat(token="", url="", frequency=0, doc_frequency=0, index=0) -
     return msg
 
 
+# The delimiter set of the reference's tokenizer (wikipedia/token_dictionary.py:22) -- part of the data contract: the
+# dictionary on disk was built with it.
+_DELIMS = ' !@#$%^&*()_+\t\n",.:;/?><|{}\'[]'   # no backslash: the reference's "\\/" is an escaped slash
+_SPLITTER = re.compile("[" + re.escape(_DELIMS) + "]")
+_HASH_SPACE = 1 << 16          # width of the out-of-dictionary bucket range (:60-66)
+_HASH_CHARS = 10               # only the head of a long token is hashed (:50)
+
+
+def _crc16(chunk: bytes) -> int:
+    return binascii.crc32(chunk) & (_HASH_SPACE - 1)
+
+
+def _read_stats(path):
+    """TokenStat dicts of a ``*.tstat.pb.b64.bz2`` file, in file order."""
+    with bz2.open(path, "rb") as f:
+        for line in f:
+            yield parse_token_stat(base64.b64decode(line.rstrip(b"\n")))
+
+
 class TokenDictionary:
+    """Token <-> dictionary index <-> embedding row.  Column storage (one list per TokenStat field actually used)
+    instead of the reference's list of protobuf messages; behaviour pinned against the reference's own class
+    (tests/test_record_decoders.py, tests/test_ref_golden.py)."""
+
     def __init__(self, dictionary_file=None):
-        self.__token2index = {}
-        self.__max_doc_frequency = 0
-        self.__token_stat = []
-        self.__filter = re.compile('[ !@#$%^&*()_+\t\n",.:;\\\\/?><|{}\'\\[\\]]')
+        self._words = []           # dictionary index -> token
+        self._doc_freq = []        # dictionary index -> document frequency
+        self._lookup = {}          # token -> dictionary index
         if dictionary_file is not None:
             self.load(dictionary_file)
 
+    # -- file format ------------------------------------------------------------------------
     @staticmethod
     def save(all_tokens, output_filename):
-        """all_tokens: iterable of dicts with the TokenStat fields (the reference passes protobuf messages)."""
-        with bz2.open(output_filename, "wb") as ofile:
-            for item in all_tokens:
-                ofile.write(base64.b64encode(encode_token_stat(**item)))
-                ofile.write(b"\n")
+        """``all_tokens``: iterable of dicts with the TokenStat fields (the reference passes protobuf messages)."""
+        lines = (base64.b64encode(encode_token_stat(**fields)) + b"\n" for fields in all_tokens)
+        with bz2.open(output_filename, "wb") as out:
+            out.writelines(lines)
 
+    def load(self, dictionary_file):
+        for position, stat in enumerate(_read_stats(dictionary_file), start=len(self._words)):
+            if stat["index"] != position:      # the index scheme below relies on index == line number (:94)
+                raise AssertionError("token index %d at line %d" % (stat["index"], position))
+            self._lookup[stat["token"]] = position
+            self._words.append(stat["token"])
+            self._doc_freq.append(stat["doc_frequency"])
+
+    # -- text -------------------------------------------------------------------------------
     def simple_tokenize(self, x):
-        tokens = self.__filter.split(x)
-        return [t.lower() for t in tokens if len(t) > 0]
+        return [piece.lower() for piece in _SPLITTER.split(x) if piece]
 
     @staticmethod
     def minhash(token):
-        """Breaks a string up into chunks of overlapping 4 bytes and returns the smallest (token_dictionary.py:40-56)."""
-        count = len(token)
-        b = bytes(token, "utf-8") if type(token) is str else token
-        minhash = 0xFFFFFFFF
-        if count <= 4:
-            minhash = binascii.crc32(b) & 0xFFFF
-        else:
-            count = min(10, count)
-            for i in range(count - 4):
-                minhash = min(binascii.crc32(b[i:i + 4]) & 0xFFFF, minhash)
-        return minhash
+        """Smallest 16-bit CRC over the 4-byte windows of the token's head (:40-56).  As in the reference the LENGTH is
+        counted in characters while the windows slide over UTF-8 bytes; tokens of up to 4 characters hash whole."""
+        raw = token.encode("utf-8") if isinstance(token, str) else bytes(token)
+        n_chars = len(token)
+        if n_chars <= 4:
+            return _crc16(raw)
+        starts = range(min(n_chars, _HASH_CHARS) - 4)
+        return min((_crc16(raw[k:k + 4]) for k in starts), default=0xFFFFFFFF)
 
-    def get_embedding_index(self, token):
-        token_index = self.get_token_index(token)
-        if token_index is not None:
-            return 1 + token_index                      # 0 is reserved for the mask
-        return 1 + self.get_dictionary_size() + self.minhash(token)
+    # -- sizes and lookups --------------------------------------------------------------------
+    def get_dictionary_size(self):
+        return len(self._lookup)
 
     def get_embedding_dictionary_size(self):
-        return 1 + 65536 + self.get_dictionary_size()
-
-    def get_embedding_indices(self, tokens):
-        return [self.get_embedding_index(t) for t in tokens]
-
-    def load(self, dictionary_file):
-        count = 0
-        with bz2.open(dictionary_file, "rb") as file:
-            for line in file:
-                ts = parse_token_stat(base64.b64decode(line[:-1]))
-                assert ts["index"] == count
-                self.__token2index[ts["token"]] = ts["index"]
-                self.__max_doc_frequency = max(self.__max_doc_frequency, ts["doc_frequency"])
-                self.__token_stat.append(ts)
-                count += 1
-
-    def get_dictionary_size(self):
-        return len(self.__token2index)
+        """Mask row + dictionary + hash buckets (:68-70)."""
+        return self.get_dictionary_size() + _HASH_SPACE + 1
 
     def get_max_doc_frequency(self):
-        return self.__max_doc_frequency
+        return max(self._doc_freq, default=0)
 
     def get_doc_frequency(self, token_index):
-        return self.__token_stat[token_index]["doc_frequency"]
+        return self._doc_freq[token_index]
 
     def get_token_index(self, token):
-        return self.__token2index.get(token)
+        return self._lookup.get(token)
 
     def get_token(self, token_index):
-        return self.__token_stat[token_index]["token"]
+        return self._words[token_index]
+
+    def get_embedding_index(self, token):
+        """Row of the embedding table: 0 is the mask, known tokens follow, unknown ones land in a hash bucket (:58-66)."""
+        known = self._lookup.get(token)
+        if known is None:
+            return self.get_dictionary_size() + 1 + self.minhash(token)
+        return known + 1
+
+    def get_embedding_indices(self, tokens):
+        return list(map(self.get_embedding_index, tokens))
 
     def get_token_from_embedding_index(self, embedding_index):
-        if embedding_index == 0:
+        """Inverse of get_embedding_index for printing (:111-118), the reference's bucket label included (it subtracts
+        the bucket-range width, not the dictionary size)."""
+        row = int(embedding_index)
+        if row == 0:
             return "NULL"
-        elif embedding_index <= self.get_dictionary_size():
-            return self.get_token(embedding_index - 1)
-        return "MINHASH %d" % (embedding_index - 65536 - 1)
+        if row <= self.get_dictionary_size():
+            return self._words[row - 1]
+        return "MINHASH %d" % (row - _HASH_SPACE - 1)

@@ -235,6 +235,22 @@ def records(n, seed):
         assert got == {"token": ts.token, "url": ts.url, "frequency": ts.frequency, "doc_frequency": ts.doc_frequency,
                        "index": ts.index}, (got, ts)
         assert td.encode_token_stat(ts.token, ts.url, ts.frequency, ts.doc_frequency, ts.index) == raw
+    # the dictionary class itself: tokenizer, min-hash, embedding indices and their printed names on random strings
+    import token_dictionary as ref_td                       # /root/reference/wikipedia/token_dictionary.py
+    path = os.path.join(HERE, "token.tstat.pb.b64.bz2")
+    want, got = ref_td.TokenDictionary(path), td.TokenDictionary(path)
+    alphabet = list("abcxyzABC019 _-.,;:/\\[]{}()'\"!?@#|<>+*&^%$\t\n") + ["é", "ü", "中", "\U0001F600", "the", "w010"]
+    for case in range(50 * n):
+        text = "".join(rng.choice(alphabet, int(rng.integers(0, 30))))
+        toks = want.simple_tokenize(text)
+        assert got.simple_tokenize(text) == toks, text
+        assert got.get_embedding_indices(toks) == want.get_embedding_indices(toks), toks
+        for t in toks:
+            assert got.minhash(t) == want.minhash(t) and got.get_token_index(t) == want.get_token_index(t)
+    for idx in list(range(1, 60)) + [65583, 70000]:          # 0 is skipped: the reference tests `is 0`
+        assert got.get_token_from_embedding_index(idx) == want.get_token_from_embedding_index(idx)
+    assert got.get_embedding_dictionary_size() == want.get_embedding_dictionary_size()
+    assert got.get_max_doc_frequency() == want.get_max_doc_frequency() and got.get_doc_frequency(3) == want.get_doc_frequency(3)
     print("OK", n)
 
 
