@@ -13,3 +13,7 @@ run fast_sync "--fast-sync"
 run fast_sync_graphs "--fast-sync --step-graphs"
 tail -3 gpurun_out/r2_fast_sync_tests.log
 for f in gpurun_out/r2_bench_${N}gpu_*.json; do echo $f; head -c 400 $f; echo; done
+# BASELINE configs[4]: 100M-row x 128 table row-sharded over the N GPUs -- lookup GB/s vs NVLink peak, full step, full-size properties
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 \
+    tools/table_sweep.py --steps 30 --warmup 5 > gpurun_out/r2_table_sweep_${N}gpu.json 2> gpurun_out/r2_table_sweep_${N}gpu.err
+head -c 1200 gpurun_out/r2_table_sweep_${N}gpu.json; tail -3 gpurun_out/r2_table_sweep_${N}gpu.err
