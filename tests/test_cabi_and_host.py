@@ -132,3 +132,54 @@ def test_inbatch_cfg_layout_and_workspace_query():
     assert 0 < h.esr_inbatch_workspace_bytes(C.byref(cfg)) < full
     cfg.D = 100
     assert h.esr_inbatch_workspace_bytes(C.byref(cfg)) == 0     # unsupported width is refused, not rounded
+
+
+def test_argument_validation_needs_no_gpu():
+    """Every entry point rejects null pointers / bad shapes / unknown ranks with ESR_EINVAL before it touches CUDA
+    (include/esr.h error convention), so these calls are safe on a box without a GPU."""
+    from esrecsys_b200 import _lib
+    h = _lib.lib()
+    EINVAL = _lib.ESR_EINVAL
+    assert b"inval" in h.esr_strerror(EINVAL).lower() or b"argument" in h.esr_strerror(EINVAL).lower()
+    # null table / plan / cfg
+    assert h.esr_table_gather_f32(None, None, 4, None, None) == EINVAL
+    assert h.esr_table_export_f32(None, None, None) == EINVAL
+    assert h.esr_plan_build_i32(None, None, 0, None) == EINVAL
+    assert h.esr_glove_prep_f32(None, None, None, None, None, None, 0, None) == EINVAL
+    assert h.esr_glove_step_f32(None, None, None, None, None, None, None, None, 0, None) == EINVAL
+    # a table whose row width is not a multiple of 4 floats (rows must be 16-byte aligned)
+    t = _lib.EsrTable()
+    t.struct_size = C.sizeof(_lib.EsrTable)
+    t.D, t.V = 6, 10
+    assert h.esr_table_gather_f32(C.byref(t), None, 0, None, None) == EINVAL
+    # a struct older than the library's (struct_size too small)
+    p = _lib.EsrPlan()
+    p.struct_size = 8
+    assert h.esr_plan_build_i32(C.byref(p), None, 0, None) == EINVAL
+    # dense optimizers: step count starts at 1 (optax bias correction), null params
+    assert h.esr_dense_adam_f32(None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 0, None) == EINVAL
+    assert h.esr_dense_adam_f32(None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 1, None) == EINVAL
+    assert h.esr_dense_sgdm_f32(None, None, None, 16, 0.1, 0.9, None) == EINVAL
+    # ranking / retrieval
+    assert h.esr_sort_cols_f32(None, 10, 1, 0, 10, None, None, None, 0, None) == EINVAL
+    assert h.esr_sample_uniform_i32(1, 1, 8, 0, None, None) == EINVAL
+    assert h.esr_rowwise_dot_f32(None, None, 4, 0, None, None) == EINVAL
+    # peer path: more ranks than one NVSwitch domain, rank outside the group, too many floats
+    assert h.esr_peer_gather_f32(None, None, 9, None, None, 4, 128, None, None, None) == EINVAL
+    assert h.esr_peer_gather_f32(None, None, 2, None, None, 4, 128, None, None, None) == EINVAL
+    assert h.esr_peer_allreduce_f32(None, 2, 2, None, None, 0, None, None) == EINVAL
+    assert h.esr_peer_allreduce_f32(None, 2, 0, None, None, 7, None, None) == EINVAL
+    assert h.esr_route_plan_i32(None, None, 4, 2, None, None, None, None, None, 0, None) == EINVAL
+    # in-batch scorer: unsupported width -> no workspace, and the call itself refuses
+    cfg = _lib.EsrInbatchCfg()
+    cfg.struct_size = C.sizeof(_lib.EsrInbatchCfg)
+    cfg.Bq = cfg.Bk = 256
+    cfg.D = 96
+    cfg.scale = 1.0
+    cfg.b_norm = 256.0
+    assert h.esr_inbatch_workspace_bytes(C.byref(cfg)) == 0
+    assert h.esr_inbatch_fwd_bwd_bf16(None, None, C.byref(cfg), None, None, None, None, 0, None) in (EINVAL, _lib.ESR_ENOTSUP)
+    # host decoders: null output buffers
+    n = C.c_int64(0)
+    used = C.c_size_t(0)
+    assert h.esr_decode_cooccur_b64(b"", 0, None, None, None, 0, C.byref(n), C.byref(used)) in (0, EINVAL)
