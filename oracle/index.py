@@ -10,7 +10,9 @@ spotify/models.py:42-45) hides it.  SURVEY.md section 0.1 row D7 therefore makes
 * stable sort of the slots by table row,
 * unique rows + segment offsets,
 * cyclic owner routing for the row-sharded table (rows are frequency ranks,
-  wikipedia/make_dictionary.py:113-116, so block sharding would hot-spot rank 0).
+  wikipedia/make_dictionary.py:113-116, so block sharding would hot-spot rank 0),
+* the peer-memory path's owner-side id pull / resolve and source-side emit map
+  (csrc/peer_ops.cu; pinned by the conservation checks in tests/test_oracle_index.py).
 
 Parity unpinned (no reference tests exist); everything here is plain integer
 NumPy and is pinned by hand-written micro cases in tests/test_oracle_index.py.
@@ -104,6 +106,75 @@ def route_plan(uniq: np.ndarray, n_ranks: int):
 def exchange_counts(all_send_counts: np.ndarray):
     """Simulate the count all-to-all: ``recv_counts[r][s] = send_counts[s][r]``."""
     return np.ascontiguousarray(np.asarray(all_send_counts, np.int32).T)
+
+
+# --------------------------------------------------------------------------
+# Peer-memory path (csrc/peer_ops.cu): what every rank derives, on the device, from
+# the route plans all ranks published -- no id exchange, no host-known sizes.
+# ``all_counts[s][q]`` = rows source s routes to owner q (route_plan counts),
+# ``all_send_local[s]`` = source s's owner-local ids in owner-bucket order.
+# --------------------------------------------------------------------------
+
+EMIT_SHIFT = 27     # emit_map = owner << 27 | index in the owner's inbox (include/esr.h, EsrGloveCfg.emit_map)
+
+
+def peer_pull_ids(all_counts, all_send_local, me: int, map_stride: int):
+    """Owner ``me``: esr_peer_pull_ids_i32.  Returns ``(recv_ids int32[total], src_meta int32[3n+4],
+    slot_map int32[n, map_stride])``: recv_ids is source-major; src_meta[3s:3s+3] = (offset of source s in
+    recv_ids, its count, displacement of my bucket inside source s's list), src_meta[3n] = total;
+    slot_map[s, x] = position of owner-local row x in source s's bucket, -1 if s does not name x."""
+    counts = np.asarray(all_counts, np.int64)
+    n = counts.shape[0]
+    src_meta = np.zeros(3 * n + 4, np.int32)
+    slot_map = np.full((n, map_stride), -1, np.int32)
+    parts, off = [], 0
+    for s in range(n):
+        dsp = int(counts[s, :me].sum())
+        cnt = int(counts[s, me])
+        src_meta[3 * s: 3 * s + 3] = (off, cnt, dsp)
+        ids = np.asarray(all_send_local[s], np.int32)[dsp: dsp + cnt]
+        slot_map[s, ids] = np.arange(cnt, dtype=np.int32)
+        parts.append(ids)
+        off += cnt
+    src_meta[3 * n] = off
+    recv_ids = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+    return recv_ids, src_meta, slot_map
+
+
+def peer_resolve(n: int, recv_ids, src_meta, slot_map):
+    """esr_peer_resolve_i32.  For received entry k (source s, row x): the entry of the FIRST source naming x owns
+    the row; ``desc[k, q]`` = index in my inbox of source q's gradient row for x (offset_q + position) for
+    q >= s naming x, -1 otherwise; non-owning entries are all -1.  Returns ``(desc int32[total, n], own bool[total])``
+    (the kernel's compacted own_list holds the k with own[k], in no particular order)."""
+    total = int(src_meta[3 * n])
+    desc = np.full((total, n), -1, np.int32)
+    own = np.zeros(total, bool)
+    offs = [int(src_meta[3 * s]) for s in range(n)]
+    for k in range(total):
+        s = 0
+        while s + 1 < n and k >= offs[s + 1]:
+            s += 1
+        x = int(recv_ids[k])
+        pos = slot_map[:, x]
+        if (pos[:s] >= 0).any():
+            continue
+        own[k] = True
+        for q in range(s, n):
+            if pos[q] >= 0:
+                desc[k, q] = offs[q] + int(pos[q])
+    return desc, own
+
+
+def peer_emit_map(all_counts, me: int, uniq, inv_order, n: int):
+    """Source ``me``: esr_peer_emit_plan_i32.  emit_map[u] = owner << 27 | (rows the sources before me send to that
+    owner + position of row u inside my bucket for it); inv_order[u] = position of uniq[u] in my owner-bucket order."""
+    counts = np.asarray(all_counts, np.int64)
+    uniq = np.asarray(uniq, np.int64)
+    own = uniq % n
+    off = counts[:me, :].sum(axis=0)                     # [owner]
+    dsp = np.concatenate([[0], np.cumsum(counts[me])])[:n]
+    idx = off[own] + np.asarray(inv_order, np.int64) - dsp[own]
+    return ((own << EMIT_SHIFT) | idx).astype(np.int32)
 
 
 def _splitmix64(x):

@@ -51,3 +51,83 @@ def test_exchange_counts_transpose():
     sc = np.arange(9, dtype=np.int32).reshape(3, 3)
     rc = oidx.exchange_counts(sc)
     assert rc[2, 0] == sc[0, 2] and rc.sum() == sc.sum()
+
+
+def _published(uniqs, n):
+    """Route plans of n sources: (all_counts [n][n], all_send_local, orders, inv_orders)."""
+    counts, sls, orders, invs = [], [], [], []
+    for u in uniqs:
+        c, _, sl, order = oidx.route_plan(u, n)
+        inv = np.empty(len(u), np.int32)
+        inv[order] = np.arange(len(u), dtype=np.int32)
+        counts.append(c); sls.append(sl); orders.append(order); invs.append(inv)
+    return np.stack(counts), sls, orders, invs
+
+
+def test_peer_pull_resolve_emit_micro():
+    # 2 ranks; source 0 names rows {0,1,2,4}, source 1 names {1,2,3}; owner 0 holds even rows, owner 1 odd rows
+    uniqs = [np.array([0, 1, 2, 4], np.int32), np.array([1, 2, 3], np.int32)]
+    counts, sls, orders, invs = _published(uniqs, 2)
+    assert counts.tolist() == [[3, 1], [1, 2]]
+    assert sls[0].tolist() == [0, 1, 2, 0] and sls[1].tolist() == [1, 0, 1]
+    # owner 0: source 0 sends local rows 0,1,2 (global 0,2,4), source 1 sends local row 1 (global 2)
+    recv, meta, smap = oidx.peer_pull_ids(counts, sls, 0, 4)
+    assert recv.tolist() == [0, 1, 2, 1]
+    assert meta[:6].tolist() == [0, 3, 0, 3, 1, 0] and meta[6] == 4
+    assert smap.tolist() == [[0, 1, 2, -1], [-1, 0, -1, -1]]
+    desc, own = oidx.peer_resolve(2, recv, meta, smap)
+    assert own.tolist() == [True, True, True, False]            # source 1's entry for local row 1 is owned by source 0's
+    assert desc.tolist() == [[0, -1], [1, 3], [2, -1], [-1, -1]]
+    # owner 1: source 0 sends local 0 (global 1), displacement 3 in its list; source 1 sends local 0, 1 (global 1, 3)
+    recv, meta, smap = oidx.peer_pull_ids(counts, sls, 1, 4)
+    assert recv.tolist() == [0, 0, 1] and meta[:6].tolist() == [0, 1, 3, 1, 2, 1]
+    desc, own = oidx.peer_resolve(2, recv, meta, smap)
+    assert own.tolist() == [True, False, True] and desc.tolist() == [[0, 1], [-1, -1], [-1, 2]]
+    # sources: where each unique row's gradient lands (owner << 27 | inbox index)
+    em0 = oidx.peer_emit_map(counts, 0, uniqs[0], invs[0], 2)
+    em1 = oidx.peer_emit_map(counts, 1, uniqs[1], invs[1], 2)
+    S = oidx.EMIT_SHIFT
+    assert em0.tolist() == [0, (1 << S) | 0, 1, 2]
+    assert em1.tolist() == [(1 << S) | 1, 3, (1 << S) | 2]
+
+
+def test_peer_scatter_merge_conserves_every_gradient():
+    """n virtual ranks: every source scatters one gradient per unique row through emit_map into the owners' inboxes;
+    every owner merges through desc.  Each (source, row) gradient must be summed exactly once, in source order."""
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 8):
+        V = 997
+        sizes = rng.integers(0, 300, size=n)
+        sizes[rng.integers(0, n)] = 0 if n > 2 else sizes[0]                     # an empty source
+        uniqs = [np.unique(rng.integers(0, V, size=int(sz))).astype(np.int32) for sz in sizes]
+        counts, sls, orders, invs = _published(uniqs, n)
+        V_max = oidx.shard_rows(V, 0, n)
+        inbox_cap = int(sum(len(u) for u in uniqs)) + 1
+        inbox = [np.full(inbox_cap, np.nan) for _ in range(n)]
+        filled = [np.zeros(inbox_cap, bool) for _ in range(n)]
+        for s in range(n):                                                       # the row pass's peer scatter
+            em = oidx.peer_emit_map(counts, s, uniqs[s], invs[s], n)
+            o, idx = em >> oidx.EMIT_SHIFT, em & ((1 << oidx.EMIT_SHIFT) - 1)
+            for u in range(len(uniqs[s])):
+                assert o[u] == uniqs[s][u] % n
+                assert not filled[o[u]][idx[u]], "two gradients land in one inbox slot"
+                filled[o[u]][idx[u]] = True
+                inbox[o[u]][idx[u]] = 1000.0 * s + uniqs[s][u]                   # identifies (source, row)
+        expect = {}
+        for s in range(n):
+            for r in uniqs[s]:
+                expect.setdefault(int(r), []).append(1000.0 * s + int(r))
+        seen = set()
+        for me in range(n):                                                      # the owners' merge
+            recv, meta, smap = oidx.peer_pull_ids(counts, sls, me, V_max)
+            total = int(meta[3 * n])
+            assert total == int(counts[:, me].sum()) and filled[me].sum() == total
+            desc, own = oidx.peer_resolve(n, recv, meta, smap)
+            for k in np.flatnonzero(own):
+                g = int(oidx.global_row(recv[k:k + 1], me, n)[0])
+                got = [inbox[me][d] for d in desc[k] if d >= 0]
+                assert got == expect[g], (n, me, g)                              # exactly the sources naming g, in source order
+                assert g not in seen
+                seen.add(g)
+            assert (desc[~own] == -1).all()
+        assert seen == set(expect)
