@@ -7,6 +7,8 @@ export ESR_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental pieces (bit-identity of the accreg row pass, the reference-run pipeline through libesr)
 timeout 400 python -m pytest tests/test_gpu_glove.py -q -x -k "accreg" > gpurun_out/r2_accreg_tests.log 2>&1
 timeout 200 python -m pytest tests/test_ref_golden.py -q -m gpu > gpurun_out/r2_ref_golden.log 2>&1
+# 1b. N virtual ranks on this one GPU: the peer path's integer kernels vs oracle/index.py, the sharded step vs the oracle
+timeout 400 python -m pytest tests/test_gpu_virtual_peers.py -q > gpurun_out/r2_virtual_peers.log 2>&1
 # 2. row-pass A/B, default vs accreg (Zipf + uniform, checksums must match)
 timeout 150 python tools/probe_l2_hints.py --variants 0,3 --out gpurun_out/r2_probe_accreg.json > gpurun_out/r2_probe_accreg.log 2>&1
 # 3. bench lines, default and accreg (no CPU leg, no in-batch leg: short)
@@ -19,5 +21,5 @@ for k in auto accreg; do
       --log-file gpurun_out/r2_ncu_rows_${k}.csv python tools/prof_glove.py --V 1000000 --D 128 --B 262144 --uniform --steps 1 \
       --variant $([ $k = accreg ] && echo 3 || echo 0) > gpurun_out/r2_ncu_rows_${k}.log 2>&1
 done
-tail -3 gpurun_out/r2_accreg_tests.log gpurun_out/r2_ref_golden.log
+tail -3 gpurun_out/r2_accreg_tests.log gpurun_out/r2_ref_golden.log gpurun_out/r2_virtual_peers.log
 cat gpurun_out/r2_probe_accreg.json | head -c 1500
