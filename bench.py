@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--fast-sync", action="store_true",
                     help="N>1 peer path, experimental: libesr peer all-reduce / barrier kernels instead of NCCL + symm-mem barrier")
     ap.add_argument("--step-graphs", action="store_true", help="N>1 peer path, experimental: CUDA-graph the sharded step")
+    ap.add_argument("--overlap-ids", action="store_true",
+                    help="N>1 peer path, experimental: id pull / resolve / emit plan on a side stream next to gather + prep")
     return ap.parse_args()
 
 
@@ -238,8 +240,8 @@ def run_sharded(a, rank, world, local):
     V, D, B = a.vocab, a.dim, a.batch
     torch.manual_seed(a.seed)
     kw = {}
-    if a.exchange == "peer" and (a.fast_sync or a.step_graphs):      # experimental switches of the peer path (off by default)
-        kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs}
+    if a.exchange == "peer" and (a.fast_sync or a.step_graphs or a.overlap_ids):   # experimental switches of the peer path (off by default)
+        kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs, "overlap_ids": a.overlap_ids}
     tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr, **kw)
     tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
     ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)

@@ -228,6 +228,8 @@ class PeerShardedGloveTrainer:
                     id lists and resolve who sends what -> emit plan -> row pass, whose gradient rows are STORED
                     STRAIGHT INTO THE OWNERS' INBOXES over NVLink -> all-reduce(2) -> finish -> barrier
                     -> owners merge their inbox locally, Adagrad -> barrier
+    ``overlap_ids=True`` (EXPERIMENTAL, off): pull / resolve / emit plan move to a second side stream behind a barrier at
+    the top of the step, which also replaces the barrier at its end.
     ``graphs=True`` captures both halves into CUDA graphs per parity after two eager steps (the eager step is ~25 host
     calls and partly host-bound).  EXPERIMENTAL and off by default: in round 1 the replay of the captured
     NCCL all-reduce + symmetric-memory barrier sequence dead-locked in the 2-GPU bench (killed by its timeout).
@@ -239,7 +241,7 @@ class PeerShardedGloveTrainer:
     LAUNCHES_PER_STEP = 25
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
-                 graphs=False, fast_sync=False):
+                 graphs=False, fast_sync=False, overlap_ids=False):
         import torch.distributed._symmetric_memory as symm_mem
         L.require_cuda()
         self.group = group if group is not None else dist.group.WORLD
@@ -331,6 +333,14 @@ class PeerShardedGloveTrainer:
             self.sync, self.p_sync = symm((words,), torch.int32)
             self.sync.zero_()
             self.sync_seq = torch.zeros(1, **i32)
+        # overlap_ids (EXPERIMENTAL, off): the owner-side id pull / resolve and the source-side emit plan depend on the
+        # published route plans only, so they run on a second side stream next to gather + prep instead of between the
+        # first all-reduce and the row pass; a barrier at the top of the step (all plans published, all updates of the
+        # previous step applied) replaces the one at its end
+        self.overlap_ids = bool(overlap_ids)
+        self.s_ids = torch.cuda.Stream(self.dev)
+        self.ev_top = torch.cuda.Event()
+        self.ev_ids = torch.cuda.Event()
         torch.cuda.current_stream().synchronize()
         self._hdls[0].barrier()
 
@@ -361,14 +371,11 @@ class PeerShardedGloveTrainer:
         L.check(L.lib().esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner),
                                              L.ptr(cplan.uniq), L.ptr(self.scratch), L.stream_ptr()), "esr_plan_compact_i32")
 
-    def _step_body(self, k):
+    def _ids_body(self, k, sp):
+        """Owner side: which rows the sources send me and where each source's gradient for a row lands in my inbox;
+        source side: where my gradient rows go.  Depends on the published route plans only."""
         lib, n = L.lib(), self.n
-        plan, pub, cplan, st = self.plans[k], self.pub[k], self.cplans[k], self.step_fn
-        sp = L.stream_ptr()
-        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
-                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
-        st.prep(cplan, self.st_counts[k])
-        self._all_reduce(st.scalars[0:3])                       # also orders: all fetches done, all route plans published
+        plan, pub = self.plans[k], self.pub[k]
         L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
                                           L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
                                           sp), "esr_peer_pull_ids_i32")
@@ -377,6 +384,27 @@ class PeerShardedGloveTrainer:
         L.check(lib.esr_peer_emit_plan_i32(pub["p_counts"], n, self.rank, L.ptr(plan.uniq), L.ptr(plan.n_uniq),
                                            plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
                                            L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
+
+    def _step_body(self, k):
+        lib, n = L.lib(), self.n
+        plan, cplan, st = self.plans[k], self.cplans[k], self.step_fn
+        sp = L.stream_ptr()
+        if self.overlap_ids:
+            main = torch.cuda.current_stream(self.dev)
+            self.barrier()                                      # every route plan of this step is published and every
+            self.ev_top.record(main)                            # owner has applied the previous step's updates
+            self.s_ids.wait_event(self.ev_top)
+            with torch.cuda.stream(self.s_ids):
+                self._ids_body(k, L.stream_ptr())
+                self.ev_ids.record(self.s_ids)
+        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
+                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
+        st.prep(cplan, self.st_counts[k])
+        self._all_reduce(st.scalars[0:3])                       # also orders: all fetches done, all route plans published
+        if self.overlap_ids:
+            torch.cuda.current_stream(self.dev).wait_event(self.ev_ids)
+        else:
+            self._ids_body(k, sp)
         st.rows(cplan)                                          # gradient rows go straight to the owners' inboxes
         self._all_reduce(st.scalars[3:5])
         st.finish(cplan)
@@ -385,7 +413,8 @@ class PeerShardedGloveTrainer:
                                                L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
                                                self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, sp),
                 "esr_peer_apply_adagrad_f32")
-        self.barrier()                                          # every owner has applied its updates
+        if not self.overlap_ids:
+            self.barrier()                                      # every owner has applied its updates
 
     def _capture(self):
         """Capture the two halves per parity into CUDA graphs (the eager step is ~25 host calls: at 0.5 ms per step the

@@ -30,7 +30,9 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
         E, b = synth.init_glove_tables(V, D, 0)
         b = (np.random.default_rng(5).standard_normal(V) * 0.05).astype(np.float32)
         ids, counts = synth.glove_batches(V, B_loc * world, steps, 1)     # global batches
-        kw = {"fast_sync": True} if peer == "fast" else {}        # libesr peer all-reduce / barrier kernels (experimental)
+        # experimental switches of the peer path: libesr peer all-reduce / barrier kernels; id phases on a side stream
+        kw = {"fast": {"fast_sync": True}, "overlap": {"overlap_ids": True},
+              "fast_overlap": {"fast_sync": True, "overlap_ids": True}}.get(peer, {})
         tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode, **kw)
         tr.load_dense(E, b)
         Eo, bo = E.copy(), b.copy()
@@ -52,8 +54,9 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("peer", [False, True] + (["fast"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []),
-                         ids=["nccl_a2a", "peer_memory"] + (["peer_fast_sync"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("peer", [False, True] + (["fast", "overlap", "fast_overlap"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []),
+                         ids=["nccl_a2a", "peer_memory"] + (["peer_fast_sync", "peer_overlap_ids", "peer_fast_sync_overlap_ids"]
+                                                            if os.environ.get("ESR_TEST_EXPERIMENTAL") else []))
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B_loc", [(5000, 64, 1024), (300, 128, 512)])
 def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode, peer):

@@ -19,12 +19,10 @@ What is CHECKED at full size (size-independent properties, bit-exact):
     row INSIDE the batch shrank, and most of those rows moved.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
