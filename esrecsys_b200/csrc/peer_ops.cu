@@ -37,7 +37,7 @@ struct Cyclic {
 // Persistent grid: groups of TPR lanes stride over quads of unique rows (sizes are only known on the
 // device, so a capacity-sized grid would launch mostly empty blocks).
 template <int TPR, int ROWS>
-__global__ void __launch_bounds__(kThreads) k_peer_gather(PeerPtrs rows, PeerPtrs bias, const int32_t* __restrict__ uniq,
+__global__ void __launch_bounds__(kThreads) k_peer_gather(const __grid_constant__ PeerPtrs rows, const __grid_constant__ PeerPtrs bias, const int32_t* __restrict__ uniq,
                                                           const int32_t* __restrict__ n_uniq, int64_t cap, Cyclic cyc,
                                                           int D4, float4* __restrict__ out, float* __restrict__ out_bias) {
   const int lane = threadIdx.x % TPR;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kThreads) k_peer_gather(PeerPtrs rows, PeerPtr
 
 // src_meta[s] = {offset of source s in recv_ids, count, displacement inside source s's bucket list}
 // slot_map[s][x] = position of owner-local row x in source s's list (-1: source s does not name x)
-__global__ void __launch_bounds__(kThreads) k_peer_pull_ids(PeerPtrs counts, PeerPtrs send_local, int n_ranks, int me,
+__global__ void __launch_bounds__(kThreads) k_peer_pull_ids(const __grid_constant__ PeerPtrs counts, const __grid_constant__ PeerPtrs send_local, int n_ranks, int me,
                                                             int64_t recv_cap, int32_t* __restrict__ recv_ids,
                                                             int32_t* __restrict__ src_meta, int32_t* __restrict__ slot_map,
                                                             int64_t map_stride) {
@@ -416,7 +416,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-__global__ void __launch_bounds__(32) k_peer_allreduce(PeerPtrs sync, int n, int me, const float* in, float* out, int count,
+__global__ void __launch_bounds__(32) k_peer_allreduce(const __grid_constant__ PeerPtrs sync, int n, int me, const float* in, float* out, int count,
                                                        uint32_t* seq_counter) {
   const int lane = threadIdx.x;
   const uint32_t seq = *seq_counter + 1u;
@@ -465,7 +465,7 @@ extern "C" int esr_peer_allreduce_f32(void* const* peer_sync, int32_t n_ranks, i
 }
 
 // emit_map[u] = owner << 27 | (offset of my bucket in owner's inbox + position inside the bucket)
-__global__ void __launch_bounds__(kThreads) k_peer_emit_plan(PeerPtrs counts, int n_ranks, int me, Cyclic cyc,
+__global__ void __launch_bounds__(kThreads) k_peer_emit_plan(const __grid_constant__ PeerPtrs counts, int n_ranks, int me, Cyclic cyc,
                                                              const int32_t* __restrict__ uniq,
                                                              const int32_t* __restrict__ n_uniq, int64_t cap,
                                                              const int32_t* __restrict__ inv_order, int64_t inbox_cap,

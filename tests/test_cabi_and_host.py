@@ -183,3 +183,34 @@ def test_argument_validation_needs_no_gpu():
     n = C.c_int64(0)
     used = C.c_size_t(0)
     assert h.esr_decode_cooccur_b64(b"", 0, None, None, None, 0, C.byref(n), C.byref(used)) in (0, EINVAL)
+
+
+def test_sass_of_the_hot_kernels():
+    """Static guard on the built library (cuobjdump, no GPU): the default row pass is spill-free and stages rows with
+    cp.async (LDGSTS) + packed f32x2 math; the in-batch kernels really are tcgen05 / TMEM / TMA code."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_evidence.py")], capture_output=True, text=True,
+                         check=True).stdout
+    rows = {}
+    for line in out.splitlines():
+        if line.startswith("#") or "|" not in line:
+            continue
+        name, regs, smem, local, n_ins, mn = [x.strip() for x in line.split("|")]
+        rows[name] = dict(regs=int(regs), local=int(local), mn=mn)
+    default = rows["k_glove_rows_grp_async<8, 4, 2, true, false>"]          # D = 128: 8 lanes x 4 float4 per row
+    assert default["local"] == 0 and default["regs"] <= 128                 # 2 CTAs of 256 threads per SM
+    assert "LDGSTS" in default["mn"] and "FFMA2" in default["mn"]
+    assert "LDG.E.EF" in rows["k_glove_rows_grp_async<8, 4, 2, true, true>"]["mn"]     # accreg: evict-first accumulator loads
+    scores = [v for k, v in rows.items() if k.startswith("k_inbatch_scores<")]
+    bwd = [v for k, v in rows.items() if k.startswith("k_inbatch_bwd<")]
+    assert scores and bwd
+    for v in scores + bwd:
+        assert v["local"] == 0
+        assert "UTCHMMA" in v["mn"] and "LDTM" in v["mn"] and "UTMALDG" in v["mn"]
+    # TMA-store epilogue of the passes that write the bf16 dL/dS block (the softmax statistics pass, mode 1, writes none)
+    assert all("UTMASTG" in v["mn"] for k, v in rows.items() if k.startswith("k_inbatch_scores<") and not k.endswith(", 1>"))
+    assert any("UBLKCP" in v["mn"] for k, v in rows.items() if k.startswith("k_glove_rows_tma<"))
