@@ -14,7 +14,8 @@ combine + finish).  Prints ONE JSON line (rank 0).
 * roofline   : the row-pass kernel's ALGORITHMIC bytes (U*R*4 + U*16 + B*12)
                / its CUDA-event duration, on the timed (Zipf) stream; roofline_uniform is the same
                kernel on the uniform no-reuse control stream, where the >=70 % target is judged.
-* cpu_baseline: oracle/glove_torch.py (a port of the reference's dense-Adam step) on the host.
+* cpu_baseline: oracle/glove_torch.py (a port of the reference's dense-Adam step) on the host;
+               cpu_baseline_same_algorithm: the sparse-Adagrad rule the GPU path runs, on the host.
 * --impl reference: only that CPU leg, as its own JSON line.
 """
 from __future__ import annotations
@@ -98,6 +99,35 @@ def cpu_reference(a, steps, warmup):
                 sample="%d steps of B=%d on the %dx%d table: oracle/glove_torch.step_adam_dense (dense grad + optax.adam "
                        "over all rows, as wikipedia/train_cooccurence.py:71-101), torch CPU ops, %d threads"
                        % (steps, B, V, D, cores)), dt / steps * 1e3
+
+
+def cpu_same_algorithm(a, steps, warmup):
+    """SURVEY.md 8(d) baseline (S): the north-star rule itself (sparse Adagrad on the touched rows only) on the host,
+    oracle/glove_torch.step_adagrad_sparse, multi-threaded torch CPU ops."""
+    import torch
+    from esrecsys_b200 import synth
+    from oracle import glove_torch as ogt
+    torch.manual_seed(a.seed)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    V, D, B = a.vocab, a.dim, a.batch
+    n = max(1, min(a.nbatch, steps + warmup))
+    ids, counts = synth.glove_batches(V, B, n, a.seed)
+    E = torch.randn(V, D) / np.sqrt(D)
+    b = torch.zeros(V)
+    accE, accb = torch.full_like(E, 0.1), torch.full_like(b, 0.1)
+    ti = [torch.from_numpy(ids[k, 0].astype(np.int64)) for k in range(n)]
+    tj = [torch.from_numpy(ids[k, 1].astype(np.int64)) for k in range(n)]
+    tx = [torch.from_numpy(counts[k]) for k in range(n)]
+    for k in range(warmup):
+        ogt.step_adagrad_sparse(E, b, accE, accb, ti[k % n], tj[k % n], tx[k % n], a.lr)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ogt.step_adagrad_sparse(E, b, accE, accb, ti[k % n], tj[k % n], tx[k % n], a.lr)
+    dt = time.perf_counter() - t0
+    return dict(value=B * steps / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d steps of B=%d on the %dx%d table: oracle/glove_torch.step_adagrad_sparse (unique rows, index_add "
+                       "segment sums, Adagrad on the touched rows only), torch CPU ops, %d threads" % (steps, B, V, D, cores))
 
 
 def run_reference(a):
@@ -435,6 +465,7 @@ def run_ours(a):
             torch.cuda.empty_cache()
             cb, _ = cpu_reference(a, a.cpu_steps, 1)
             line["cpu_baseline"] = cb
+            line["cpu_baseline_same_algorithm"] = cpu_same_algorithm(a, 2 * a.cpu_steps, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
