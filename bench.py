@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-inbatch", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="plan/staging buffers in flight (GloveTrainer)")
     ap.add_argument("--row-blocks", type=int, default=-1, help="persistent row-pass grid (-1 = trainer default, 0 = 2 CTAs per SM)")
+    ap.add_argument("--stream-priority", action="store_true",
+                    help="N=1, experimental: the step's stream at high priority over the plan stream")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: row exchange over NVLink peer memory (libesr kernels) or NCCL all-to-all")
     ap.add_argument("--fast-sync", action="store_true",
@@ -406,7 +408,8 @@ def run_ours(a):
     cnt_dev = [torch.from_numpy(counts[k]).cuda() for k in range(a.nbatch)]
     ids_pin = [torch.from_numpy(ids[k]).pin_memory() for k in range(a.nbatch)]
     cnt_pin = [torch.from_numpy(counts[k]).pin_memory() for k in range(a.nbatch)]
-    tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel, depth=a.depth, row_blocks=None if a.row_blocks < 0 else a.row_blocks)
+    tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel, depth=a.depth, row_blocks=None if a.row_blocks < 0 else a.row_blocks,
+                      priorities=a.stream_priority)
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -426,6 +429,7 @@ def run_ours(a):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "vocab": V, "dim": D, "batch": B, "optimizer": "sparse adagrad (north star)",
                    "bias_mode": "reference_broadcast", "kernel": a.kernel, "stream": "zipf(1)",
+                   **({"stream_priority": True} if a.stream_priority else {}),
                    "l2": "no flush: table + state = %.2f GB per GPU >> 126 MB L2, fresh random rows every step" % (table.nbytes() / 1e9),
                    "parallelism": "replicas" if world > 1 else "single"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,

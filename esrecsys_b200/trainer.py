@@ -25,7 +25,7 @@ from .engine import EmbeddingTable, GloveStep, IndexPlan
 
 class GloveTrainer:
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", chunk=0, impl="auto",
-                 graphs=True, depth=2, loss_log=4096, row_blocks=None):
+                 graphs=True, depth=2, loss_log=4096, row_blocks=None, priorities=False):
         L.require_cuda()
         if row_blocks is None:
             # The persistent row pass fills every SM with 2 CTAs, which leaves no registers for the plan
@@ -42,7 +42,9 @@ class GloveTrainer:
         self.plans = [IndexPlan(2 * self.B, table.V, self.dev) for _ in range(self.depth)]
         self.ids = [torch.zeros(2 * self.B, dtype=torch.int32, device=self.dev) for _ in range(self.depth)]
         self.counts = [torch.ones(self.B, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
-        self.s_main = torch.cuda.Stream(self.dev)
+        # priorities (EXPERIMENTAL, off): the step's short kernels (prep / combine / finish) on a high-priority stream, so
+        # their CTAs are placed ahead of the pending radix-sort CTAs of the next batch's plan instead of queueing behind them
+        self.s_main = torch.cuda.Stream(self.dev, priority=-1 if priorities else 0)
         self.s_side = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.depth)]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First gpurun call of round 2 (1 GPU): everything written at the end of round 1 without GPU time.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/r2_first_call.sh'
-# Results land in gpurun_out/r2_*.  Nothing here is a benchmark of record except the two bench.py lines.
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/r2_first_call.sh'
+# Results land in gpurun_out/r2_*.  Nothing here is a benchmark of record except the default bench.py line.
 mkdir -p gpurun_out
 export ESR_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental pieces (bit-identity of the accreg row pass, the reference-run pipeline through libesr)
@@ -15,6 +15,7 @@ timeout 150 python tools/probe_l2_hints.py --variants 0,3 --out gpurun_out/r2_pr
 unset ESR_TEST_EXPERIMENTAL
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch --kernel accreg > gpurun_out/r2_bench_accreg.json 2> gpurun_out/r2_bench_accreg.err
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch --no-uniform --stream-priority > gpurun_out/r2_bench_priority.json 2> gpurun_out/r2_bench_priority.err
 # 4. DRAM traffic of the row pass on the uniform stream, default vs accreg (one ncu pass each, row-pass kernel only)
 for k in auto accreg; do
   timeout 300 ncu --set full --clock-control none -k regex:k_glove_rows_grp_async -c 2 --csv --page raw \
