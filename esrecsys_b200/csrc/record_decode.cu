@@ -172,7 +172,8 @@ extern "C" int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes
   while (rec < max_records && (size_t)(end - p) >= 12) {
     uint64_t len;
     memcpy(&len, p, 8);
-    if ((uint64_t)(end - p) < 16 + len) break;  // incomplete record
+    const uint64_t avail = (uint64_t)(end - p);
+    if (avail < 16 || len > avail - 16) break;  // incomplete record (also a corrupt length: 16 + len must not wrap)
     const unsigned char* q = p + 12;
     const unsigned char* qe = q + len;
     int64_t start[16];
