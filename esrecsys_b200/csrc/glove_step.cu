@@ -72,6 +72,7 @@ int group_lanes(int D4) {
   return g;
 }
 
+constexpr int kHotRows = 16;       // HOT variant of the row pass: table rows 0..15 cached in shared memory per CTA
 constexpr int kMinAutoChunk = 16;
 constexpr int kHeavyParts = 32;   // straddling segments with more partials than this are combined by several blocks
 constexpr int kHeavySplit = 8;    // blocks per heavy segment
@@ -314,6 +315,8 @@ struct RowsArgs {
   int32_t chunk;
   int32_t per_pair;
   int32_t emit;
+  const uint8_t* ver;  // HOT variant only: buffer of each row (NULL: rows[0])
+  int32_t hot_rows;    // HOT variant only: min(HOT, V)
   float c2B;      // -2 / B_global
   float inv_B;    // 1 / B_global
   float lr, eps;
@@ -754,7 +757,12 @@ __device__ __forceinline__ void grow_store_f(const Row<NV>& r, float4* __restric
 // go through cp.async.cg (normal L2 priority) but through ld.global.cs into registers one slot ahead (SASS LDG.E.EF:
 // evict-first in L2), so it stops displacing table rows that a later slot re-reads as a partner.  Same arithmetic,
 // bit-identical results.  (The L2::cache_hint form of cp.async faults on B200: profiles/r1_summary.md 3c.)
-template <int G, int NV, int MINB, bool FULLD, bool ACCREG = false>
+// HOT > 0 (cfg.reserved == 4, experimental, not the default): every CTA keeps the table's first HOT rows -- ids are
+// frequency ranks (wikipedia/make_dictionary.py:113-116; the compact table of the sharded path is sorted by row too), so
+// under Zipf(1) rows 0..15 are 23 % of all partner reads -- in shared memory for the whole pass; a slot whose partner is
+// one of them reads it from there instead of staging it through cp.async (no L2 read, one crossing of the shared-memory
+// pipe instead of two).  Same values, same arithmetic: bit-identical results.
+template <int G, int NV, int MINB, bool FULLD, bool ACCREG = false, int HOT = 0>
 __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const RowsArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ float red[32 * 2];
@@ -773,6 +781,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
   const float4* const accp = reinterpret_cast<const float4*>(a.acc);
   float sums[2] = {0.f, 0.f};
+  const unsigned char* const hot = dyn_raw + (size_t)kWarps * GP * (sizeof(GroupMeta) + (size_t)NB * RB);
+  const uint32_t n_hot = HOT > 0 ? (uint32_t)a.hot_rows : 0u;
+  if (HOT > 0) {
+    float4* hp = reinterpret_cast<float4*>(const_cast<unsigned char*>(hot));
+    for (uint32_t e = threadIdx.x; e < n_hot * D4; e += kThreads) {
+      const uint32_t r = e / D4;
+      hp[e] = ((a.ver != nullptr && a.ver[r]) ? rows1 : rows0)[(uint64_t)r * D4 + (e - r * D4)];
+    }
+    __syncthreads();
+  }
   // Persistent warps pull work items (GP consecutive chunks) from a counter.  Items are handed out from
   // the END of the sorted stream: the cold rows (singleton segments, three DRAM rows per slot) are the
   // long items, so they start first and the cheap hot-row chunks fill in behind them (LPT order), and a
@@ -804,8 +822,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
     if (s < cnt) {
       const int32_t code = gm.rec[s].code;
       const uint32_t q = (uint32_t)(code & kRowMask);
-      grow_copy_async_f<G, NV, FULLD>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4, gl,
-                             a.D4, true);
+      if (HOT == 0 || q >= n_hot)
+        grow_copy_async_f<G, NV, FULLD>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4,
+                                        gl, a.D4, true);
     }
   };
   // self / accumulator rows of slot s (self: chunk start or segment head; acc: a segment that both
@@ -866,7 +885,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       rec = gm.rec[s];
       is_head = key_cur != k0;
       is_end = key_cur != k2;
-      grow_from_smem_f<G, NV, FULLD>(P, reinterpret_cast<const float4*>(bufs + (size_t)(s % 3) * RB), gl, a.D4);
+      const uint32_t pq = (uint32_t)(rec.code & kRowMask);
+      grow_from_smem_f<G, NV, FULLD>(P, reinterpret_cast<const float4*>(HOT > 0 && pq < n_hot ? hot + (size_t)pq * RB
+                                                                                                : bufs + (size_t)(s % 3) * RB),
+                                     gl, a.D4);
       if (s == 0 || is_head) {
         grow_from_smem_f<G, NV, FULLD>(cur, reinterpret_cast<const float4*>(bufs + 3 * (size_t)RB), gl, a.D4);
         row_zero(grad);
@@ -1547,6 +1569,8 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.chunk = w.chunk;
   a.per_pair = cfg->bias_mode == ESR_BIAS_PER_PAIR;
   a.emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
+  a.ver = t->ver;
+  a.hot_rows = (int32_t)std::min<int64_t>(kHotRows, t->V);
   a.c2B = -2.f / (float)cfg->B_global;
   a.inv_B = 1.f / (float)cfg->B_global;
   a.lr = cfg->lr;
@@ -1584,7 +1608,8 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
-                           bool use_async = false, int grid_override = 0, bool fifo = false, bool accreg = false) {
+                           bool use_async = false, int grid_override = 0, bool fifo = false, bool accreg = false,
+                           bool hotc = false) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
   if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
@@ -1598,6 +1623,15 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     if (smem > 48 * 1024 && configured_fifo.raise(smem))
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_fifo<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
+    ESR_LAUNCH_CHECK();
+  } else if ((phases & 1) && use_async && hotc && a.D4 == G * NV) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
+    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16) + (size_t)kHotRows * a.D4 * 16;
+    static SmemOptIn configured_hot;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && configured_hot.raise(smem))
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
@@ -1680,10 +1714,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     const int go = cfg->row_blocks;
     const bool ff = cfg->reserved == 2;  // reserved == 2: bulk-copy FIFO staging (A/B probe)
     const bool ar = cfg->reserved == 3;  // reserved == 3: accumulator rows via ld.global.cs registers (experimental)
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar);
+    const bool hc = cfg->reserved == 4;  // reserved == 4: hot rows cached in shared memory (experimental)
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar, hc);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
   }
   switch (nk) {
     case 1:

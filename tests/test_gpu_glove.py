@@ -21,7 +21,7 @@ RTOL = 1e-5
 ATOL = 1e-5
 # Row-pass variants under test.  Experimental variants that have not yet run on a GPU (written when the round's GPU
 # budget was spent) join the parity matrix with ESR_TEST_EXPERIMENTAL=1; they are never the default.
-IMPLS = ["auto", "ldg", "tma", "fifo"] + (["accreg"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else [])
+IMPLS = ["auto", "ldg", "tma", "fifo"] + (["accreg", "hot"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else [])
 
 
 def _engine():
@@ -271,13 +271,15 @@ def test_sparse_adagrad_and_scatter_rows():
 
 @pytest.mark.skipif(not os.environ.get("ESR_TEST_EXPERIMENTAL"), reason="experimental row-pass variant (ESR_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("V,D,B,uniform", [(20000, 128, 8192, False), (50000, 256, 4096, True), (300, 128, 2048, False)])
-def test_accreg_variant_bit_identical_to_default(V, D, B, uniform):
-    """The ld.global.cs accumulator staging changes where the row travels, not the arithmetic."""
+@pytest.mark.parametrize("variant", ["accreg", "hot"])
+def test_accreg_variant_bit_identical_to_default(V, D, B, uniform, variant):
+    """The ld.global.cs accumulator staging / the shared-memory cache of the hottest rows change where a row travels,
+    not the arithmetic."""
     eng = _engine()
     E, b = _tables(V, D, seed=V)
     ids, counts = _batch(V, B, seed=V + 3, uniform=uniform, n=3)
     outs = []
-    for impl in ("auto", "accreg"):
+    for impl in ("auto", variant):
         t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
         step = eng.GloveStep(t, B, impl=impl)
         plan = eng.IndexPlan(2 * B, V)

@@ -5,16 +5,17 @@
 mkdir -p gpurun_out
 export ESR_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental pieces (bit-identity of the accreg row pass, the reference-run pipeline through libesr)
-timeout 400 python -m pytest tests/test_gpu_glove.py -q -x -k "accreg" > gpurun_out/r2_accreg_tests.log 2>&1
+timeout 400 python -m pytest tests/test_gpu_glove.py -q -x -k "accreg or hot" > gpurun_out/r2_accreg_tests.log 2>&1
 timeout 200 python -m pytest tests/test_ref_golden.py -q -m gpu > gpurun_out/r2_ref_golden.log 2>&1
 # 1b. N virtual ranks on this one GPU: the peer path's integer kernels vs oracle/index.py, the sharded step vs the oracle
 timeout 400 python -m pytest tests/test_gpu_virtual_peers.py -q > gpurun_out/r2_virtual_peers.log 2>&1
 # 2. row-pass A/B, default vs accreg (Zipf + uniform, checksums must match)
-timeout 150 python tools/probe_l2_hints.py --variants 0,3 --out gpurun_out/r2_probe_accreg.json > gpurun_out/r2_probe_accreg.log 2>&1
+timeout 150 python tools/probe_l2_hints.py --variants 0,3,4 --out gpurun_out/r2_probe_accreg.json > gpurun_out/r2_probe_accreg.log 2>&1
 # 3. bench lines, default and accreg (no CPU leg, no in-batch leg: short)
 unset ESR_TEST_EXPERIMENTAL
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch --kernel accreg > gpurun_out/r2_bench_accreg.json 2> gpurun_out/r2_bench_accreg.err
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch --kernel hot > gpurun_out/r2_bench_hot.json 2> gpurun_out/r2_bench_hot.err
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch --no-uniform --stream-priority > gpurun_out/r2_bench_priority.json 2> gpurun_out/r2_bench_priority.err
 # 4. DRAM traffic of the row pass on the uniform stream, default vs accreg (one ncu pass each, row-pass kernel only)
 for k in auto accreg; do
