@@ -23,5 +23,11 @@ for k in auto accreg; do
       --log-file gpurun_out/r2_ncu_rows_${k}.csv python tools/prof_glove.py --V 1000000 --D 128 --B 262144 --uniform --steps 1 \
       --variant $([ $k = accreg ] && echo 3 || echo 0) > gpurun_out/r2_ncu_rows_${k}.log 2>&1
 done
+# 5. the Zipf stream (the headline): default vs hot-row cache, one ncu pass each (L1/shared pipe, L2 reads, duration)
+for v in 0 4; do
+  timeout 300 ncu --set full --clock-control none -k regex:k_glove_rows_grp_async -c 2 --csv --page raw \
+      --log-file gpurun_out/r2_ncu_rows_zipf_v${v}.csv python tools/prof_glove.py --V 1000000 --D 128 --B 262144 --steps 1 \
+      --variant $v > gpurun_out/r2_ncu_rows_zipf_v${v}.log 2>&1
+done
 tail -3 gpurun_out/r2_accreg_tests.log gpurun_out/r2_ref_golden.log gpurun_out/r2_virtual_peers.log
 cat gpurun_out/r2_probe_accreg.json | head -c 1500
