@@ -191,8 +191,8 @@ def test_sass_of_the_hot_kernels():
     import shutil
     import subprocess
     import sys
-    if shutil.which("cuobjdump") is None:
-        pytest.skip("cuobjdump not on PATH")
+    if shutil.which("cuobjdump") is None or shutil.which("c++filt") is None:
+        pytest.skip("cuobjdump / c++filt not on PATH")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_evidence.py")], capture_output=True, text=True,
                          check=True).stdout
     rows = {}
