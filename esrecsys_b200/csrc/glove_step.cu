@@ -72,7 +72,10 @@ int group_lanes(int D4) {
   return g;
 }
 
-constexpr int kHotRows = 16;       // HOT variant of the row pass: table rows 0..15 cached in shared memory per CTA
+// HOT variants of the row pass: bytes of shared memory per CTA spent on the cache of the table's first rows (8 KB is
+// what 2 CTAs per SM leave free at D = 128 and D = 256); ACCREG + HOT adds the accumulator buffers it no longer needs.
+constexpr int kHotBytes = 8192;
+constexpr int kHotRows = 16, kHotRowsAccReg = 48;  // template tags (rows at D = 128); the row count is a launch argument
 constexpr int kMinAutoChunk = 16;
 constexpr int kHeavyParts = 32;   // straddling segments with more partials than this are combined by several blocks
 constexpr int kHeavySplit = 8;    // blocks per heavy segment
@@ -315,8 +318,9 @@ struct RowsArgs {
   int32_t chunk;
   int32_t per_pair;
   int32_t emit;
-  const uint8_t* ver;  // HOT variant only: buffer of each row (NULL: rows[0])
-  int32_t hot_rows;    // HOT variant only: min(HOT, V)
+  const uint8_t* ver;  // HOT variants only: buffer of each row (NULL: rows[0])
+  int64_t V;           // HOT variants only: table rows
+  int32_t hot_rows;    // HOT variants only: rows cached per CTA (set by the launcher from its shared-memory budget)
   float c2B;      // -2 / B_global
   float inv_B;    // 1 / B_global
   float lr, eps;
@@ -767,7 +771,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ float red[32 * 2];
   constexpr int GP = 32 / G;  // chunks per warp
-  constexpr int NB = 5;       // row buffers per group: P0 P1 P2 S A
+  // row buffers per group: P0 P1 P2 S A; the combined ACCREG + HOT variant drops A (the accumulator row travels through
+  // registers) and spends the 16 KB on a larger hot-row cache
+  constexpr int NB = (ACCREG && HOT > 0) ? 4 : 5;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, grp = lane / G;
   const int gidx = (threadIdx.x >> 5) * GP + grp;
@@ -1570,7 +1576,8 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.per_pair = cfg->bias_mode == ESR_BIAS_PER_PAIR;
   a.emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
   a.ver = t->ver;
-  a.hot_rows = (int32_t)std::min<int64_t>(kHotRows, t->V);
+  a.V = t->V;
+  a.hot_rows = 0;
   a.c2B = -2.f / (float)cfg->B_global;
   a.inv_B = 1.f / (float)cfg->B_global;
   a.lr = cfg->lr;
@@ -1609,7 +1616,7 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
                            bool use_async = false, int grid_override = 0, bool fifo = false, bool accreg = false,
-                           bool hotc = false) {
+                           bool hotc = false, bool hot_accreg = false) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
   if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
@@ -1624,14 +1631,29 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_fifo<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
+  } else if ((phases & 1) && use_async && hot_accreg && a.D4 == G * NV) {
+    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
+    const size_t RB = (size_t)a.D4 * 16;
+    RowsArgs b = a;
+    b.hot_rows = (int32_t)std::min<int64_t>((int64_t)((kHotBytes + (size_t)kWarps * GP * RB) / RB), a.V);
+    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 4 * RB) + (size_t)b.hot_rows * RB;
+    static SmemOptIn configured_hot_accreg;  // per <G, NV> instantiation
+    if (smem > 48 * 1024 && configured_hot_accreg.raise(smem))
+      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, true, kHotRowsAccReg>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_glove_rows_grp_async<G, NV, 2, true, true, kHotRowsAccReg><<<row_blocks, kThreads, smem, stream>>>(b);
+    ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async && hotc && a.D4 == G * NV) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
-    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16) + (size_t)kHotRows * a.D4 * 16;
+    const size_t RB = (size_t)a.D4 * 16;
+    RowsArgs b = a;
+    b.hot_rows = (int32_t)std::min<int64_t>((int64_t)(kHotBytes / RB), a.V);
+    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * RB) + (size_t)b.hot_rows * RB;
     static SmemOptIn configured_hot;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && configured_hot.raise(smem))
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows><<<row_blocks, kThreads, smem, stream>>>(a);
+    k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows><<<row_blocks, kThreads, smem, stream>>>(b);
     ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
@@ -1715,10 +1737,11 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     const bool ff = cfg->reserved == 2;  // reserved == 2: bulk-copy FIFO staging (A/B probe)
     const bool ar = cfg->reserved == 3;  // reserved == 3: accumulator rows via ld.global.cs registers (experimental)
     const bool hc = cfg->reserved == 4;  // reserved == 4: hot rows cached in shared memory (experimental)
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar, hc);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar, hc);
+    const bool ha = cfg->reserved == 5;  // reserved == 5: 3 + 4 combined, larger cache in the accumulator buffer's place
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar, hc, ha);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
   }
   switch (nk) {
     case 1:

@@ -184,13 +184,15 @@ class GloveStep:
             impl, variant = "auto", 3
         if impl == "hot":           # experimental: the table's first 16 rows (frequency ranks) cached in shared memory per CTA
             impl, variant = "auto", 4
+        if impl == "hot_accreg":    # experimental: both; the accumulator buffers' shared memory goes to a 3x larger cache
+            impl, variant = "auto", 5
         cfg.impl = impl if isinstance(impl, int) else {"auto": L.IMPL_AUTO, "ldg": L.IMPL_LDG, "tma": L.IMPL_TMA}[impl]
         cfg.B = self.B
         cfg.B_global = int(B_global if B_global is not None else B)
         cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
         cfg.chunk = chunk
         cfg.row_blocks = int(row_blocks)
-        cfg.reserved = int(variant)     # row-pass staging A/B: 0 cp.async (default), 1 registers, 2 bulk-copy FIFO, 3 cp.async + acc rows via ld.cs, 4 cp.async + hot rows in smem
+        cfg.reserved = int(variant)     # row-pass staging A/B: 0 cp.async (default), 1 registers, 2 bulk-copy FIFO, 3 cp.async + acc rows via ld.cs, 4 cp.async + hot rows in smem, 5 = 3 + 4
         self.cfg = cfg
         self.emit = bool(emit_grads)
         self.ws_bytes = int(L.lib().esr_glove_workspace_bytes(self.B, table.D, chunk))

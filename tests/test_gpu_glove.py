@@ -21,7 +21,7 @@ RTOL = 1e-5
 ATOL = 1e-5
 # Row-pass variants under test.  Experimental variants that have not yet run on a GPU (written when the round's GPU
 # budget was spent) join the parity matrix with ESR_TEST_EXPERIMENTAL=1; they are never the default.
-IMPLS = ["auto", "ldg", "tma", "fifo"] + (["accreg", "hot"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else [])
+IMPLS = ["auto", "ldg", "tma", "fifo"] + (["accreg", "hot", "hot_accreg"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else [])
 
 
 def _engine():
@@ -271,7 +271,7 @@ def test_sparse_adagrad_and_scatter_rows():
 
 @pytest.mark.skipif(not os.environ.get("ESR_TEST_EXPERIMENTAL"), reason="experimental row-pass variant (ESR_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("V,D,B,uniform", [(20000, 128, 8192, False), (50000, 256, 4096, True), (300, 128, 2048, False)])
-@pytest.mark.parametrize("variant", ["accreg", "hot"])
+@pytest.mark.parametrize("variant", ["accreg", "hot", "hot_accreg"])
 def test_accreg_variant_bit_identical_to_default(V, D, B, uniform, variant):
     """The ld.global.cs accumulator staging / the shared-memory cache of the hottest rows change where a row travels,
     not the arithmetic."""

@@ -10,7 +10,7 @@ timeout 200 python -m pytest tests/test_ref_golden.py -q -m gpu > gpurun_out/r2_
 # 1b. N virtual ranks on this one GPU: the peer path's integer kernels vs oracle/index.py, the sharded step vs the oracle
 timeout 400 python -m pytest tests/test_gpu_virtual_peers.py -q > gpurun_out/r2_virtual_peers.log 2>&1
 # 2. row-pass A/B, default vs accreg (Zipf + uniform, checksums must match)
-timeout 150 python tools/probe_l2_hints.py --variants 0,3,4 --out gpurun_out/r2_probe_accreg.json > gpurun_out/r2_probe_accreg.log 2>&1
+timeout 150 python tools/probe_l2_hints.py --variants 0,3,4,5 --out gpurun_out/r2_probe_accreg.json > gpurun_out/r2_probe_accreg.log 2>&1
 # 3. bench lines, default and accreg (no CPU leg, no in-batch leg: short)
 unset ESR_TEST_EXPERIMENTAL
 timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --no-inbatch > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
