@@ -274,6 +274,8 @@ def run_sharded(a, rank, world, local):
     kw = {}
     if a.exchange == "peer" and (a.fast_sync or a.step_graphs or a.overlap_ids):   # experimental switches of the peer path (off by default)
         kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs, "overlap_ids": a.overlap_ids}
+    if a.exchange == "peer" and a.kernel != "auto":                   # row-pass variant on the compact table (EMIT mode)
+        kw["impl"] = a.kernel
     tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr, **kw)
     tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
     ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)

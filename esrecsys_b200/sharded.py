@@ -241,7 +241,7 @@ class PeerShardedGloveTrainer:
     LAUNCHES_PER_STEP = 25
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
-                 graphs=False, fast_sync=False, overlap_ids=False):
+                 graphs=False, fast_sync=False, overlap_ids=False, impl="auto"):
         import torch.distributed._symmetric_memory as symm_mem
         L.require_cuda()
         self.group = group if group is not None else dist.group.WORLD
@@ -299,7 +299,7 @@ class PeerShardedGloveTrainer:
         # full persistent grid: leaving CTA slots free (as the single-GPU trainer does for its plan stream) measured
         # 2 % slower here -- the id kernels of this path are short and run between the phases anyway
         self.step_fn = GloveStep(self.compact, self.B, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
-                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db)
+                                 B_global=self.B * self.n, dE=self.inbox_dE, db=self.inbox_db, impl=impl)
         cfg = self.step_fn.cfg
         cfg.emit_map = L.ptr(self.emit_map)
         cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
