@@ -31,3 +31,4 @@ for v in 0 4; do
 done
 tail -3 gpurun_out/r2_accreg_tests.log gpurun_out/r2_ref_golden.log gpurun_out/r2_virtual_peers.log
 cat gpurun_out/r2_probe_accreg.json | head -c 1500
+python tools/r2_digest.py gpurun_out

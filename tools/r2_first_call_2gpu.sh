@@ -19,3 +19,4 @@ for f in gpurun_out/r2_bench_${N}gpu_*.json; do echo $f; head -c 400 $f; echo; d
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 \
     tools/table_sweep.py --steps 30 --warmup 5 > gpurun_out/r2_table_sweep_${N}gpu.json 2> gpurun_out/r2_table_sweep_${N}gpu.err
 head -c 1200 gpurun_out/r2_table_sweep_${N}gpu.json; tail -3 gpurun_out/r2_table_sweep_${N}gpu.err
+python tools/r2_digest.py gpurun_out
