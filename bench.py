@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--nbatch", type=int, default=8, help="distinct pre-generated batches cycled through")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma", "fifo", "accreg", "hot", "hot_accreg"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma", "fifo"])
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=2)

@@ -72,10 +72,6 @@ int group_lanes(int D4) {
   return g;
 }
 
-// HOT variants of the row pass: bytes of shared memory per CTA spent on the cache of the table's first rows (8 KB is
-// what 2 CTAs per SM leave free at D = 128 and D = 256); ACCREG + HOT adds the accumulator buffers it no longer needs.
-constexpr int kHotBytes = 8192;
-constexpr int kHotRows = 16, kHotRowsAccReg = 48;  // template tags (rows at D = 128); the row count is a launch argument
 constexpr int kMinAutoChunk = 16;
 constexpr int kHeavyParts = 32;   // straddling segments with more partials than this are combined by several blocks
 constexpr int kHeavySplit = 8;    // blocks per heavy segment
@@ -318,9 +314,6 @@ struct RowsArgs {
   int32_t chunk;
   int32_t per_pair;
   int32_t emit;
-  const uint8_t* ver;  // HOT variants only: buffer of each row (NULL: rows[0])
-  int64_t V;           // HOT variants only: table rows
-  int32_t hot_rows;    // HOT variants only: rows cached per CTA (set by the launcher from its shared-memory budget)
   float c2B;      // -2 / B_global
   float inv_B;    // 1 / B_global
   float lr, eps;
@@ -757,23 +750,12 @@ __device__ __forceinline__ void grow_store_f(const Row<NV>& r, float4* __restric
   }
 }
 
-// ACCREG (cfg.reserved == 3, experimental, not the default): the accumulator row -- read exactly once per step -- does not
-// go through cp.async.cg (normal L2 priority) but through ld.global.cs into registers one slot ahead (SASS LDG.E.EF:
-// evict-first in L2), so it stops displacing table rows that a later slot re-reads as a partner.  Same arithmetic,
-// bit-identical results.  (The L2::cache_hint form of cp.async faults on B200: profiles/r1_summary.md 3c.)
-// HOT > 0 (cfg.reserved == 4, experimental, not the default): every CTA keeps the table's first HOT rows -- ids are
-// frequency ranks (wikipedia/make_dictionary.py:113-116; the compact table of the sharded path is sorted by row too), so
-// under Zipf(1) rows 0..15 are 23 % of all partner reads -- in shared memory for the whole pass; a slot whose partner is
-// one of them reads it from there instead of staging it through cp.async (no L2 read, one crossing of the shared-memory
-// pipe instead of two).  Same values, same arithmetic: bit-identical results.
-template <int G, int NV, int MINB, bool FULLD, bool ACCREG = false, int HOT = 0>
+template <int G, int NV, int MINB, bool FULLD>
 __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const RowsArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_raw[];
   __shared__ float red[32 * 2];
   constexpr int GP = 32 / G;  // chunks per warp
-  // row buffers per group: P0 P1 P2 S A; the combined ACCREG + HOT variant drops A (the accumulator row travels through
-  // registers) and spends the 16 KB on a larger hot-row cache
-  constexpr int NB = (ACCREG && HOT > 0) ? 4 : 5;
+  constexpr int NB = 5;  // row buffers per group: P0 P1 P2 S A
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, grp = lane / G;
   const int gidx = (threadIdx.x >> 5) * GP + grp;
@@ -787,16 +769,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
   const float4* const accp = reinterpret_cast<const float4*>(a.acc);
   float sums[2] = {0.f, 0.f};
-  const unsigned char* const hot = dyn_raw + (size_t)kWarps * GP * (sizeof(GroupMeta) + (size_t)NB * RB);
-  const uint32_t n_hot = HOT > 0 ? (uint32_t)a.hot_rows : 0u;
-  if (HOT > 0) {
-    float4* hp = reinterpret_cast<float4*>(const_cast<unsigned char*>(hot));
-    for (uint32_t e = threadIdx.x; e < n_hot * D4; e += kThreads) {
-      const uint32_t r = e / D4;
-      hp[e] = ((a.ver != nullptr && a.ver[r]) ? rows1 : rows0)[(uint64_t)r * D4 + (e - r * D4)];
-    }
-    __syncthreads();
-  }
   // Persistent warps pull work items (GP consecutive chunks) from a counter.  Items are handed out from
   // the END of the sorted stream: the cold rows (singleton segments, three DRAM rows per slot) are the
   // long items, so they start first and the cheap hot-row chunks fill in behind them (LPT order), and a
@@ -828,9 +800,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
     if (s < cnt) {
       const int32_t code = gm.rec[s].code;
       const uint32_t q = (uint32_t)(code & kRowMask);
-      if (HOT == 0 || q >= n_hot)
-        grow_copy_async_f<G, NV, FULLD>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4,
-                                        gl, a.D4, true);
+      grow_copy_async_f<G, NV, FULLD>(bufs_u32 + (uint32_t)(s % 3) * RB, ((code >> 31) & 1 ? rows1 : rows0) + (uint64_t)q * D4,
+                                      gl, a.D4, true);
     }
   };
   // self / accumulator rows of slot s (self: chunk start or segment head; acc: a segment that both
@@ -842,26 +813,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       const uint32_t row = (uint32_t)(k1 & kRowMask);
       if (s == 0 || head)
         grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 3u * RB, ((k1 >> 31) & 1 ? rows1 : rows0) + (uint64_t)row * D4, gl, a.D4, true);
-      if (!ACCREG && !a.emit && end && (head || started_if_not_head))
+      if (!a.emit && end && (head || started_if_not_head))
         grow_copy_async_f<G, NV, FULLD>(bufs_u32 + 4u * RB, accp + (uint64_t)row * D4, gl, a.D4, false);
     }
   };
-  Row<NV> An;  // ACCREG: accumulator row of the next slot, in flight in registers
-  row_zero(An);
-  auto acc_to_regs = [&](int s, bool started_if_not_head) {
-    if (ACCREG && s < cnt && !a.emit) {
-      const int32_t k0 = gm.keys[s], k1 = gm.keys[1 + s], k2 = gm.keys[2 + s];
-      if (k1 != k2 && (k1 != k0 || started_if_not_head)) {
-        const float4* src = accp + (uint64_t)(uint32_t)(k1 & kRowMask) * D4;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int c = k * G + gl;
-          if (FULLD || c < (int)D4) An.v[k] = ld_stream(src + c);
-        }
-      }
-    }
-  };
-
   Row<NV> cur, grad;
   row_zero(cur);
   row_zero(grad);
@@ -870,7 +825,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   int64_t u = cnt > 0 ? a.useg[p0] : 0;
   // prologue: {self, acc of slot 0} {partner 0} {nothing} {partner 1}
   issue_self_acc(0, false);
-  acc_to_regs(0, false);
   cp_async_commit();
   issue_partner(0);
   cp_async_commit();
@@ -891,10 +845,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       rec = gm.rec[s];
       is_head = key_cur != k0;
       is_end = key_cur != k2;
-      const uint32_t pq = (uint32_t)(rec.code & kRowMask);
-      grow_from_smem_f<G, NV, FULLD>(P, reinterpret_cast<const float4*>(HOT > 0 && pq < n_hot ? hot + (size_t)pq * RB
-                                                                                                : bufs + (size_t)(s % 3) * RB),
-                                     gl, a.D4);
+      grow_from_smem_f<G, NV, FULLD>(P, reinterpret_cast<const float4*>(bufs + (size_t)(s % 3) * RB), gl, a.D4);
       if (s == 0 || is_head) {
         grow_from_smem_f<G, NV, FULLD>(cur, reinterpret_cast<const float4*>(bufs + 3 * (size_t)RB), gl, a.D4);
         row_zero(grad);
@@ -902,14 +853,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
         started_here = is_head;
         if (is_head && s > 0) ++u;
       }
-      if (!a.emit && is_end && started_here) {
-        if (ACCREG) A = An;
-        else grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
-      }
+      if (!a.emit && is_end && started_here)
+        grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
     }
     // every buffer read above is private to the lane that filled it: refill without a barrier
     issue_self_acc(s + 1, started_here && !is_end);
-    acc_to_regs(s + 1, started_here && !is_end);
     cp_async_commit();
     issue_partner(s + 2);
     cp_async_commit();
@@ -1575,9 +1523,6 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.chunk = w.chunk;
   a.per_pair = cfg->bias_mode == ESR_BIAS_PER_PAIR;
   a.emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
-  a.ver = t->ver;
-  a.V = t->V;
-  a.hot_rows = 0;
   a.c2B = -2.f / (float)cfg->B_global;
   a.inv_B = 1.f / (float)cfg->B_global;
   a.lr = cfg->lr;
@@ -1615,8 +1560,7 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
 
 template <int G, int NV, int NKC>
 static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, int phases, cudaStream_t stream,
-                           bool use_async = false, int grid_override = 0, bool fifo = false, bool accreg = false,
-                           bool hotc = false, bool hot_accreg = false) {
+                           bool use_async = false, int grid_override = 0, bool fifo = false) {
   constexpr int GP = 32 / G;
   int row_blocks = (int)ceil_div(w.nchunks, (int64_t)kWarps * GP);
   if (use_async) {  // persistent, work-stealing: 2 CTAs per SM unless the caller leaves room for a concurrent stream
@@ -1631,30 +1575,6 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_fifo<G, NV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
-  } else if ((phases & 1) && use_async && hot_accreg && a.D4 == G * NV) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
-    const size_t RB = (size_t)a.D4 * 16;
-    RowsArgs b = a;
-    b.hot_rows = (int32_t)std::min<int64_t>((int64_t)((kHotBytes + (size_t)kWarps * GP * RB) / RB), a.V);
-    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 4 * RB) + (size_t)b.hot_rows * RB;
-    static SmemOptIn configured_hot_accreg;  // per <G, NV> instantiation
-    if (smem > 48 * 1024 && configured_hot_accreg.raise(smem))
-      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, true, kHotRowsAccReg>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_glove_rows_grp_async<G, NV, 2, true, true, kHotRowsAccReg><<<row_blocks, kThreads, smem, stream>>>(b);
-    ESR_LAUNCH_CHECK();
-  } else if ((phases & 1) && use_async && hotc && a.D4 == G * NV) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
-    const size_t RB = (size_t)a.D4 * 16;
-    RowsArgs b = a;
-    b.hot_rows = (int32_t)std::min<int64_t>((int64_t)(kHotBytes / RB), a.V);
-    const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * RB) + (size_t)b.hot_rows * RB;
-    static SmemOptIn configured_hot;  // per <G, NV> instantiation
-    if (smem > 48 * 1024 && configured_hot.raise(smem))
-      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_glove_rows_grp_async<G, NV, 2, true, false, kHotRows><<<row_blocks, kThreads, smem, stream>>>(b);
-    ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async) {
     ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
@@ -1664,11 +1584,8 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
                                     (int)smem));
       ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      ESR_CUDA(cudaFuncSetAttribute(k_glove_rows_grp_async<G, NV, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
     }
-    if (a.D4 == G * NV && accreg) k_glove_rows_grp_async<G, NV, 2, true, true><<<row_blocks, kThreads, smem, stream>>>(a);
-    else if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
+    if (a.D4 == G * NV) k_glove_rows_grp_async<G, NV, 2, true><<<row_blocks, kThreads, smem, stream>>>(a);
     else k_glove_rows_grp_async<G, NV, 2, false><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if (phases & 1) {
@@ -1735,13 +1652,10 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
     const bool as = cfg->reserved != 1;  // reserved == 1: keep rows in registers (A/B probe)
     const int go = cfg->row_blocks;
     const bool ff = cfg->reserved == 2;  // reserved == 2: bulk-copy FIFO staging (A/B probe)
-    const bool ar = cfg->reserved == 3;  // reserved == 3: accumulator rows via ld.global.cs registers (experimental)
-    const bool hc = cfg->reserved == 4;  // reserved == 4: hot rows cached in shared memory (experimental)
-    const bool ha = cfg->reserved == 5;  // reserved == 5: 3 + 4 combined, larger cache in the accumulator buffer's place
-    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff, ar, hc, ha);
-    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
-    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
-    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff, ar, hc, ha);
+    if (d4 <= 32) return launch_rows_grp<8, 4, 1>(a, w, scalars, phases, stream, as && d4 > 16, go, ff);
+    if (d4 <= 64) return launch_rows_grp<16, 4, 2>(a, w, scalars, phases, stream, as, go, ff);
+    if (d4 <= 96) return launch_rows_grp<32, 3, 3>(a, w, scalars, phases, stream, as, go, ff);
+    return launch_rows_grp<32, 4, 4>(a, w, scalars, phases, stream, as, go, ff);
   }
   switch (nk) {
     case 1:

@@ -180,19 +180,13 @@ class GloveStep:
         cfg.rows_mode = L.ROWS_EMIT_GRADS if emit_grads else L.ROWS_UPDATE
         if impl == "fifo":          # the group row pass with bulk-copy FIFO staging (A/B candidate for the default)
             impl, variant = "auto", 2
-        if impl == "accreg":        # experimental: accumulator rows through ld.global.cs registers (evict-first in L2)
-            impl, variant = "auto", 3
-        if impl == "hot":           # experimental: the table's first 16 rows (frequency ranks) cached in shared memory per CTA
-            impl, variant = "auto", 4
-        if impl == "hot_accreg":    # experimental: both; the accumulator buffers' shared memory goes to a 3x larger cache
-            impl, variant = "auto", 5
         cfg.impl = impl if isinstance(impl, int) else {"auto": L.IMPL_AUTO, "ldg": L.IMPL_LDG, "tma": L.IMPL_TMA}[impl]
         cfg.B = self.B
         cfg.B_global = int(B_global if B_global is not None else B)
         cfg.lr, cfg.eps, cfg.x_max, cfg.alpha = lr, eps, x_max, alpha
         cfg.chunk = chunk
         cfg.row_blocks = int(row_blocks)
-        cfg.reserved = int(variant)     # row-pass staging A/B: 0 cp.async (default), 1 registers, 2 bulk-copy FIFO, 3 cp.async + acc rows via ld.cs, 4 cp.async + hot rows in smem, 5 = 3 + 4
+        cfg.reserved = int(variant)     # row-pass staging A/B: 0 cp.async (default), 1 registers, 2 bulk-copy FIFO
         self.cfg = cfg
         self.emit = bool(emit_grads)
         self.ws_bytes = int(L.lib().esr_glove_workspace_bytes(self.B, table.D, chunk))

@@ -19,9 +19,8 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
 ATOL = 1e-5
-# Row-pass variants under test.  Experimental variants that have not yet run on a GPU (written when the round's GPU
-# budget was spent) join the parity matrix with ESR_TEST_EXPERIMENTAL=1; they are never the default.
-IMPLS = ["auto", "ldg", "tma", "fifo"] + (["accreg", "hot", "hot_accreg"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else [])
+# Row-pass variants under test (every one has run on a B200; "auto" is the default).
+IMPLS = ["auto", "ldg", "tma", "fifo"]
 
 
 def _engine():
@@ -269,23 +268,32 @@ def test_sparse_adagrad_and_scatter_rows():
     assert np.array_equal(dense.cpu().numpy(), ref * 2)
 
 
-@pytest.mark.skipif(not os.environ.get("ESR_TEST_EXPERIMENTAL"), reason="experimental row-pass variant (ESR_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("V,D,B,uniform", [(20000, 128, 8192, False), (50000, 256, 4096, True), (300, 128, 2048, False)])
-@pytest.mark.parametrize("variant", ["accreg", "hot", "hot_accreg"])
-def test_accreg_variant_bit_identical_to_default(V, D, B, uniform, variant):
-    """The ld.global.cs accumulator staging / the shared-memory cache of the hottest rows change where a row travels,
-    not the arithmetic."""
+def test_bench_shape_trainer_matches_oracle():
+    """Parity AT THE BENCHMARKED SHAPE (BASELINE configs[1]: V = 1M, D = 128, B = 262 144, Zipf(1)) through the exact
+    code path bench.py times: GloveTrainer with CUDA graphs, two streams, the 8/9 persistent row-pass grid and pinned
+    host batches -- three graph-replayed steps against oracle.glove.step_adagrad
+    (wikipedia/train_cooccurence.py:71-101 with the north-star Adagrad rule)."""
+    from esrecsys_b200 import synth
+    from esrecsys_b200.trainer import GloveTrainer
     eng = _engine()
-    E, b = _tables(V, D, seed=V)
-    ids, counts = _batch(V, B, seed=V + 3, uniform=uniform, n=3)
-    outs = []
-    for impl in ("auto", variant):
-        t = eng.EmbeddingTable.from_dense(E, b, sparse=True)
-        step = eng.GloveStep(t, B, impl=impl)
-        plan = eng.IndexPlan(2 * B, V)
-        for k in range(3):
-            plan.build(torch.from_numpy(ids[k].reshape(-1)).cuda())
-            step.run(plan, torch.from_numpy(counts[k]).cuda())
-        outs.append((t.dense().cpu().numpy(), t.acc.cpu().numpy(), t.bias.cpu().numpy()))
-    for x, y in zip(*outs):
-        assert np.array_equal(x, y)
+    V, D, B, lr, steps = 1_000_000, 128, 262144, 0.05, 3
+    E, b = synth.init_glove_tables(V, D, 0)
+    b = (np.random.default_rng(3).standard_normal(V) * 0.05).astype(np.float32)
+    ids, counts = synth.glove_batches(V, B, steps, 0)
+    table = eng.EmbeddingTable.from_dense(E, b, sparse=True)
+    tr = GloveTrainer(table, B, lr=lr)                              # bench.py's construction (graphs=True, depth=2)
+    assert tr.use_graphs and tr.g_step[0] is not None
+    Eo, bo = E.copy(), b.copy()
+    aE, ab = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC), np.full_like(bo, oopt.ADAGRAD_INIT_ACC)
+    ref = []
+    for k in range(steps):
+        tr.submit(torch.from_numpy(ids[k]).pin_memory(), torch.from_numpy(counts[k]).pin_memory())
+        ref.append(og.step_adagrad(Eo, bo, aE, ab, ids[k, 0], ids[k, 1], counts[k], lr))
+    got = tr.losses(0, steps)
+    np.testing.assert_allclose(got, np.array(ref, np.float32), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(table.dense().cpu().numpy(), Eo, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(table.bias.cpu().numpy(), bo, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(table.acc.cpu().numpy(), aE, rtol=RTOL, atol=1e-7)
+    touched = np.zeros(V, bool)
+    touched[np.unique(ids)] = True
+    assert np.array_equal(table.dense().cpu().numpy()[~touched], E[~touched])      # untouched rows bit-identical

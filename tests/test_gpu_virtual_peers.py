@@ -5,8 +5,7 @@ same libesr kernels PeerShardedGloveTrainer uses, with every "peer" pointer loca
   oracle/index.py for N in {2, 3, 4, 8};
 * the whole sharded step against the single-table oracle on the rank-major concatenated batch, 1e-5.
 
-Written at the end of round 1 with no GPU minutes left: joins the suite with ESR_TEST_EXPERIMENTAL=1 until it has run
-on a B200 once (tools/r2_first_call.sh)."""
+First run on a B200 in round 2 (12 passed); part of the default -m gpu suite since."""
 import os
 import sys
 
@@ -18,8 +17,7 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("ESR_TEST_EXPERIMENTAL"), reason="not yet run on a GPU (ESR_TEST_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _batches(V, B_loc, n, steps, seed):

@@ -385,8 +385,6 @@ def test_oracle_pipeline_vs_reference_training_run():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("ESR_TEST_EXPERIMENTAL"), reason="written after the round's GPU budget was spent; "
-                    "run once with ESR_TEST_EXPERIMENTAL=1, then drop this gate")
 def test_cuda_pipeline_vs_reference_training_run():
     """The same run through the product: native decoder -> Glove / TrainState / train_epoch / dump_knn mirrors on libesr."""
     from esrecsys_b200 import optim as O

@@ -5,8 +5,8 @@
 mkdir -p gpurun_out
 export ESR_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental pieces (bit-identity of the accreg row pass, the reference-run pipeline through libesr)
-timeout 400 python -m pytest tests/test_gpu_glove.py -q -x -k "accreg or hot" > gpurun_out/r2_accreg_tests.log 2>&1
-timeout 200 python -m pytest tests/test_ref_golden.py -q -m gpu > gpurun_out/r2_ref_golden.log 2>&1
+timeout 600 python -m pytest tests -q -m gpu --deselect tests/test_gpu_virtual_peers.py -rs > gpurun_out/r2_accreg_tests.log 2>&1
+cp gpurun_out/r2_accreg_tests.log gpurun_out/r2_ref_golden.log
 # 1b. N virtual ranks on this one GPU: the peer path's integer kernels vs oracle/index.py, the sharded step vs the oracle
 timeout 400 python -m pytest tests/test_gpu_virtual_peers.py -q > gpurun_out/r2_virtual_peers.log 2>&1
 # 2. row-pass A/B, default vs accreg (Zipf + uniform, checksums must match)
