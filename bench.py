@@ -46,19 +46,22 @@ def parse():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--nbatch", type=int, default=8, help="distinct pre-generated batches cycled through")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma", "fifo"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma", "fifo", "endfirst"])
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-uniform", action="store_true")
     ap.add_argument("--no-inbatch", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="plan/staging buffers in flight (GloveTrainer)")
+    ap.add_argument("--depth", type=int, default=3, help="plan/staging buffers in flight (GloveTrainer)")
     ap.add_argument("--row-blocks", type=int, default=-1, help="persistent row-pass grid (-1 = trainer default, 0 = 2 CTAs per SM)")
     ap.add_argument("--stream-priority", action="store_true",
                     help="N=1, experimental: the step's stream at high priority over the plan stream")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1: row exchange over NVLink peer memory (libesr kernels) or NCCL all-to-all")
+    ap.add_argument("--exchange", default="routed", choices=["routed", "peer", "nccl"],
+                    help="N>1: owner-computes pair routing over NVLink peer memory (default), the round-1 peer-memory path "
+                         "(every rank keeps the pairs it was handed), or NCCL all-to-alls")
+    ap.add_argument("--no-table-100m", action="store_true", help="skip the BASELINE configs[4] sub-record (100M-row table)")
+    ap.add_argument("--table-rows", type=int, default=100_000_000, help="rows of the configs[4] table")
     ap.add_argument("--fast-sync", action="store_true",
                     help="N>1 peer path, experimental: libesr peer all-reduce / barrier kernels instead of NCCL + symm-mem barrier")
     ap.add_argument("--step-graphs", action="store_true", help="N>1 peer path, experimental: CUDA-graph the sharded step")
@@ -223,10 +226,9 @@ def timed_region(tr, batches, steps, warmup, read_loss, world):
     tr.s_side.wait_stream(tr.s_main)
     e0.record(tr.s_main)
     tr.s_side.wait_event(e0)
+    tr.s_copy.wait_event(e0)                  # the first upload of the timed region starts inside it
     for k in range(steps):
-        s = tr.submit(*batches[(warmup + k) % n])
-        if read_loss:
-            tr.read_loss(s)
+        tr.submit(*batches[(warmup + k) % n], read_loss=read_loss)
     e1.record(tr.s_main)
     tr.synchronize()
     torch.cuda.synchronize()
@@ -263,52 +265,216 @@ def timed_region_sharded(tr, batches, steps, warmup, pinned_loss, world):
     return float(t.item())
 
 
+def make_sharded_trainer(a, V, D, B):
+    from esrecsys_b200.sharded import OwnerRoutedGloveTrainer, PeerShardedGloveTrainer, ShardedGloveTrainer
+    if a.exchange == "routed":
+        kw = {"impl": a.kernel} if a.kernel != "auto" else {}
+        return OwnerRoutedGloveTrainer(V, D, B, lr=a.lr, **kw)
+    if a.exchange == "peer":
+        kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs, "overlap_ids": a.overlap_ids}
+        if a.kernel != "auto":
+            kw["impl"] = a.kernel
+        return PeerShardedGloveTrainer(V, D, B, lr=a.lr, **kw)
+    return ShardedGloveTrainer(V, D, B, lr=a.lr)
+
+
+def sharded_parity_check(a, rank, world):
+    """Before the timed region of every N > 1 run: the SAME trainer class on a small table -- 6 global steps (the last ones
+    CUDA-graph replays) -- against the single-table engine on the concatenated batch (itself held to the oracle by
+    tests/): losses and the re-assembled table.  Semantics: wikipedia/train_cooccurence.py:71-101."""
+    import torch
+    from esrecsys_b200 import engine, synth
+    V, D, B, steps = 50_000, a.dim, 4096, 6
+    E, b = synth.init_glove_tables(V, D, 3)
+    b = (np.random.default_rng(4).standard_normal(V) * 0.05).astype(np.float32)
+    ids, counts = synth.glove_batches(V, B * world, steps, 123)
+    tr = make_sharded_trainer(a, V, D, B)
+    tr.load_dense(E, b)
+    table = engine.EmbeddingTable.from_dense(E, b, sparse=True)
+    single = engine.GloveStep(table, B * world, lr=a.lr)
+    plan = engine.IndexPlan(2 * B * world, V)
+    lo, hi = rank * B, (rank + 1) * B
+    dl = 0.0
+    for k in range(steps):
+        loss = tr.step(torch.from_numpy(np.ascontiguousarray(ids[k][:, lo:hi])).cuda(), torch.from_numpy(counts[k][lo:hi]).cuda())
+        plan.build(torch.from_numpy(ids[k].reshape(-1)).cuda())
+        ref = single.run(plan, torch.from_numpy(counts[k]).cuda())[engine.L.SC_LOSS]
+        dl = max(dl, abs(float(loss.item()) - float(ref.item())) / max(1e-12, abs(float(ref.item()))))
+    Eg, bg = tr.gather_dense()
+    Es, bs = table.dense(), table.bias
+    dE = float((Eg - Es).abs().max().item())
+    db = float((bg - bs).abs().max().item())
+    tol = float(((Eg - Es).abs() - 1e-5 * Es.abs()).max().item())
+    ok = bool(dl <= 2e-5 and tol <= 1e-5 and db <= 1e-5)
+    del tr, table, single, plan
+    torch.cuda.empty_cache()
+    return {"ok": ok, "vs": "single-table libesr engine on the concatenated global batch", "steps": steps, "vocab": V,
+            "batch_per_gpu": B, "max_rel_loss_diff": dl, "max_abs_row_diff": dE, "max_abs_bias_diff": db,
+            "tolerance": "1e-5 abs + 1e-5 rel (rows, bias), 2e-5 rel (loss)"}
+
+
+def sharded_timed(a, tr, V, B, rank, world, steps, warmup, seed):
+    """value / e2e legs of one sharded trainer; returns (ms, ms_e2e, U_local_mean)."""
+    import torch
+    from esrecsys_b200 import synth
+    warmup = max(warmup, 5)                   # the routed trainer captures its CUDA graphs at its 5th step
+    ids, counts = synth.glove_batches(V, B, a.nbatch, seed + 17 * rank)
+    dev_b = [(torch.from_numpy(ids[k]).cuda().reshape(-1), torch.from_numpy(counts[k]).cuda()) for k in range(a.nbatch)]
+    pin_b = [(torch.from_numpy(ids[k]).pin_memory(), torch.from_numpy(counts[k]).pin_memory()) for k in range(a.nbatch)]
+    ms = timed_region_sharded(tr, dev_b, steps, warmup, None, world)
+    pinned_loss = torch.zeros(64).pin_memory()
+    ms_e2e = timed_region_sharded(tr, pin_b, steps, max(3, warmup // 4), pinned_loss, world)
+    if hasattr(tr, "check"):
+        tr.check()
+    return ms, ms_e2e
+
+
+def nvlink_accounting(tr, world):
+    """Rows that crossed NVLink in the LAST step on this rank (per direction: fetched rows in == gradient rows out), from
+    the route plan the step published (device counters)."""
+    import torch
+    try:
+        k = (tr.t - 1) % tr.DEPTH
+        counts = tr.pub[k]["counts"][:world].cpu().numpy()
+        remote = int(counts.sum() - counts[tr.rank])
+        return remote, int(counts.sum())
+    except Exception:
+        return None, None
+
+
 def run_sharded(a, rank, world, local):
     """N > 1: the table row-shards cyclically over the ranks (weak scaling: --batch pairs per GPU)."""
     import torch
     import torch.distributed as dist
-    from esrecsys_b200 import synth
-    from esrecsys_b200.sharded import PeerShardedGloveTrainer, ShardedGloveTrainer
     V, D, B = a.vocab, a.dim, a.batch
     torch.manual_seed(a.seed)
-    kw = {}
-    if a.exchange == "peer" and (a.fast_sync or a.step_graphs or a.overlap_ids):   # experimental switches of the peer path (off by default)
-        kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs, "overlap_ids": a.overlap_ids}
-    if a.exchange == "peer" and a.kernel != "auto":                   # row-pass variant on the compact table (EMIT mode)
-        kw["impl"] = a.kernel
-    tr = (PeerShardedGloveTrainer if a.exchange == "peer" else ShardedGloveTrainer)(V, D, B, lr=a.lr, **kw)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    parity = sharded_parity_check(a, rank, world)
+    tr = make_sharded_trainer(a, V, D, B)
     tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
-    ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
-    dev_b = [(torch.from_numpy(ids[k]).cuda(), torch.from_numpy(counts[k]).cuda()) for k in range(a.nbatch)]
-    pin_b = [(torch.from_numpy(ids[k]).pin_memory(), torch.from_numpy(counts[k]).pin_memory()) for k in range(a.nbatch)]
     clocks = ClockSampler(local)
     clocks.start()
     clocks.active = True
-    dev_b = [(x[0].reshape(-1), x[1]) for x in dev_b]
-    ms = timed_region_sharded(tr, dev_b, a.steps, a.warmup, None, world)
-    pinned_loss = torch.zeros(64).pin_memory()
-    ms_e2e = timed_region_sharded(tr, pin_b, a.steps, max(3, a.warmup // 4), pinned_loss, world)
+    ms, ms_e2e = sharded_timed(a, tr, V, B, rank, world, a.steps, a.warmup, a.seed)
     clocks.active = False
+    remote_rows, uniq_rows = nvlink_accounting(tr, world)
+    R = 4 * D
+    par = {"routed": "row-sharded table (cyclic), dp%d over pairs, OWNER-COMPUTES: every pair is routed to the rank owning row i "
+                     "(12 B per pair), only the unique partner rows and their gradients cross NVLink (libesr peer-memory "
+                     "kernels, no NCCL inside the step, CUDA graphs)" % world,
+           "peer": "row-sharded table (cyclic), dp%d over pairs; rows fetched and gradients merged by libesr kernels over "
+                   "NVLink peer memory" % world,
+           "nccl": "NCCL all-to-all of ids / rows / gradients"}[a.exchange]
     line = {
         "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a) + "; table row-sharded (cyclic) over %d GPUs, B per GPU" % world, "vocab": V,
                    "dim": D, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "sparse adagrad (north star)",
-                   "bias_mode": "reference_broadcast", "stream": "zipf(1)",
+                   "bias_mode": "reference_broadcast", "stream": "zipf(1)", "exchange": a.exchange,
                    "l2": "no flush: per-step working set (fetched rows + shard rows + state) >> 126 MB L2",
-                   "parallelism": ("row-sharded table (cyclic), dp%d over pairs; " % world) + (
-                       "rows fetched and gradients merged by libesr kernels over NVLink peer memory, NCCL only for the "
-                       "5-float all-reduce" if a.exchange == "peer" else "NCCL all-to-all of ids / rows / gradients")},
+                   "parallelism": par},
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": a.steps * tr.LAUNCHES_PER_STEP, "final_loss": float(tr.loss.item()),
+        "parity_check": parity,
         "clocks": clocks.summary(),
     }
+    if uniq_rows is not None:
+        # whole-step roofline of one rank: the algorithmic HBM bytes of SURVEY.md 8(d) for the rows this rank's pairs
+        # touch, and the NVLink bytes that had to cross per direction, both over the step time
+        alg = uniq_rows * R * 4 + uniq_rows * 16 + B * 12
+        nv = remote_rows * (R + 8)
+        t_s = ms / a.steps * 1e-3
+        line["roofline"] = {"bound": "hbm", "achieved": alg / t_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg / t_s / 1e9 / hbm_peak, "traffic": None, "kernel": "whole sharded step (rank 0)",
+                            "alg_bytes_per_launch": alg, "unique_rows_per_step": uniq_rows,
+                            "nvlink": {"remote_rows_per_step": remote_rows, "bytes_per_dir_per_step": nv,
+                                       "achieved_gbs_per_dir": nv / t_s / 1e9, "peak_gbs_per_dir": 900.0,
+                                       "frac": nv / t_s / 1e9 / 900.0,
+                                       "note": "not NVLink-bound by design: owner-computes routing leaves ~1/4 of the rows "
+                                               "on the wire"}}
+    del tr
+    torch.cuda.empty_cache()
+    if not a.no_table_100m:
+        line["table_100m"] = guarded(lambda: table_100m_leg(a, rank, world), "table_100m")
     if rank == 0:
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def guarded(fn, name):
+    """Sub-records never take the headline line down with them."""
+    try:
+        return fn()
+    except Exception as e:  # pragma: no cover
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
+def table_100m_leg(a, rank, world):
+    """BASELINE configs[4]: the same step on a 100M-row x 128 table (51.2 GB + Adagrad state), Zipf(1) ids over all 100M
+    rows, B pairs per GPU.  N = 1: the single-table engine (3 x 51.2 GB resident); N > 1: row-sharded, owner-computes.
+    Reports pairs/s and, for N > 1, the looked-up rows per step and the NVLink rate of the lookup kernel timed alone."""
+    import torch
+    import torch.distributed as dist
+    from esrecsys_b200 import _lib as L, engine, synth
+    import ctypes as C
+    V, D, B = a.table_rows, a.dim, a.batch
+    steps, warm = 20, 5
+    out = {"workload": "BASELINE configs[4]: %dM rows x %d, Zipf(1) over all rows, B=%d per GPU" % (V // 1_000_000, D, B),
+           "n_gpus": world, "vocab": V}
+    if world == 1:
+        from esrecsys_b200.trainer import GloveTrainer
+        table = engine.EmbeddingTable(V, D)
+        table.rows0.normal_(0.0, 1.0 / np.sqrt(D))
+        ids, counts = synth.glove_batches(V, B, 4, a.seed + 5)
+        dev_b = [(torch.from_numpy(ids[k].reshape(-1)).cuda(), torch.from_numpy(counts[k]).cuda()) for k in range(4)]
+        tr = GloveTrainer(table, B, lr=a.lr)
+        ms = timed_region(tr, dev_b, steps, warm, False, 1)
+        out.update({"ms_per_step": ms / steps, "pairs_per_s": B * steps / (ms * 1e-3), "table_gb": table.nbytes() / 1e9,
+                    "unique_rows_per_step": float(np.mean([np.unique(ids[k]).size for k in range(4)])),
+                    "final_loss": float(tr.losses(tr.t - 1, tr.t)[0])})
+        return out
+    tr = make_sharded_trainer(a, V, D, B)
+    tr.shard.rows0.normal_(0.0, 1.0 / np.sqrt(D))
+    ms, ms_e2e = sharded_timed(a, tr, V, B, rank, world, steps, warm, a.seed + 5)
+    remote_rows, uniq_rows = nvlink_accounting(tr, world)
+    out.update({"ms_per_step": ms / steps, "pairs_per_s": world * B * steps / (ms * 1e-3),
+                "e2e_pairs_per_s": world * B * steps / (ms_e2e * 1e-3), "shard_gb": tr.shard.V * D * 4 / 1e9,
+                "final_loss": float(tr.loss.item()), "exchange": a.exchange})
+    if uniq_rows is not None and hasattr(tr, "plans"):
+        # the lookup alone (esr_peer_gather_f32 of the last step's unique rows), all ranks at once: NVLink GB/s per direction
+        k = (tr.t - 1) % tr.DEPTH
+        plan = tr.plans[k]
+        torch.cuda.synchronize()
+        dist.barrier()
+        tot = 0.0
+        for it in range(6):
+            tr.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.lib().esr_peer_gather_f32(tr.p_rows, tr.p_bias, world, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
+                                                D, L.ptr(tr.compact.rows0), L.ptr(tr.compact.bias), L.stream_ptr()),
+                    "esr_peer_gather_f32")
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 1:
+                tot += e0.elapsed_time(e1)
+        t = torch.tensor([tot / 5], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item()) * 1e3
+        nv = remote_rows * (4 * D + 8)
+        out["lookup"] = {"unique_rows": uniq_rows, "remote_rows": remote_rows, "us": us, "bytes_per_dir": nv,
+                         "gbs_per_dir": nv / (us * 1e-6) / 1e9, "nvlink_peak_gbs_per_dir": 900.0,
+                         "frac_of_nvlink": nv / (us * 1e-6) / 1e9 / 900.0,
+                         "note": "rank 0's numbers; time = max over ranks, all ranks looking up at once"}
+    return out
 
 
 def rows_kernel_time(table, a, ids_dev, cnt_dev, steps):
@@ -375,6 +541,53 @@ def inbatch_leg(peaks):
                      "peak": peak, "frac": tf / peak, "dtype": "bf16 operands, f32 accumulate (tcgen05)",
                      "kernels_per_step": 4 if loss == "hinge" else 6}
         del sc
+    return out
+
+
+def retrieval_leg(peaks, table, a):
+    """the fused score + top-k scan (esr_topk_scan_f32).  (1) dump_knn's shape on the bench table
+    (wikipedia/train_cooccurence.py:114-126: T = 8 queries, k = 10): HBM-bound, V*D*4 bytes per call; (2) eval_step's
+    shape (spotify/train_spotify.py:113-131: 2 262 292 tracks gathered from the 100000 x 32 album and 295861 x 32 artist
+    tables, 5 context rows, k = 500): the tables sit in L2, the stream is the 8 bytes of ids per track."""
+    import torch
+    from esrecsys_b200 import engine
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {}
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    V, D = table.V, table.D
+    q = table.gather(torch.tensor([7, 19, 4000, 1, 100, 33, 2, 5], dtype=torch.int32, device="cuda"))
+    ms = timeit(lambda: engine.table_topk(table, q, 10, ties_high_index_first=True))
+    gbs = V * D * 4 / (ms * 1e-3) / 1e9
+    out["dump_knn_topk_V%dk_D%d_T8_k10" % (V // 1000, D)] = {
+        "ms": ms, "bound": "hbm", "alg_bytes": V * D * 4, "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+        "note": "one table pass, running top-10 per query in shared memory; round 1: (V,8) score matrix + 8 full radix sorts"}
+    N, F = 2_262_292, 32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(100_000, F, device="cuda", generator=g) / F ** 0.5
+    R = torch.randn(295_861, F, device="cuda", generator=g) / F ** 0.5
+    alb = torch.randint(0, 734_684, (N,), device="cuda", generator=g, dtype=torch.int32)
+    art = torch.randint(0, 295_861, (N,), device="cuda", generator=g, dtype=torch.int32)
+    ctx_alb, ctx_art = alb[:5].clone(), art[:5].clone()
+    ctx = torch.cat([A[(ctx_alb % 100_000).long()], R[ctx_art.long()]], dim=1).contiguous()
+    ms = timeit(lambda: engine.topk_scan(A, ctx, 500, rows_b=R, idx_a=alb, idx_b=art, mod_a=100_000, max_over_queries=True,
+                                         ctx_a=ctx_alb, ctx_b=ctx_art, boost=0.1))
+    out["spotify_eval_top500_N2262292_F32"] = {
+        "ms": ms, "tracks_per_s": N / (ms * 1e-3), "bound": "l2 / issue (embedding tables are L2-resident)",
+        "id_bytes": 8 * N, "gathered_row_bytes": N * 2 * F * 4,
+        "note": "fused gather + 5 dots + max + isin boosts + running top-500; round 1: (N,64) candidate matrix + (N,5) "
+                "scores + full radix sort of N keys"}
     return out
 
 
@@ -462,13 +675,17 @@ def run_ours(a):
                                         "kernel": "k_glove_rows_grp_async", "kernel_ms": t_u,
                                         "alg_bytes_per_launch": abu, "unique_rows_per_step": Uu, "stream": "uniform"}
         if not a.no_inbatch:
-            line["other_workloads"] = inbatch_leg(peaks)
+            line["other_workloads"] = guarded(lambda: inbatch_leg(peaks), "inbatch")
+            line["retrieval"] = guarded(lambda: retrieval_leg(peaks, table, a), "retrieval")
         clocks.active = False
     line["clocks"] = clocks.summary()
     if rank == 0:
-        if world == 1 and not a.no_cpu:
-            del tr, table
+        del tr, table, ids_dev, cnt_dev
+        torch.cuda.empty_cache()
+        if world == 1 and not a.no_table_100m:
+            line["table_100m"] = guarded(lambda: table_100m_leg(a, 0, 1), "table_100m")
             torch.cuda.empty_cache()
+        if world == 1 and not a.no_cpu:
             cb, _ = cpu_reference(a, a.cpu_steps, 1)
             line["cpu_baseline"] = cb
             line["cpu_baseline_same_algorithm"] = cpu_same_algorithm(a, 2 * a.cpu_steps, 1)

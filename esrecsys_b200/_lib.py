@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libesr.so")
 
-ESR_OK, ESR_EINVAL, ESR_EWORKSPACE, ESR_ECUDA, ESR_ENOTSUP = 0, -1, -2, -3, -4
+ESR_OK, ESR_EINVAL, ESR_EWORKSPACE, ESR_ECUDA, ESR_ENOTSUP, ESR_ENOMEM = 0, -1, -2, -3, -4, -5
 OPT_ADAGRAD, OPT_ADAM, OPT_SGDM = 0, 1, 2
 BIAS_REFERENCE_BROADCAST, BIAS_PER_PAIR = 0, 1
 ROWS_UPDATE, ROWS_EMIT_GRADS = 0, 1
@@ -37,7 +37,16 @@ class EsrPlan(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("key_bits", C.c_int32), ("n_slots", C.c_int64),
                 ("keys", C.c_void_p), ("sorted_keys", C.c_void_p), ("perm", C.c_void_p),
                 ("partner", C.c_void_p), ("useg", C.c_void_p), ("uniq", C.c_void_p),
-                ("seg_off", C.c_void_p), ("n_uniq", C.c_void_p)]
+                ("seg_off", C.c_void_p), ("n_uniq", C.c_void_p), ("n_valid", C.c_void_p)]
+
+
+class EsrTopkCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("T", C.c_int32), ("rows_a", C.c_void_p), ("rows_a1", C.c_void_p),
+                ("ver", C.c_void_p), ("rows_b", C.c_void_p), ("idx_a", C.c_void_p), ("idx_b", C.c_void_p),
+                ("queries", C.c_void_p), ("ctx_a", C.c_void_p), ("ctx_b", C.c_void_p), ("N", C.c_int64),
+                ("Da", C.c_int32), ("Db", C.c_int32), ("mod_a", C.c_int32), ("max_over_queries", C.c_int32),
+                ("n_ctx_a", C.c_int32), ("n_ctx_b", C.c_int32), ("boost", C.c_float), ("k", C.c_int32),
+                ("ties_high_index_first", C.c_int32), ("reserved", C.c_int32)]
 
 
 class EsrGloveCfg(C.Structure):
@@ -102,6 +111,19 @@ _SIGNATURES = {
     "esr_peer_sync_bytes": (C.c_size_t, []),
     "esr_peer_allreduce_f32": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     "esr_peer_resolve_i32": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P]),
+    "esr_pipeline_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "esr_pipeline_streams": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "esr_pipeline_set_buffers": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_size_t, _P, _P, C.c_int64, _P]),
+    "esr_pipeline_capture_begin": (C.c_int, [_P, C.c_int32]),
+    "esr_pipeline_capture_end": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "esr_pipeline_submit": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int64)]),
+    "esr_pipeline_sync": (C.c_int, [_P]),
+    "esr_pipeline_destroy": (C.c_int, [_P]),
+    "esr_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "esr_topk_scan_f32": (C.c_int, [C.POINTER(EsrTopkCfg), _P, _P, _P, C.c_size_t, _P]),
+    "esr_peer_route_pairs_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "esr_peer_route_pairs_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "esr_peer_collect_pairs_i32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "esr_peer_apply_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                              C.c_float, C.c_float, _P]),
     "esr_route_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -35,6 +35,7 @@ extern "C" const char* esr_strerror(int rc) {
     case ESR_EWORKSPACE: return "workspace too small (see esr_*_workspace_bytes)";
     case ESR_ECUDA: return "CUDA error (see esr_last_cuda_error)";
     case ESR_ENOTSUP: return "not supported by this build";
+    case ESR_ENOMEM: return "host allocation failed";
     default: return "unknown error code";
   }
 }

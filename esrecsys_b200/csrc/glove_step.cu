@@ -159,11 +159,17 @@ __global__ void __launch_bounds__(kThreads) k_glove_prep(const int32_t* __restri
                                                          const int32_t* __restrict__ partner,
                                                          const float* __restrict__ counts,
                                                          const float* __restrict__ bias, const uint8_t* __restrict__ ver,
-                                                         int64_t n, int64_t B, float x_max, float alpha,
+                                                         int64_t n_cap, const int32_t* __restrict__ n_valid, int64_t B,
+                                                         float x_max, float alpha,
                                                          int32_t* __restrict__ skv, SlotRec* __restrict__ rec,
-                                                         float* __restrict__ blk, float* __restrict__ scalars) {
+                                                         float* __restrict__ blk, float* __restrict__ scalars,
+                                                         int32_t* __restrict__ wl_count, int32_t wl_words) {
   __shared__ float red[32 * 3];
   __shared__ bool last_block;
+  const int64_t n = n_valid ? min(n_cap, (int64_t)__ldg(n_valid)) : n_cap;
+  // the row pass's work lists / work counter / heavy-segment tickets start every step at zero: cleared here rather than by a
+  // memset node in front of the row pass (one launch less on the step's critical path)
+  for (int32_t k = blockIdx.x * kThreads + threadIdx.x; k < wl_words; k += gridDim.x * kThreads) wl_count[k] = 0;
   // kPrepItems slots per thread, every load of a stage issued before the first use: the kernel is a chain of
   // dependent gathers (perm -> counts, row -> bias / version), so its time is (latency x stages), not bytes.
   const int64_t p0 = blockIdx.x * (int64_t)(kThreads * kPrepItems) + threadIdx.x;
@@ -310,6 +316,8 @@ struct RowsArgs {
   EmitPeers peers;
   int64_t n;
   int64_t nchunks;
+  const int32_t* n_valid;  // optional (EsrPlan.n_valid): only the first *n_valid sorted slots are real
+  int32_t interleave;      // persistent async row pass: alternate work items from both ends of the sorted stream
   int32_t D4;
   int32_t chunk;
   int32_t per_pair;
@@ -319,6 +327,13 @@ struct RowsArgs {
   float lr, eps;
 };
 
+
+// Slots / chunks the pass really covers: the host-side capacity clamped by the device-side count of the plan
+// (row-sharded path: the pairs a rank receives are only counted on the device).
+__device__ __forceinline__ int64_t eff_n(const RowsArgs& a) {
+  return a.n_valid ? min(a.n, (int64_t)__ldg(a.n_valid)) : a.n;
+}
+__device__ __forceinline__ int64_t eff_chunks(const RowsArgs& a, int64_t n) { return (n + a.chunk - 1) / a.chunk; }
 
 // Close a finished segment: Adagrad row write (UPDATE) or gradient emit (EMIT).
 template <int NK>
@@ -356,11 +371,12 @@ struct ChunkMeta {
 
 __device__ __forceinline__ ChunkMeta load_chunk(const RowsArgs& a, int64_t c, int lane) {
   ChunkMeta m;
+  const int64_t n = eff_n(a);
   const int64_t p0 = c * a.chunk;
-  m.cnt = (int)min((int64_t)a.chunk, a.n - p0);
+  m.cnt = (int)min((int64_t)a.chunk, n - p0);
   m.kl = lane < m.cnt ? a.skv[p0 + lane] : kNoKey;
   const int32_t kprev0 = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-  const int32_t knextN = p0 + m.cnt < a.n ? a.skv[p0 + m.cnt] : kNoKey;
+  const int32_t knextN = p0 + m.cnt < n ? a.skv[p0 + m.cnt] : kNoKey;
   int32_t kp = __shfl_up_sync(FULL, m.kl, 1);
   if (lane == 0) kp = kprev0;
   int32_t kn = __shfl_down_sync(FULL, m.kl, 1);
@@ -453,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows(const RowsArgs a)
   const int64_t c = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
   float sums[2] = {0.f, 0.f};  // S1, S2 contributions (lane-uniform)
 
-  if (c < a.nchunks) {
+  if (c < eff_chunks(a, eff_n(a))) {
     const ChunkMeta m = load_chunk(a, c, lane);
     const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
     SegState<NK> st;
@@ -553,10 +569,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
   // Blocks are scheduled in index order; the sorted stream ends with the cold rows (singleton
   // segments: three DRAM rows per slot), the expensive chunks.  Walk the chunks from the END so the
   // long blocks start first and the cheap hot-row chunks fill the tail (longest-processing-time first).
-  const int64_t c = a.nchunks - 1 - ((blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * GP + grp);
+  const int64_t n_eff = eff_n(a);
+  const int64_t c = eff_chunks(a, n_eff) - 1 - ((blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5)) * GP + grp);
   const uint32_t D4 = (uint32_t)a.D4;
   const int64_t p0 = c * a.chunk;
-  const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+  const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, n_eff - p0) : 0;
   const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
   const float4* const rows0 = reinterpret_cast<const float4*>(a.rows[0]);
   const float4* const rows1 = reinterpret_cast<const float4*>(a.rows[1]);
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp(const RowsArg
   }
   if (gl == 0 && cnt > 0) {
     gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-    gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+    gm.keys[1 + cnt] = p0 + cnt < n_eff ? a.skv[p0 + cnt] : kNoKey;
     gm.keys[2 + cnt] = kNoKey;
   }
   __syncwarp();
@@ -773,15 +790,28 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   // the END of the sorted stream: the cold rows (singleton segments, three DRAM rows per slot) are the
   // long items, so they start first and the cheap hot-row chunks fill in behind them (LPT order), and a
   // warp that drew cheap items simply draws more of them.
-  const int64_t nitems = (a.nchunks + GP - 1) / GP;
+  const int64_t n_eff = eff_n(a), nchunks = eff_chunks(a, n_eff);
+  const int64_t nitems = (nchunks + GP - 1) / GP;
+  // a.interleave: even draws come from the END of the sorted stream (cold rows), odd draws from its FRONT (the Zipf head:
+  // partner reads only, served by L2), so DRAM-bound and L2-bound items are in flight together instead of one after the other
+  const int64_t n_end = a.interleave ? (nitems + 1) / 2 : nitems;
+  const int64_t front_limit = nchunks - n_end * GP;  // chunks below this index belong to the front draws
   for (;;) {
   int64_t item = 0;
   if (lane == 0) item = atomicAdd(a.work_counter, 1);
   item = __shfl_sync(FULL, item, 0);
   if (item >= nitems) break;
-  const int64_t c = a.nchunks - 1 - (item * GP + grp);
+  int64_t c;
+  bool valid;
+  if (!a.interleave || (item & 1) == 0) {
+    c = nchunks - 1 - ((a.interleave ? item >> 1 : item) * GP + grp);
+    valid = c >= 0 && (!a.interleave || c >= front_limit);
+  } else {
+    c = (item >> 1) * GP + grp;
+    valid = c < front_limit;
+  }
   const int64_t p0 = c * a.chunk;
-  const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+  const int cnt = valid ? (int)min((int64_t)a.chunk, n_eff - p0) : 0;
   __syncwarp();  // the previous item's readers are done with gm
   for (int s = gl; s < cnt; s += G) {
     gm.keys[1 + s] = a.skv[p0 + s];
@@ -789,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   }
   if (gl == 0 && cnt > 0) {
     gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-    gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+    gm.keys[1 + cnt] = p0 + cnt < n_eff ? a.skv[p0 + cnt] : kNoKey;
     gm.keys[2 + cnt] = kNoKey;
     gm.keys[3 + cnt] = kNoKey;
   }
@@ -1001,7 +1031,8 @@ __global__ void __launch_bounds__(kThreads, tma_min_blocks(NK)) k_glove_rows_tma
   const float mbs = a.scalars[ESR_SC_SUM_BS] * a.inv_B;
   const int64_t stride = (int64_t)gridDim.x * kWarps;
 
-  for (int64_t c = blockIdx.x * (int64_t)kWarps + wid; c < a.nchunks; c += stride) {
+  const int64_t nchunks_eff = eff_chunks(a, eff_n(a));
+  for (int64_t c = blockIdx.x * (int64_t)kWarps + wid; c < nchunks_eff; c += stride) {
     const ChunkMeta m = load_chunk(a, c, lane);
     // lane s issues the copies of slot s (it holds the slot's key and record)
     auto issue = [&](int s) {
@@ -1097,15 +1128,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_fifo(const Ro
   const float* const rows0 = a.rows[0];
   const float* const rows1 = a.rows[1];
   float sums[2] = {0.f, 0.f};
-  const int64_t nitems = (a.nchunks + GP - 1) / GP;
+  const int64_t n_eff = eff_n(a), nchunks = eff_chunks(a, n_eff);
+  const int64_t nitems = (nchunks + GP - 1) / GP;
   for (;;) {
     int64_t item = 0;
     if (lane == 0) item = atomicAdd(a.work_counter, 1);
     item = __shfl_sync(FULL, item, 0);
     if (item >= nitems) break;
-    const int64_t c = a.nchunks - 1 - (item * GP + grp);
+    const int64_t c = nchunks - 1 - (item * GP + grp);
     const int64_t p0 = c * a.chunk;
-    const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, a.n - p0) : 0;
+    const int cnt = c >= 0 ? (int)min((int64_t)a.chunk, n_eff - p0) : 0;
     __syncwarp();  // the previous item's readers are done with gm
     for (int s = gl; s < cnt; s += G) {
       gm.keys[1 + s] = a.skv[p0 + s];
@@ -1113,7 +1145,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_fifo(const Ro
     }
     if (gl == 0 && cnt > 0) {
       gm.keys[0] = p0 > 0 ? a.skv[p0 - 1] : kNoKey;
-      gm.keys[1 + cnt] = p0 + cnt < a.n ? a.skv[p0 + cnt] : kNoKey;
+      gm.keys[1 + cnt] = p0 + cnt < n_eff ? a.skv[p0 + cnt] : kNoKey;
       gm.keys[2 + cnt] = kNoKey;
       gm.keys[3 + cnt] = kNoKey;
     }
@@ -1269,7 +1301,7 @@ struct Straddler {
 
 __device__ __forceinline__ Straddler straddler_of(const RowsArgs& a, int64_t c) {
   Straddler s;
-  const int64_t pl = min((c + 1) * (int64_t)a.chunk, a.n) - 1;
+  const int64_t pl = min((c + 1) * (int64_t)a.chunk, eff_n(a)) - 1;
   s.key = a.skv[pl];
   s.u = a.useg[pl];
   s.np = (a.seg_off[s.u + 1] - 1) / a.chunk - c + 1;
@@ -1471,7 +1503,10 @@ bool glove_table_ok(const EsrTable* t, bool update) {
 
 bool cfg_ok(const EsrGloveCfg* cfg, const EsrPlan* plan) {
   if (!cfg || cfg->struct_size < sizeof(EsrGloveCfg) || !plan || plan->struct_size < sizeof(EsrPlan)) return false;
-  if (cfg->B < 0 || plan->n_slots != 2 * cfg->B || cfg->B_global < cfg->B || (cfg->B > 0 && cfg->B_global <= 0)) return false;
+  // B is a CAPACITY when the plan carries n_valid (row-sharded path: the pairs a rank processes are counted on the device),
+  // so only then may it exceed the global normaliser
+  if (cfg->B < 0 || plan->n_slots != 2 * cfg->B || (cfg->B > 0 && cfg->B_global <= 0)) return false;
+  if (plan->n_valid == nullptr && cfg->B_global < cfg->B) return false;
   if (cfg->bias_mode != ESR_BIAS_REFERENCE_BROADCAST && cfg->bias_mode != ESR_BIAS_PER_PAIR) return false;
   if (cfg->rows_mode != ESR_ROWS_UPDATE && cfg->rows_mode != ESR_ROWS_EMIT_GRADS) return false;
   return true;
@@ -1519,6 +1554,8 @@ RowsArgs make_rows_args(const EsrTable* t, const EsrPlan* plan, const EsrGloveCf
   a.emit_map = cfg->emit_map;
   load_emit_peers(cfg, &a.peers);
   a.n = plan->n_slots;
+  a.n_valid = plan->n_valid;
+  a.interleave = cfg->reserved == 7 ? 0 : 1;  // default since round 2 (148.5 vs 157.1 us per step); 7 = the old end-first order (A/B)
   a.D4 = t->D / 4;
   a.chunk = w.chunk;
   a.per_pair = cfg->bias_mode == ESR_BIAS_PER_PAIR;
@@ -1552,8 +1589,8 @@ extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const 
   carve_ws(ws, cfg->B, t->D, cfg->chunk, &w);
   const int64_t n = plan->n_slots;
   k_glove_prep<<<w.prep_blocks, kThreads, 0, stream>>>(plan->sorted_keys, plan->perm, plan->partner, counts, t->bias,
-                                                       t->ver, n, cfg->B, cfg->x_max, cfg->alpha, w.skv, w.rec, w.prep_blk,
-                                                       scalars);
+                                                       t->ver, n, plan->n_valid, cfg->B, cfg->x_max, cfg->alpha, w.skv, w.rec,
+                                                       w.prep_blk, scalars, w.wl_count, (int32_t)(4 + w.heavy_cap));
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
@@ -1568,7 +1605,6 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     row_blocks = (int)std::min<int64_t>(row_blocks, cap);
   }
   if ((phases & 1) && use_async && fifo) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + kFifoBufs * ((size_t)a.D4 * 16 + 8));
     static SmemOptIn configured_fifo;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && configured_fifo.raise(smem))
@@ -1576,7 +1612,6 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     k_glove_rows_grp_fifo<G, NV, 2><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if ((phases & 1) && use_async) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     const size_t smem = (size_t)kWarps * GP * (sizeof(GroupMeta) + 5 * (size_t)a.D4 * 16);
     static SmemOptIn configured;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && configured.raise(smem)) {
@@ -1589,7 +1624,6 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
     else k_glove_rows_grp_async<G, NV, 2, false><<<row_blocks, kThreads, smem, stream>>>(a);
     ESR_LAUNCH_CHECK();
   } else if (phases & 1) {
-    ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
     constexpr size_t smem = (size_t)kWarps * GP * sizeof(GroupMeta);
     static SmemOptIn configured;  // per <G, NV> instantiation
     if (smem > 48 * 1024 && configured.raise(smem))
@@ -1608,7 +1642,6 @@ static int launch_rows_grp(const RowsArgs& a, const GloveWs& w, float* scalars, 
 template <int NK, int S, int MINB>
 static int launch_rows(const RowsArgs& a, const GloveWs& w, float* scalars, bool tma, int phases, cudaStream_t stream) {
   int row_blocks = w.row_blocks;
-  if (phases & 1) ESR_CUDA(cudaMemsetAsync(w.wl_count, 0, (4 + w.heavy_cap) * sizeof(int32_t), stream));
   if (tma) {
     const size_t smem = (size_t)kWarps * kTmaStages * 3 * a.D4 * 16;
     static SmemOptIn configured;  // per NK instantiation: largest dynamic smem opted in

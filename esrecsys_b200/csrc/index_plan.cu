@@ -29,10 +29,17 @@ __device__ __forceinline__ int head_flag(const int32_t* __restrict__ sk, int64_t
   return p == 0 ? 1 : (sk[p] != sk[p - 1]);
 }
 
+// Real slots of the plan: the host-side capacity clamped by EsrPlan.n_valid (padding sorts to the end and is skipped).
+__device__ __forceinline__ int64_t eff_slots(int64_t n, const int32_t* n_valid) {
+  return n_valid ? min(n, (int64_t)__ldg(n_valid)) : n;
+}
+
 // Pass A: number of segment heads in each tile.
-__global__ void __launch_bounds__(kTileThreads) k_head_count(const int32_t* __restrict__ sk, int64_t n,
+__global__ void __launch_bounds__(kTileThreads) k_head_count(const int32_t* __restrict__ sk, int64_t n_cap,
+                                                            const int32_t* __restrict__ n_valid,
                                                             int32_t* __restrict__ tile_count) {
   __shared__ float red[32];
+  const int64_t n = eff_slots(n_cap, n_valid);
   const int64_t base = (int64_t)blockIdx.x * kTile;
   int c = 0;
 #pragma unroll
@@ -55,8 +62,10 @@ __global__ void __launch_bounds__(kTileThreads) k_head_count(const int32_t* __re
 // Pass B: exclusive scan of the tile counts (single block), total -> n_uniq, seg_off[total] = n.
 __global__ void __launch_bounds__(1024) k_tile_scan(const int32_t* __restrict__ tile_count, int32_t n_tiles,
                                                     int32_t* __restrict__ tile_base, int32_t* __restrict__ n_uniq,
-                                                    int32_t* __restrict__ seg_off, int64_t n) {
+                                                    int32_t* __restrict__ seg_off, int64_t n_cap,
+                                                    const int32_t* __restrict__ n_valid) {
   using Scan = cub::BlockScan<int, 1024>;
+  const int64_t n = eff_slots(n_cap, n_valid);
   __shared__ typename Scan::TempStorage tmp;
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -80,11 +89,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const int32_t* __restrict__ 
 
 // Pass C: useg, uniq, seg_off; optionally partner rows.
 __global__ void __launch_bounds__(kTileThreads) k_head_write(
-    const int32_t* __restrict__ sk, const int32_t* __restrict__ perm, const int32_t* __restrict__ keys, int64_t n,
-    const int32_t* __restrict__ tile_base, int32_t* __restrict__ useg, int32_t* __restrict__ uniq,
-    int32_t* __restrict__ seg_off, int32_t* __restrict__ partner) {
+    const int32_t* __restrict__ sk, const int32_t* __restrict__ perm, const int32_t* __restrict__ keys, int64_t n_cap,
+    const int32_t* __restrict__ n_valid, const int32_t* __restrict__ tile_base, int32_t* __restrict__ useg,
+    int32_t* __restrict__ uniq, int32_t* __restrict__ seg_off, int32_t* __restrict__ partner) {
   using Scan = cub::BlockScan<int, kTileThreads>;
   __shared__ typename Scan::TempStorage tmp;
+  const int64_t n = eff_slots(n_cap, n_valid);
   // blocked arrangement: thread t owns kItems consecutive slots so the scan order is slot order
   const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
   int f[kItems], key[kItems];
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(kTileThreads) k_head_write(
   int ex;
   Scan(tmp).ExclusiveSum(tsum, ex);
   int run = tile_base[blockIdx.x] + ex;  // heads strictly before this thread's first slot
-  const int64_t half = n >> 1;
+  const int64_t half = n_cap >> 1;  // slot layout [i ; j] of the CAPACITY, whatever part of it is real
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     int64_t p = base + k;
@@ -204,12 +214,12 @@ extern "C" int esr_plan_build_i32(const EsrPlan* plan, void* ws, size_t ws_bytes
   ESR_CUDA(cub::DeviceRadixSort::SortPairs(w.sort_tmp, avail, plan->keys, plan->sorted_keys, w.iota, plan->perm, (int)n,
                                            0, end_bit, stream));
   const int32_t tiles = (int32_t)ceil_div(n, kTile);
-  k_head_count<<<tiles, kTileThreads, 0, stream>>>(plan->sorted_keys, n, w.tile_count);
+  k_head_count<<<tiles, kTileThreads, 0, stream>>>(plan->sorted_keys, n, plan->n_valid, w.tile_count);
   ESR_LAUNCH_CHECK();
-  k_tile_scan<<<1, 1024, 0, stream>>>(w.tile_count, tiles, w.tile_base, plan->n_uniq, plan->seg_off, n);
+  k_tile_scan<<<1, 1024, 0, stream>>>(w.tile_count, tiles, w.tile_base, plan->n_uniq, plan->seg_off, n, plan->n_valid);
   ESR_LAUNCH_CHECK();
-  k_head_write<<<tiles, kTileThreads, 0, stream>>>(plan->sorted_keys, plan->perm, plan->keys, n, w.tile_base, plan->useg,
-                                                   plan->uniq, plan->seg_off, plan->partner);
+  k_head_write<<<tiles, kTileThreads, 0, stream>>>(plan->sorted_keys, plan->perm, plan->keys, n, plan->n_valid, w.tile_base,
+                                                   plan->useg, plan->uniq, plan->seg_off, plan->partner);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

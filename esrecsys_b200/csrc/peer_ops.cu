@@ -45,16 +45,20 @@ __global__ void __launch_bounds__(kThreads) k_peer_gather(const __grid_constant_
   const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
   for (int64_t first = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR) * ROWS; first < n; first += groups * ROWS) {
     const float4* src[ROWS];
+    float bv[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int64_t u = first + r;
       src[r] = nullptr;
+      bv[r] = 0.f;
       if (u < n) {
         const int32_t row = uniq[u];
         const int owner = cyc.owner(row);
         const int64_t local = cyc.local(row);
         src[r] = reinterpret_cast<const float4*>(rows.p[owner]) + local * D4;
-        if (lane == 0) out_bias[u] = reinterpret_cast<const float*>(bias.p[owner])[local];
+        // the bias is a 4-byte PEER load too: keep it in a register and store it after the row loads are in flight -- storing
+        // it here put one full NVLink round trip in front of every batch of row loads (measured: 430 vs 665 GB/s)
+        if (lane == 0) bv[r] = reinterpret_cast<const float*>(bias.p[owner])[local];
       }
     }
     for (int c = lane; c < D4; c += TPR) {
@@ -65,6 +69,11 @@ __global__ void __launch_bounds__(kThreads) k_peer_gather(const __grid_constant_
 #pragma unroll
       for (int r = 0; r < ROWS; ++r)
         if (src[r]) st_stream(out + (first + r) * D4 + c, v[r]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) out_bias[first + r] = bv[r];
     }
   }
 }
@@ -171,38 +180,54 @@ __global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const in
   }
 }
 
-// One group of TPR lanes per OWNER entry (compacted list), EB entries per iteration: sum the row's gradients
-// over the sources in source order (from my inbox, where the sources' row passes scattered them), then
-// optax.adagrad on the local shard row.  NR = number of sources rounded up to a power of two (compile time,
-// so the per-source loops carry no dead code); every load of the EB entries is issued before its first use.
-// (The first version looped over ESR_MAX_PEERS with predicates: 128 registers, 2 CTAs per SM, 2 TB/s.)
-template <int TPR, int NR, int EB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
-                                                                       const float* __restrict__ inbox_db, int n_ranks,
-                                                                       const int32_t* __restrict__ recv_ids,
-                                                                       const int32_t* __restrict__ src_meta,
-                                                                       const int32_t* __restrict__ desc,
-                                                                       const int32_t* __restrict__ own_list, int D4,
-                                                                       float* __restrict__ rows, float* __restrict__ acc,
-                                                                       float* __restrict__ bias, float* __restrict__ bias_acc,
-                                                                       float lr, float eps) {
+// One group of TPR lanes per OWNER entry (compacted list), EB entries per iteration: sum the row's gradients over the
+// sources in source order (from my inbox, where the sources' row passes scattered them), then optax.adagrad on the local
+// shard row.  Every entry has at least one source (the first one naming the row); its gradient row, the shard row and the
+// accumulator row of all EB entries are issued before the first use.  Further sources -- rare: only rows that several
+// ranks touched in the same step -- are added in source order, four independent loads at a time.  No per-source register
+// arrays sized for the worst case: 60-70 registers, no spills for any rank count (round 1's compile-time NR version
+// spilled 10-50 words per thread at its 80 / 128-register caps).
+template <int TPR, int EB>
+__global__ void __launch_bounds__(kThreads, 2) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
+                                                                    const float* __restrict__ inbox_db, int n_ranks,
+                                                                    const int32_t* __restrict__ recv_ids,
+                                                                    const int32_t* __restrict__ src_meta,
+                                                                    const int32_t* __restrict__ desc,
+                                                                    const int32_t* __restrict__ own_list, int D4,
+                                                                    float* __restrict__ rows, float* __restrict__ acc,
+                                                                    float* __restrict__ bias, float* __restrict__ bias_acc,
+                                                                    float lr, float eps) {
   const int lane = threadIdx.x % TPR;
   const int64_t total = src_meta[n_ranks * 3 + 1];
   const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
   for (int64_t i0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; i0 < total; i0 += groups * EB) {
-    int gi[EB][NR];
-    int64_t x[EB];
+    int64_t x[EB], k[EB];
+    int first[EB];   // inbox row of the first source naming the row
+    int q0[EB];      // that source
     bool on[EB];
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
       const int64_t i = i0 + e * groups;
       on[e] = i < total;
-      const int64_t k = on[e] ? own_list[i] : 0;
-      x[e] = on[e] ? recv_ids[k] : 0;
-#pragma unroll
-      for (int q = 0; q < NR; ++q) gi[e][q] = (on[e] && q < n_ranks) ? desc[k * n_ranks + q] : -1;
+      k[e] = on[e] ? own_list[i] : 0;
+      x[e] = on[e] ? recv_ids[k[e]] : 0;
     }
-    // bias scalars (lane 0) -- loaded up front so their latency overlaps the row traffic
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      first[e] = -1;
+      q0[e] = n_ranks;
+      if (on[e]) {
+        for (int q = 0; q < n_ranks; ++q) {
+          const int d = desc[k[e] * n_ranks + q];
+          if (d >= 0) {
+            first[e] = d;
+            q0[e] = q;
+            break;
+          }
+        }
+      }
+    }
+    // bias scalars (lane 0): every source's share, source order
     float bp[EB], ba[EB], bg[EB];
 #pragma unroll
     for (int e = 0; e < EB; ++e) {
@@ -210,29 +235,38 @@ __global__ void __launch_bounds__(kThreads, MINB) k_peer_merge_adagrad(const flo
       if (on[e] && lane == 0) {
         bp[e] = bias[x[e]];
         ba[e] = bias_acc[x[e]];
-#pragma unroll
-        for (int q = 0; q < NR; ++q)
-          if (gi[e][q] >= 0) bg[e] += inbox_db[gi[e][q]];
+        for (int q = q0[e]; q < n_ranks; ++q) {
+          const int d = desc[k[e] * n_ranks + q];
+          if (d >= 0) bg[e] += inbox_db[d];
+        }
       }
     }
     for (int c = lane; c < D4; c += TPR) {
-      float4 g[EB][NR], pv[EB], av[EB];
+      float4 g[EB], pv[EB], av[EB];
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
+        g[e] = f4_zero();
         if (on[e]) {
           pv[e] = reinterpret_cast<const float4*>(rows)[x[e] * D4 + c];
           av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + x[e] * D4 + c);
+          if (first[e] >= 0) g[e] = ld_stream(inbox_dE + (int64_t)first[e] * D4 + c);
         }
-#pragma unroll
-        for (int q = 0; q < NR; ++q) g[e][q] = gi[e][q] >= 0 ? ld_stream(inbox_dE + (int64_t)gi[e][q] * D4 + c) : f4_zero();
       }
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
         if (on[e]) {
-          float4 s = g[e][0];
+          // further sources in source order, 4 independent loads per round
+          for (int qb = q0[e] + 1; qb < n_ranks; qb += 4) {
+            int d[4];
+            float4 t[4];
 #pragma unroll
-          for (int q = 1; q < NR; ++q) f4_add(s, g[e][q]);   // source order: a missing source adds +0.0
-          adagrad4(pv[e], av[e], s, lr, eps);
+            for (int j = 0; j < 4; ++j) d[j] = qb + j < n_ranks ? desc[k[e] * n_ranks + qb + j] : -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = d[j] >= 0 ? ld_stream(inbox_dE + (int64_t)d[j] * D4 + c) : f4_zero();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f4_add(g[e], t[j]);   // a missing source adds +0.0
+          }
+          adagrad4(pv[e], av[e], g[e], lr, eps);
           reinterpret_cast<float4*>(rows)[x[e] * D4 + c] = pv[e];
           st_stream(reinterpret_cast<float4*>(acc) + x[e] * D4 + c, av[e]);
         }
@@ -345,20 +379,9 @@ extern "C" int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE
   const int32_t* own_list = desc + recv_cap * n_ranks;
   const int tpr = tpr_for(D4);
   const int grid = 8 * sm_count();
-#define ESR_MERGE(NR, EB, MINB)                                                                                          \
-  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, NR, EB, MINB><<<grid, kThreads, 0, stream>>>(                          \
-                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, own_list, \
-                            D4, shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)))
-  if (n_ranks == 1) {
-    ESR_MERGE(1, 4, 3);
-  } else if (n_ranks == 2) {
-    ESR_MERGE(2, 4, 2);
-  } else if (n_ranks <= 4) {
-    ESR_MERGE(4, 2, 3);
-  } else {
-    ESR_MERGE(8, 2, 2);
-  }
-#undef ESR_MERGE
+  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 4><<<grid, kThreads, 0, stream>>>(
+                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, own_list, D4,
+                            shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)));
   ESR_LAUNCH_CHECK();
   k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
   ESR_LAUNCH_CHECK();
@@ -491,7 +514,7 @@ __global__ void __launch_bounds__(kThreads) k_peer_emit_plan(const __grid_consta
     const int o = cyc.owner(uniq[u]);
     const int64_t idx = (int64_t)off[o] + inv_order[u] - dsp[o];
     if (idx >= inbox_cap || idx >= (1 << 27)) {
-      *err = 1;
+      atomicOr(err, 1);
       emit_map[u] = o << 27;  // clamp: keep the store in bounds
     } else {
       emit_map[u] = (o << 27) | (int32_t)idx;
@@ -514,6 +537,250 @@ extern "C" int esr_peer_emit_plan_i32(const void* const* peer_counts, int32_t n_
     if ((1 << b) == n_ranks) cyc.shift = b;
   k_peer_emit_plan<<<2 * sm_count(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
       pc, n_ranks, me, cyc, uniq, n_uniq, cap, inv_order, inbox_cap, emit_map, err);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OWNER-COMPUTES pair routing.  A pair (i, j, x) is processed by the rank that OWNS row i (owner = i % n): that
+// rank reads E[i] from its own shard, so only the unique PARTNER rows j of its pairs cross NVLink (ids are frequency
+// ranks and i > j -- wikipedia/make_dictionary.py:113-116, make_cooccurrence.py:48 -- so the j side is the hot,
+// heavily duplicated side), and only their gradients travel back.  Counted on the bench stream (Zipf(1), V = 1M,
+// B = 262 144 per GPU, 8 ranks): 28 062 remote unique rows per rank and step instead of 119 861 when every rank
+// keeps the pairs it was handed (4.3x fewer NVLink bytes in each direction); V = 100M: 56 770 instead of 208 461.
+// The triples themselves are 12 bytes per pair: routing them costs 2 % of what it saves.
+//
+//  esr_peer_route_pairs_i32   source side (ids only: side stream): STABLE partition of my B pairs by owner(i) written
+//                             straight into the owners' pair inboxes (region of source `me`), plus my per-owner
+//                             counts.  Stable => the received batch is a deterministic function of the global batch.
+//  esr_peer_collect_pairs_i32 owner side, after a barrier: concatenates the regions in source order into the flat
+//                             [i ; j] slot array of the plan (capacity B_cap per half, padding key = pad_key sorts to
+//                             the end), the counts, and *n_valid = 2 m.  err |= 2 if m > B_cap (pairs dropped).
+// Bit-exact contract: oracle/index.py route_pairs / collect_pairs.
+// ---------------------------------------------------------------------------------------------
+namespace esr {
+namespace {
+
+constexpr int kRouteItems = 8;
+constexpr int kRouteTile = kThreads * kRouteItems;  // 2048 pairs per block, blocked arrangement (order preserving)
+
+struct OwnerCounts {  // per-owner counters packed 16 bits each (a tile holds 2048 pairs < 65536)
+  unsigned long long lo, hi;  // owners 0..3, 4..7
+  __device__ __forceinline__ void add(int o) {
+    if (o < 4) lo += 1ull << (16 * o);
+    else hi += 1ull << (16 * (o - 4));
+  }
+  __device__ __forceinline__ int get(int o) const { return (int)(((o < 4 ? lo : hi) >> (16 * (o & 3))) & 0xffffull); }
+};
+
+__device__ __forceinline__ unsigned long long warp_excl_scan_u64(unsigned long long v, unsigned long long* total) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(FULL, x, o);
+    if (lane >= o) x += y;
+  }
+  *total = __shfl_sync(FULL, x, 31);
+  return x - v;
+}
+
+// per block and owner: number of pairs of the tile whose row i lives on that owner
+__global__ void __launch_bounds__(kThreads) k_pair_count(const int32_t* __restrict__ ids_i, int64_t B, Cyclic cyc,
+                                                         int32_t* __restrict__ blk_cnt /* [blocks][8] */) {
+  __shared__ int cnt[ESR_MAX_PEERS];
+  if (threadIdx.x < ESR_MAX_PEERS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
+  OwnerCounts c{0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k)
+    if (base + k < B) c.add(cyc.owner(ids_i[base + k]));
+  for (int o = 0; o < cyc.n; ++o) {
+    int v = c.get(o);
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[o], v);  // integer counts: order-independent
+  }
+  __syncthreads();
+  if (threadIdx.x < ESR_MAX_PEERS) blk_cnt[blockIdx.x * ESR_MAX_PEERS + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// one block: exclusive prefix over the blocks for every owner, totals to the owners' count tables
+__global__ void __launch_bounds__(ESR_MAX_PEERS * 32) k_pair_scan(const int32_t* __restrict__ blk_cnt, int n_blocks, int n_ranks,
+                                                                  int me, int32_t* __restrict__ blk_base,
+                                                                  const __grid_constant__ PeerPtrs peer_counts,
+                                                                  int32_t* __restrict__ my_counts) {
+  const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp o scans owner o
+  if (o >= n_ranks) return;
+  int carry = 0;
+  for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+    const int b = b0 + lane;
+    const int v = b < n_blocks ? blk_cnt[b * ESR_MAX_PEERS + o] : 0;
+    int x = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int y = __shfl_up_sync(FULL, x, s);
+      if (lane >= s) x += y;
+    }
+    if (b < n_blocks) blk_base[b * ESR_MAX_PEERS + o] = carry + x - v;
+    carry += __shfl_sync(FULL, x, 31);
+  }
+  if (lane == 0) {
+    my_counts[o] = carry;
+    reinterpret_cast<int32_t*>(const_cast<void*>(peer_counts.p[o]))[me] = carry;  // owner o: "source me sends you carry pairs"
+  }
+}
+
+// stable scatter of the tile's pairs into the owners' inbox regions of source `me`
+__global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __restrict__ ids, const float* __restrict__ counts,
+                                                           int64_t B, Cyclic cyc, int me, const int32_t* __restrict__ blk_base,
+                                                           const __grid_constant__ PeerPtrs peer_ids,
+                                                           const __grid_constant__ PeerPtrs peer_cnt) {
+  __shared__ unsigned long long wlo[kThreads / 32], whi[kThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
+  int32_t vi[kRouteItems], vj[kRouteItems];
+  float vx[kRouteItems];
+  int own[kRouteItems];
+  OwnerCounts c{0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k) {
+    own[k] = -1;
+    if (base + k < B) {
+      vi[k] = ids[base + k];
+      vj[k] = ids[B + base + k];
+      vx[k] = counts[base + k];
+      own[k] = cyc.owner(vi[k]);
+      c.add(own[k]);
+    }
+  }
+  // exclusive prefix of the per-thread counters over the block, thread order (= pair order)
+  unsigned long long tlo, thi;
+  OwnerCounts ex;
+  ex.lo = warp_excl_scan_u64(c.lo, &tlo);
+  ex.hi = warp_excl_scan_u64(c.hi, &thi);
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 31) {
+    wlo[wid] = tlo;
+    whi[wid] = thi;
+  }
+  __syncthreads();
+  for (int w = 0; w < wid; ++w) {
+    ex.lo += wlo[w];
+    ex.hi += whi[w];
+  }
+  int run[ESR_MAX_PEERS];
+#pragma unroll
+  for (int o = 0; o < ESR_MAX_PEERS; ++o) run[o] = o < cyc.n ? blk_base[blockIdx.x * ESR_MAX_PEERS + o] + ex.get(o) : 0;
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k) {
+    if (own[k] >= 0) {
+      int pos = 0;
+#pragma unroll
+      for (int o = 0; o < ESR_MAX_PEERS; ++o)
+        if (o == own[k]) pos = run[o]++;
+      // region of source `me` in owner's inbox: ids [me][2][B], counts [me][B]
+      int32_t* dst = reinterpret_cast<int32_t*>(const_cast<void*>(peer_ids.p[own[k]])) + (int64_t)me * 2 * B;
+      dst[pos] = vi[k];
+      dst[B + pos] = vj[k];
+      reinterpret_cast<float*>(const_cast<void*>(peer_cnt.p[own[k]]))[(int64_t)me * B + pos] = vx[k];
+    }
+  }
+}
+
+// owner side: regions -> flat [i ; j] keys of capacity 2 * B_cap, counts, n_valid; padding keys sort to the end
+__global__ void __launch_bounds__(kThreads) k_pair_collect(const int32_t* __restrict__ in_ids, const float* __restrict__ in_cnt,
+                                                           const int32_t* __restrict__ in_counts, int n_ranks, int64_t B,
+                                                           int64_t B_cap, int32_t pad_key, int32_t* __restrict__ keys,
+                                                           float* __restrict__ counts, int32_t* __restrict__ n_valid,
+                                                           int32_t* __restrict__ err) {
+  __shared__ int64_t off[ESR_MAX_PEERS + 1];
+  if (threadIdx.x == 0) {
+    int64_t o = 0;
+    for (int s = 0; s < n_ranks; ++s) {
+      off[s] = o;
+      o += min((int64_t)max(in_counts[s], 0), B);
+    }
+    off[n_ranks] = o;
+  }
+  __syncthreads();
+  const int64_t m_all = off[n_ranks];
+  const int64_t m = min(m_all, B_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *n_valid = (int32_t)(2 * m);
+    if (m_all > B_cap) atomicOr(err, 2);
+  }
+  for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < B_cap; p += (int64_t)gridDim.x * kThreads) {
+    if (p < m) {
+      int s = 0;
+      while (s + 1 < n_ranks && p >= off[s + 1]) ++s;
+      const int64_t q = p - off[s];
+      keys[p] = in_ids[(int64_t)s * 2 * B + q];
+      keys[B_cap + p] = in_ids[(int64_t)s * 2 * B + B + q];
+      counts[p] = in_cnt[(int64_t)s * B + q];
+    } else {
+      keys[p] = pad_key;
+      keys[B_cap + p] = pad_key;
+      counts[p] = 0.f;
+    }
+  }
+}
+
+Cyclic make_cyclic(int n_ranks) {
+  Cyclic cyc;
+  cyc.n = n_ranks;
+  cyc.shift = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == n_ranks) cyc.shift = b;
+  return cyc;
+}
+
+}  // namespace
+}  // namespace esr
+
+extern "C" size_t esr_peer_route_pairs_workspace_bytes(int64_t B) {
+  if (B < 0) return 0;
+  const int64_t blocks = ceil_div(B > 0 ? B : 1, (int64_t)kRouteTile);
+  return 2 * align_up((size_t)blocks * ESR_MAX_PEERS * sizeof(int32_t), 256) + 256;
+}
+
+extern "C" int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts, int64_t B, int32_t n_ranks, int32_t me,
+                                        void* const* peer_pair_ids, void* const* peer_pair_cnt,
+                                        void* const* peer_pair_counts, int32_t* my_counts, void* ws, size_t ws_bytes,
+                                        esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && B >= 0 && B < ((int64_t)1 << 30));
+  ESR_REQUIRE(my_counts != nullptr);
+  PeerPtrs pi, pc, pn;
+  ESR_REQUIRE(load_ptrs(&pi, reinterpret_cast<const void* const*>(peer_pair_ids), n_ranks) &&
+              load_ptrs(&pc, reinterpret_cast<const void* const*>(peer_pair_cnt), n_ranks) &&
+              load_ptrs(&pn, reinterpret_cast<const void* const*>(peer_pair_counts), n_ranks));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int blocks = (int)ceil_div(B > 0 ? B : 1, (int64_t)kRouteTile);
+  ESR_REQUIRE(ws != nullptr && (B == 0 || (ids && counts)));
+  if (ws_bytes < esr_peer_route_pairs_workspace_bytes(B)) return ESR_EWORKSPACE;
+  Carver c(ws);
+  int32_t* blk_cnt = c.take<int32_t>((size_t)blocks * ESR_MAX_PEERS);
+  int32_t* blk_base = c.take<int32_t>((size_t)blocks * ESR_MAX_PEERS);
+  const Cyclic cyc = make_cyclic(n_ranks);
+  k_pair_count<<<blocks, kThreads, 0, stream>>>(ids, B, cyc, blk_cnt);
+  ESR_LAUNCH_CHECK();
+  k_pair_scan<<<1, ESR_MAX_PEERS * 32, 0, stream>>>(blk_cnt, blocks, n_ranks, me, blk_base, pn, my_counts);
+  ESR_LAUNCH_CHECK();
+  if (B > 0) {
+    k_pair_scatter<<<blocks, kThreads, 0, stream>>>(ids, counts, B, cyc, me, blk_base, pi, pc);
+    ESR_LAUNCH_CHECK();
+  }
+  return ESR_OK;
+}
+
+extern "C" int esr_peer_collect_pairs_i32(const int32_t* in_ids, const float* in_cnt, const int32_t* in_counts, int32_t n_ranks,
+                                          int64_t B, int64_t B_cap, int32_t pad_key, int32_t* keys, float* counts,
+                                          int32_t* n_valid, int32_t* err, esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && B >= 0 && B_cap > 0 && B_cap < ((int64_t)1 << 30));
+  ESR_REQUIRE(in_ids && in_cnt && in_counts && keys && counts && n_valid && err);
+  const int64_t want = ceil_div(B_cap, (int64_t)kThreads);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  k_pair_collect<<<(unsigned)(want < cap ? want : cap), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      in_ids, in_cnt, in_counts, n_ranks, B, B_cap, pad_key, keys, counts, n_valid, err);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

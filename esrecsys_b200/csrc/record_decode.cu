@@ -13,6 +13,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <new>
+#include <vector>
+
 #include "esr.h"
 
 namespace {
@@ -80,7 +83,12 @@ extern "C" int64_t esr_decode_cooccur_b64(const char* text, size_t n_bytes, int3
   if (!text || !out_i || !out_j || !out_count || cap < 0) return ESR_EINVAL;
   const unsigned char* p = reinterpret_cast<const unsigned char*>(text);
   const unsigned char* end = p + n_bytes;
-  unsigned char buf[16384];  // <= 1001 entries per row message (wikipedia/make_cooccurrence.py:87): ~9 KB worst case
+  // <= 1001 entries per row message at the reference's default --max_row_size (wikipedia/make_cooccurrence.py:87): ~9 KB
+  // worst case, decoded on the stack; longer lines (a larger --max_row_size, many 5-byte varints) take a heap buffer.
+  unsigned char stack_buf[16384];
+  std::vector<unsigned char> heap_buf;
+  unsigned char* buf = stack_buf;
+  size_t buf_cap = sizeof(stack_buf);
   int64_t n = 0, rows = 0;
   while (p < end) {
     const unsigned char* nl = static_cast<const unsigned char*>(memchr(p, '\n', (size_t)(end - p)));
@@ -89,7 +97,16 @@ extern "C" int64_t esr_decode_cooccur_b64(const char* text, size_t n_bytes, int3
       p = nl + 1;
       continue;
     }
-    if ((size_t)(nl - p) / 4 * 3 + 3 > sizeof(buf)) return ESR_EINVAL;
+    const size_t need = (size_t)(nl - p) / 4 * 3 + 3;
+    if (need > buf_cap) {
+      try {
+        heap_buf.resize(need + need / 2);
+      } catch (const std::bad_alloc&) {
+        return ESR_ENOMEM;  // not "malformed": the row is valid, the host is out of memory
+      }
+      buf = heap_buf.data();
+      buf_cap = heap_buf.size();
+    }
     const int64_t len = b64_decode(p, nl, buf);
     if (len < 0) return ESR_EINVAL;
     // ---- CooccurrenceRow ----

@@ -56,20 +56,24 @@ __global__ void __launch_bounds__(kThreads) k_route_finish(const int32_t* __rest
 }
 
 __global__ void __launch_bounds__(kThreads) k_plan_compact(const int32_t* __restrict__ perm,
-                                                           const int32_t* __restrict__ useg, int64_t n,
+                                                           const int32_t* __restrict__ useg, int64_t n_cap,
+                                                           const int32_t* __restrict__ n_valid,
                                                            int32_t* __restrict__ slot_u /* [n] scratch */) {
+  const int64_t n = n_valid ? min(n_cap, (int64_t)__ldg(n_valid)) : n_cap;
   const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (p < n) slot_u[perm[p]] = useg[p];
 }
 
 __global__ void __launch_bounds__(kThreads) k_plan_compact2(const int32_t* __restrict__ perm,
                                                             const int32_t* __restrict__ useg,
-                                                            const int32_t* __restrict__ slot_u, int64_t n,
+                                                            const int32_t* __restrict__ slot_u, int64_t n_cap,
+                                                            const int32_t* __restrict__ n_valid,
                                                             int32_t* __restrict__ sorted_keys,
                                                             int32_t* __restrict__ partner, int32_t* __restrict__ uniq) {
+  const int64_t n = n_valid ? min(n_cap, (int64_t)__ldg(n_valid)) : n_cap;
   const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
   if (p >= n) return;
-  const int64_t half = n >> 1;
+  const int64_t half = n_cap >> 1;  // slot layout [i ; j] of the capacity
   const int64_t s = perm[p];
   const int32_t u = useg[p];
   sorted_keys[p] = u;
@@ -189,9 +193,10 @@ extern "C" int esr_plan_compact_i32(const EsrPlan* plan, int32_t* sorted_keys, i
   ESR_REQUIRE(plan->perm && plan->useg);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const unsigned grid = (unsigned)ceil_div(n, kThreads);
-  k_plan_compact<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, n, scratch);
+  k_plan_compact<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, n, plan->n_valid, scratch);
   ESR_LAUNCH_CHECK();
-  k_plan_compact2<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, scratch, n, sorted_keys, partner, uniq);
+  k_plan_compact2<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, scratch, n, plan->n_valid, sorted_keys, partner,
+                                                 uniq);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

@@ -107,7 +107,9 @@ class EmbeddingTable:
 class IndexPlan:
     """Device buffers + descriptor of one batch's index plan (EsrPlan)."""
 
-    def __init__(self, n_slots, V, device=None, with_partner=True):
+    def __init__(self, n_slots, V, device=None, with_partner=True, n_valid=None):
+        """``n_valid``: optional device int32 scalar -- only the first ``n_valid`` SORTED slots are real (the row-sharded
+        path pads its fixed-capacity slot array with a key larger than every row id; EsrPlan.n_valid)."""
         self.device = _dev(device)
         n = int(n_slots)
         self.n_slots = n
@@ -134,6 +136,8 @@ class IndexPlan:
         s.partner = L.ptr(self.partner)
         s.useg, s.uniq, s.seg_off, s.n_uniq = (L.ptr(self.useg), L.ptr(self.uniq), L.ptr(self.seg_off),
                                                L.ptr(self.n_uniq))
+        self.n_valid = n_valid
+        s.n_valid = L.ptr(n_valid) if n_valid is not None else None
         self.s = s
         self._keys = None
 
@@ -180,6 +184,8 @@ class GloveStep:
         cfg.rows_mode = L.ROWS_EMIT_GRADS if emit_grads else L.ROWS_UPDATE
         if impl == "fifo":          # the group row pass with bulk-copy FIFO staging (A/B candidate for the default)
             impl, variant = "auto", 2
+        if impl == "endfirst":      # A/B probe: the round-1 work order of the persistent row pass (cold end of the stream first)
+            impl, variant = "auto", 7
         cfg.impl = impl if isinstance(impl, int) else {"auto": L.IMPL_AUTO, "ldg": L.IMPL_LDG, "tma": L.IMPL_TMA}[impl]
         cfg.B = self.B
         cfg.B_global = int(B_global if B_global is not None else B)
@@ -307,6 +313,51 @@ def sort_cols(scores, k=None, descending=False, want_values=False):
     L.check(L.lib().esr_sort_cols_f32(L.ptr(scores), V, T, 1 if descending else 0, k, L.ptr(idx), L.ptr(val), L.ptr(ws),
                                       ws_bytes, L.stream_ptr()), "esr_sort_cols_f32")
     return (idx, val) if want_values else idx
+
+
+def topk_scan(rows_a, queries, k, *, rows_a1=None, ver=None, rows_b=None, idx_a=None, idx_b=None, mod_a=0,
+              max_over_queries=False, ctx_a=None, ctx_b=None, boost=0.1, ties_high_index_first=False, stream=None):
+    """Fused retrieval (``esr_topk_scan_f32``): one pass over the candidate rows, running top-k per list in shared memory --
+    no (N, T) score matrix, no sort of N keys.  Returns ``(values, indices)`` of shape ``(lists, k)``, best first; ``lists``
+    is T, or 1 with ``max_over_queries`` (the eval_step affinity of spotify/models.py:78-80).  See include/esr.h."""
+    dev = rows_a.device
+    queries = queries.contiguous()
+    T = queries.shape[0]
+    N = int(idx_a.numel() if idx_a is not None else (idx_b.numel() if idx_b is not None else rows_a.shape[0]))
+    cfg = L.EsrTopkCfg()
+    cfg.struct_size = C.sizeof(L.EsrTopkCfg)
+    cfg.T = T
+    cfg.rows_a, cfg.rows_a1, cfg.ver = L.ptr(rows_a), L.ptr(rows_a1), L.ptr(ver)
+    cfg.rows_b, cfg.idx_a, cfg.idx_b = L.ptr(rows_b), L.ptr(idx_a), L.ptr(idx_b)
+    cfg.queries, cfg.ctx_a, cfg.ctx_b = L.ptr(queries), L.ptr(ctx_a), L.ptr(ctx_b)
+    cfg.N = N
+    cfg.Da = rows_a.shape[1]
+    cfg.Db = rows_b.shape[1] if rows_b is not None else 0
+    cfg.mod_a = int(mod_a)
+    cfg.max_over_queries = 1 if max_over_queries else 0
+    cfg.n_ctx_a = int(ctx_a.numel()) if ctx_a is not None else 0
+    cfg.n_ctx_b = int(ctx_b.numel()) if ctx_b is not None else 0
+    cfg.boost = float(boost)
+    cfg.k = int(k)
+    cfg.ties_high_index_first = 1 if ties_high_index_first else 0
+    assert queries.shape[1] == cfg.Da + cfg.Db
+    lists = 1 if max_over_queries else T
+    ws_bytes = int(L.lib().esr_topk_workspace_bytes(N, cfg.Da + cfg.Db, T, cfg.max_over_queries, cfg.k))
+    if ws_bytes == 0:
+        raise L.EsrError("esr_topk_scan_f32: unsupported shape (N=%d, D=%d, T=%d, k=%d)" % (N, cfg.Da + cfg.Db, T, k))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    idx = torch.empty(lists, int(k), dtype=torch.int32, device=dev)
+    val = torch.empty(lists, int(k), dtype=torch.float32, device=dev)
+    L.check(L.lib().esr_topk_scan_f32(C.byref(cfg), L.ptr(idx), L.ptr(val), L.ptr(ws), ws_bytes, L.stream_ptr(stream)),
+            "esr_topk_scan_f32")
+    return val, idx
+
+
+def table_topk(table: EmbeddingTable, queries, k, ties_high_index_first=False):
+    """Top-k rows of a table per query vector: ``(values (T,k), indices (T,k))`` -- dump_knn / find_top_k without the
+    (V,T) score matrix."""
+    t = table
+    return topk_scan(t.rows0, queries, k, rows_a1=t.rows1, ver=t.ver, ties_high_index_first=ties_high_index_first)
 
 
 def top_k(scores_1d, k):

@@ -280,7 +280,9 @@ class PeerShardedGloveTrainer:
             self.pub.append(dict(counts=counts, p_counts=p_counts, send_local=send_local, p_send_local=p_send_local,
                                  order=torch.empty(n_slots, **i32), inv_order=torch.empty(n_slots, **i32)))
         # gradient inbox: the sources' row passes scatter their rows for my shard straight into it (NVLink stores)
-        self.inbox_cap = n_slots * min(self.n, 4)
+        # every source can name up to n_slots rows of ONE owner (ids congruent mod n), so the worst case is n * n_slots rows;
+        # only the part a step touches costs bandwidth.  k_peer_emit_plan still flags an overflow in ``err`` (check()).
+        self.inbox_cap = n_slots * self.n
         self.inbox_dE, self.p_inbox_dE = symm((self.inbox_cap, D), torch.float32)
         self.inbox_db, self.p_inbox_db = symm((self.inbox_cap,), torch.float32)
         self.emit_map = torch.zeros(n_slots, **i32)
@@ -446,6 +448,17 @@ class PeerShardedGloveTrainer:
         torch.cuda.current_stream().synchronize()
         self.barrier()
 
+    def check(self):
+        """Synchronise and raise if any step overflowed a gradient inbox (the device flag of esr_peer_emit_plan_i32):
+        the overflowing rows were clamped, so the tables can no longer be trusted."""
+        torch.cuda.synchronize(self.dev)
+        if int(self.err.item()) != 0:
+            raise RuntimeError("PeerShardedGloveTrainer: gradient inbox overflow (inbox_cap=%d rows); training state is invalid"
+                               % self.inbox_cap)
+
+    def synchronize(self):
+        self.check()
+
     def step(self, ids, counts):
         """ids: int32 (2, B_local) global rows (host pinned or device); counts: f32 (B_local,).
         Enqueues one step; returns the GLOBAL loss as a device scalar."""
@@ -480,6 +493,288 @@ class PeerShardedGloveTrainer:
         return self.loss
 
     def gather_dense(self):
+        self.check()
+        E = torch.zeros(self.V, self.D, device=self.dev)
+        b = torch.zeros(self.V, device=self.dev)
+        idx = torch.arange(self.rank, self.V, self.n, device=self.dev)
+        E[idx] = self.shard.rows0
+        b[idx] = self.shard.bias
+        dist.all_reduce(E, group=self.group)
+        dist.all_reduce(b, group=self.group)
+        return E, b
+
+
+def pair_capacity(B_local, n):
+    """Pairs an owner must be able to take per step: its expected share is B_local (the global batch is n * B_local and
+    ownership is cyclic over frequency-ranked ids), the margin covers the binomial spread (sigma ~ sqrt(B_local)) many
+    times over; data that concentrates row i on one owner overflows and is reported by check()."""
+    if n == 1:
+        return int(B_local)
+    cap = int(B_local) + max(int(B_local) // 8, 512)
+    return (cap + 255) // 256 * 256
+
+
+class OwnerRoutedGloveTrainer:
+    """Row-sharded GloVe step with OWNER-COMPUTES pair routing (csrc/peer_ops.cu): every pair (i, j, x) of the global
+    batch is processed by the rank that owns row i, so only the unique PARTNER rows j cross NVLink (and only their
+    gradients travel back) -- 4.3x fewer NVLink bytes per direction than PeerShardedGloveTrainer on the bench stream at
+    8 ranks.  Everything else is the peer-memory machinery of PeerShardedGloveTrainer: cyclic ownership, compact table
+    of the step's unique rows, the row pass storing gradient rows straight into the owners' inboxes, owner-side merge in
+    source order + Adagrad; no NCCL inside the step (libesr all-reduce / barrier kernels), both halves CUDA-graphed.
+
+      side stream : stage the batch -> route pairs to their owners (peer stores, stable) -> barrier (side sequence)
+                    -> collect my pairs -> index plan (device-side slot count) -> route plan (published) -> compact plan
+      main stream : barrier -> [ids stream: owners pull the id lists, resolve, emit plan] || gather unique rows (own shard
+                    + NVLink loads) -> prep -> all-reduce(3) -> row pass (gradients -> inboxes) -> all-reduce(2) -> finish
+                    -> barrier -> owner merge + Adagrad
+
+    One global step equals the single-table step on the concatenated batch (tests: N virtual ranks on one GPU against
+    oracle.glove.step_adagrad; bench.py --gpus N runs the same check before its timed region)."""
+
+    DEPTH = 2
+    # libesr kernels per step (cub sort passes included): route pairs 3, collect 1, plan 8, route plan 5, compact 2, gather,
+    # prep, pull, resolve, emit plan, rows, combine, finish, merge, clear map, 2 all-reduces + 3 barriers
+    LAUNCHES_PER_STEP = 34
+
+    def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
+                 graphs=True, pair_cap=None, impl="auto"):
+        import torch.distributed._symmetric_memory as symm_mem
+        L.require_cuda()
+        self.group = group if group is not None else dist.group.WORLD
+        self.n = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.n > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch domain; ESR_MAX_PEERS)")
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.V, self.D, self.B, self.lr = int(V), int(D), int(B_local), float(lr)
+        self.B_cap = int(pair_cap) if pair_cap is not None else pair_capacity(self.B, self.n)
+        n, B, B_cap = self.n, self.B, self.B_cap
+        n_slots = 2 * B_cap
+        gname = self.group.group_name
+        self._hdls = []
+
+        def symm(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=self.dev)
+            h = symm_mem.rendezvous(t, gname)
+            self._hdls.append(h)
+            return t, (C.c_void_p * 8)(*[int(p) for p in h.buffer_ptrs])
+
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        V_loc, V_max = shard_rows(V, self.rank, n), shard_rows(V, 0, n)
+        rows, self.p_rows = symm((V_max, D), torch.float32)
+        bias, self.p_bias = symm((V_max,), torch.float32)
+        rows.zero_()
+        bias.zero_()
+        self.shard = EmbeddingTable.wrap(rows[:V_loc], bias=bias[:V_loc], acc=torch.full((V_loc, D), 0.1, device=self.dev),
+                                         bias_acc=torch.full((V_loc,), 0.1, device=self.dev))
+        self.pub, self.pin = [], []
+        for _ in range(self.DEPTH):
+            counts, p_counts = symm((16,), torch.int32)
+            send_local, p_send_local = symm((n_slots,), torch.int32)
+            self.pub.append(dict(counts=counts, p_counts=p_counts, send_local=send_local, p_send_local=p_send_local,
+                                 order=torch.empty(n_slots, **i32), inv_order=torch.empty(n_slots, **i32)))
+            ids, p_ids = symm((n, 2, B), torch.int32)
+            cnt, p_cnt = symm((n, B), torch.float32)
+            cc, p_cc = symm((16,), torch.int32)
+            cc.zero_()
+            self.pin.append(dict(ids=ids, p_ids=p_ids, cnt=cnt, p_cnt=p_cnt, counts=cc, p_counts=p_cc))
+        self.inbox_cap = n_slots * n
+        self.inbox_dE, self.p_inbox_dE = symm((self.inbox_cap, D), torch.float32)
+        self.inbox_db, self.p_inbox_db = symm((self.inbox_cap,), torch.float32)
+        words = int(L.lib().esr_peer_sync_bytes()) // 4
+        self.sync, self.p_sync = symm((words,), torch.int32)           # main-stream sequence (barriers + all-reduces)
+        self.sync2, self.p_sync2 = symm((words,), torch.int32)         # side-stream sequence (pairs-routed barrier)
+        self.sync.zero_()
+        self.sync2.zero_()
+        self.sync_seq = torch.zeros(1, **i32)
+        self.sync_seq2 = torch.zeros(1, **i32)
+        self.emit_map = torch.zeros(n_slots, **i32)
+        self.err = torch.zeros(1, **i32)
+        self.ops = LibesrOps(self.dev)
+        self.my_counts = torch.zeros(16, **i32)
+        self.route_ws = torch.empty(int(L.lib().esr_peer_route_pairs_workspace_bytes(B)), dtype=torch.uint8, device=self.dev)
+        # per parity: the pairs I own this step (flat [i ; j] keys + counts + device-side slot count) and their plans
+        self.keys = [torch.full((n_slots,), V, **i32) for _ in range(self.DEPTH)]
+        self.cnt_l = [torch.zeros(B_cap, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
+        self.n_valid = [torch.zeros(1, **i32) for _ in range(self.DEPTH)]
+        self.plans = [IndexPlan(n_slots, V + 1, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]   # pad key = V
+        self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
+        self.cplans = [IndexPlan(n_slots, n_slots, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]
+        for cp, pl in zip(self.cplans, self.plans):
+            cp.s.n_slots = n_slots
+            cp.s.perm, cp.s.useg, cp.s.seg_off, cp.s.n_uniq = pl.s.perm, pl.s.useg, pl.s.seg_off, pl.s.n_uniq
+        self.scratch = torch.empty(n_slots, **i32)
+        self.step_fn = GloveStep(self.compact, B_cap, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
+                                 B_global=B * n, dE=self.inbox_dE, db=self.inbox_db, impl=impl)
+        cfg = self.step_fn.cfg
+        cfg.emit_map = L.ptr(self.emit_map)
+        cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
+        cfg.emit_peers_db = C.cast(self.p_inbox_db, C.c_void_p)
+        cfg.n_emit_peers = n
+        self.recv_cap = self.inbox_cap
+        self.recv_ids = torch.empty(self.recv_cap, **i32)
+        self.src_meta = torch.zeros(3 * 8 + 4, **i32)
+        self.map_stride = V_max
+        self.slot_map = torch.full((n, V_max), -1, **i32)
+        self.desc = torch.empty(self.recv_cap * (n + 1), **i32)
+        self.s_side = torch.cuda.Stream(self.dev)
+        self.s_ids = torch.cuda.Stream(self.dev)
+        self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_top, self.ev_ids = torch.cuda.Event(), torch.cuda.Event()
+        self._keep = [None] * self.DEPTH
+        self.st_ids = [torch.ones(2 * B, **i32) for _ in range(self.DEPTH)]
+        self.st_counts = [torch.ones(B, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
+        self.use_graphs = bool(graphs)
+        self.g_plan = [None] * self.DEPTH
+        self.g_step = [None] * self.DEPTH
+        self.t = 0
+        self.loss = None
+        self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        torch.cuda.current_stream().synchronize()
+        self._hdls[0].barrier()
+
+    # -- synchronisation: libesr kernels over symmetric memory (one NVLink round trip, CUDA-graph capturable) ---------
+    def _sync(self, view=None, side=False):
+        p, seq = (self.p_sync2, self.sync_seq2) if side else (self.p_sync, self.sync_seq)
+        buf = L.ptr(view) if view is not None else None
+        L.check(L.lib().esr_peer_allreduce_f32(p, self.n, self.rank, buf, buf, view.numel() if view is not None else 0,
+                                               L.ptr(seq), L.stream_ptr()), "esr_peer_allreduce_f32")
+
+    def barrier(self):
+        self._sync()
+
+    # -- the two halves of a step; every call enqueues on the CURRENT stream ------------------------------------
+    def _plan_body(self, k):
+        """Ids only (side stream): route my pairs to their owners, collect the pairs I own, index plan, owner routing of
+        the unique rows (published for the peers), the plan re-expressed in unique-row indices."""
+        lib, n = L.lib(), self.n
+        pin, pub, plan, cplan = self.pin[k], self.pub[k], self.plans[k], self.cplans[k]
+        sp = L.stream_ptr()
+        L.check(lib.esr_peer_route_pairs_i32(L.ptr(self.st_ids[k]), L.ptr(self.st_counts[k]), self.B, n, self.rank,
+                                             pin["p_ids"], pin["p_cnt"], pin["p_counts"], L.ptr(self.my_counts),
+                                             L.ptr(self.route_ws), self.route_ws.numel(), sp), "esr_peer_route_pairs_i32")
+        self._sync(side=True)                                   # every source's pairs for me have landed
+        L.check(lib.esr_peer_collect_pairs_i32(L.ptr(pin["ids"]), L.ptr(pin["cnt"]), L.ptr(pin["counts"]), n, self.B,
+                                               self.B_cap, self.V, L.ptr(self.keys[k]), L.ptr(self.cnt_l[k]),
+                                               L.ptr(self.n_valid[k]), L.ptr(self.err), sp), "esr_peer_collect_pairs_i32")
+        plan.build(self.keys[k])
+        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
+        cplan.s.n_slots = plan.n_slots
+        L.check(lib.esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner),
+                                         L.ptr(cplan.uniq), L.ptr(self.scratch), sp), "esr_plan_compact_i32")
+
+    def _ids_body(self, k, sp):
+        lib, n = L.lib(), self.n
+        plan, pub = self.plans[k], self.pub[k]
+        L.check(lib.esr_peer_pull_ids_i32(pub["p_counts"], pub["p_send_local"], n, self.rank, self.recv_cap,
+                                          L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map), self.map_stride,
+                                          sp), "esr_peer_pull_ids_i32")
+        L.check(lib.esr_peer_resolve_i32(n, L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
+                                         self.map_stride, L.ptr(self.desc), self.recv_cap, sp), "esr_peer_resolve_i32")
+        L.check(lib.esr_peer_emit_plan_i32(pub["p_counts"], n, self.rank, L.ptr(plan.uniq), L.ptr(plan.n_uniq),
+                                           plan.capacity, L.ptr(pub["inv_order"]), self.inbox_cap, L.ptr(self.emit_map),
+                                           L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
+
+    def _step_body(self, k):
+        lib, n = L.lib(), self.n
+        plan, cplan, st = self.plans[k], self.cplans[k], self.step_fn
+        main = torch.cuda.current_stream(self.dev)
+        sp = L.stream_ptr()
+        self.barrier()                      # every route plan of this step is published; every owner applied step t-1
+        self.ev_top.record(main)
+        self.s_ids.wait_event(self.ev_top)
+        with torch.cuda.stream(self.s_ids):
+            self._ids_body(k, L.stream_ptr())
+            self.ev_ids.record(self.s_ids)
+        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
+                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
+        st.prep(cplan, self.cnt_l[k])
+        self._sync(st.scalars[0:3])         # global sum(bs), sum(bs^2), S0; also: all fetches done
+        main.wait_event(self.ev_ids)
+        st.rows(cplan)                      # gradient rows go straight to the owners' inboxes
+        self._sync(st.scalars[3:5])         # global S1, S2
+        st.finish(cplan)
+        self.barrier()                      # every rank's gradients have landed in the inboxes
+        L.check(lib.esr_peer_apply_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
+                                               L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
+                                               self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, sp),
+                "esr_peer_apply_adagrad_f32")
+
+    def _capture(self):
+        """Both halves per parity into CUDA graphs.  Collective: every rank captures the same sequence."""
+        try:
+            torch.cuda.synchronize(self.dev)
+            cap = torch.cuda.Stream(self.dev)
+            for k in range(self.DEPTH):
+                gp = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gp, stream=cap, capture_error_mode="thread_local"):
+                    self._plan_body(k)
+                gs = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gs, stream=cap, capture_error_mode="thread_local"):
+                    self._step_body(k)
+                self.g_plan[k], self.g_step[k] = gp, gs
+            torch.cuda.synchronize(self.dev)
+        except Exception as e:  # pragma: no cover
+            import warnings
+            warnings.warn("owner-routed step: CUDA-graph capture failed (%s); staying on eager launches" % e)
+            self.g_plan = [None] * self.DEPTH
+            self.g_step = [None] * self.DEPTH
+            self.use_graphs = False
+
+    def load_dense(self, E, b):
+        idx = torch.arange(self.rank, self.V, self.n)
+        self.shard.rows0.copy_(torch.as_tensor(E)[idx].to(self.dev))
+        self.shard.bias.copy_(torch.as_tensor(b).reshape(-1)[idx].to(self.dev))
+        torch.cuda.current_stream().synchronize()
+        self._hdls[0].barrier()
+
+    def step(self, ids, counts):
+        """ids: int32 (2, B_local) global rows (host pinned or device) -- this rank's share of the global batch, in the
+        layout of wikipedia/cooccurrence_matrix.py:103-114; counts: f32 (B_local,).  Enqueues one step; returns the
+        GLOBAL loss as a device scalar."""
+        k = self.t % self.DEPTH
+        main = torch.cuda.current_stream(self.dev)
+        side = self.s_side
+        if self.use_graphs and self.g_step[0] is None and self.t == 2 * self.DEPTH:
+            self._capture()                    # after two eager steps per parity (lazy module / allocator state is warm)
+        side.wait_stream(main)
+        side.wait_event(self.ev_done[k])       # step t-2 is done with parity k's buffers on this rank
+        with torch.cuda.stream(side):
+            self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
+            self.st_counts[k].copy_(counts, non_blocking=True)
+            self._keep[k] = (ids, counts)
+            if self.g_plan[k] is not None:
+                self.g_plan[k].replay()
+            else:
+                self._plan_body(k)
+            self.ev_plan[k].record(side)
+        main.wait_event(self.ev_plan[k])
+        if self.g_step[k] is not None:
+            self.g_step[k].replay()
+        else:
+            self._step_body(k)
+        self.ev_done[k].record(main)
+        slot = self.t % self.loss_log.numel()
+        self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
+        self.loss = self.loss_log[slot]
+        self.t += 1
+        return self.loss
+
+    def check(self):
+        """Synchronise and raise if a step overflowed the pair capacity (bit 1) or a gradient inbox (bit 0)."""
+        torch.cuda.synchronize(self.dev)
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError("OwnerRoutedGloveTrainer: %s; training state is invalid" % " and ".join(
+                m for b, m in ((2, "an owner received more than pair_cap=%d pairs in a step" % self.B_cap),
+                               (1, "a gradient inbox overflowed (inbox_cap=%d rows)" % self.inbox_cap)) if e & b))
+
+    def synchronize(self):
+        self.check()
+
+    def gather_dense(self):
+        self.check()
         E = torch.zeros(self.V, self.D, device=self.dev)
         b = torch.zeros(self.V, device=self.dev)
         idx = torch.arange(self.rank, self.V, self.n, device=self.dev)

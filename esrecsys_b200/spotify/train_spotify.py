@@ -36,12 +36,30 @@ def eval_scores(model: SpotifyModel, params, y, all_albums, all_artists):
     return aff
 
 
+def eval_topk(model: SpotifyModel, params, y, all_albums, all_artists, k=500):
+    """``jax.lax.top_k(result[1], k)`` of eval_step (:114-120) as ONE fused pass over the corpus: every track's row is
+    gathered on the fly (``concat(album_embed[album % 100000], artist_embed[artist])``, spotify/models.py:33-46), scored
+    against the 5 context rows, max-reduced, boosted by the two raw-id ``isin`` terms (:78-80) and kept only if it beats
+    the running top-k -- no (N, 2F) candidate matrix, no (N, 5) score matrix, no sort of N keys.
+    ``all_albums`` / ``all_artists`` may be device int32 tensors (kept resident across the 1000s of eval calls)."""
+    A, R = params["album_embed"]["embedding"], params["artist_embed"]["embedding"]
+    dev = A.device
+
+    def ids(x):
+        return x if torch.is_tensor(x) and x.device == dev and x.dtype == torch.int32 else \
+            torch.as_tensor(np.asarray(x)).to(dev, torch.int32).contiguous()
+    ctx = model.get_embeddings(params, y["album_context"], y["artist_context"]).contiguous()      # (5, 2F)
+    val, idx = engine.topk_scan(A, ctx, k, rows_b=R, idx_a=ids(all_albums), idx_b=ids(all_artists), mod_a=A.shape[0],
+                                max_over_queries=True, ctx_a=ids(y["album_context"]), ctx_b=ids(y["artist_context"]),
+                                boost=0.1)
+    return val[0], idx[0]
+
+
 def eval_step(model: SpotifyModel, params, y, all_tracks, all_albums, all_artists, k=500):
     """train_spotify.py:113-131: recall of the next tracks / artists among the top-k tracks.  Returns
     (metrics f32[2], top_k_indices)."""
-    aff = eval_scores(model, params, y, all_albums, all_artists)
-    _, top = engine.top_k(aff, k)                                                           # jax.lax.top_k
-    dev = aff.device
+    _, top = eval_topk(model, params, y, all_albums, all_artists, k)                        # jax.lax.top_k
+    dev = top.device
     top_l = top.long()
     top_tracks = torch.as_tensor(np.asarray(all_tracks)).to(dev)[top_l]
     top_artists = torch.as_tensor(np.asarray(all_artists)).to(dev)[top_l]

@@ -2,21 +2,22 @@
 ``train_epoch`` (wikipedia/train_cooccurence.py:103-112) without a tracing compiler.
 
 Per step the reference does ``next(train_it)`` -> ``apply_model`` -> ``update_model``.  Here a step is
-two CUDA graphs on two streams:
+two CUDA graphs on three streams, driven by libesr's native pipeline object (csrc/pipeline.cu: ONE C call
+per step -- the torch-level loop of round 1 spent 170-200 us of host time per step, more than the GPU needs):
 
-* side stream : stage the batch (H2D from pinned memory, or D2D) and build its index plan
-                (sort / unique / segments -- depends only on the ids),
+* copy stream : stage the batch (H2D from pinned memory on a copy engine, or D2D),
+* side stream : build its index plan (sort / unique / segments -- depends only on the ids),
 * main stream : prep -> rows (+combine) -> finish on the table.
 
-Plans and staging buffers are double-buffered, so the plan of batch t+1 is built while batch t
-trains; events order the two streams.  Everything a step launches is inside the timed region of
-bench.py.
+Staging buffers and plans are triple-buffered: batch t+2 uploads while the plan of batch t+1 is built and
+batch t trains, so a step from pinned host memory costs what a step from device memory does; events order
+the streams.  Everything a step launches is inside the timed region of bench.py.  ``graphs=False`` keeps an
+eager torch-stream version of the same choreography (debugging).
 """
 from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
 import torch
 
 from . import _lib as L
@@ -25,7 +26,7 @@ from .engine import EmbeddingTable, GloveStep, IndexPlan
 
 class GloveTrainer:
     def __init__(self, table: EmbeddingTable, B, lr=0.05, bias_mode="reference_broadcast", chunk=0, impl="auto",
-                 graphs=True, depth=2, loss_log=4096, row_blocks=None, priorities=False):
+                 graphs=True, depth=3, loss_log=4096, row_blocks=None, priorities=False, validate_ids="first"):
         L.require_cuda()
         if row_blocks is None:
             # The persistent row pass fills every SM with 2 CTAs, which leaves no registers for the plan
@@ -38,58 +39,99 @@ class GloveTrainer:
         self.B = int(B)
         self.dev = table.device
         self.depth = int(depth)
+        if not 1 <= self.depth <= 4:
+            raise ValueError("depth must be 1..4")
         self.step_fn = GloveStep(table, B, lr=lr, bias_mode=bias_mode, chunk=chunk, impl=impl, row_blocks=row_blocks)
         self.plans = [IndexPlan(2 * self.B, table.V, self.dev) for _ in range(self.depth)]
         self.ids = [torch.zeros(2 * self.B, dtype=torch.int32, device=self.dev) for _ in range(self.depth)]
         self.counts = [torch.ones(self.B, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
-        # priorities (EXPERIMENTAL, off): the step's short kernels (prep / combine / finish) on a high-priority stream, so
-        # their CTAs are placed ahead of the pending radix-sort CTAs of the next batch's plan instead of queueing behind them
-        self.s_main = torch.cuda.Stream(self.dev, priority=-1 if priorities else 0)
-        self.s_side = torch.cuda.Stream(self.dev)
-        self.ev_plan = [torch.cuda.Event() for _ in range(self.depth)]
-        self.ev_done = [torch.cuda.Event() for _ in range(self.depth)]
         self.loss_log = torch.zeros(loss_log, dtype=torch.float32, device=self.dev)
         self.loss_host = torch.zeros(loss_log, dtype=torch.float32).pin_memory()
         self.t = 0
-        self.kernels_per_step = None
-        self.g_plan = [None] * self.depth
-        self.g_step = [None] * self.depth
+        # The plan sorts ceil(log2 V) key bits and the row pass uses ids as raw row offsets, so an id outside [0, V) would
+        # corrupt memory where XLA clamps / drops it.  "first": the first batch is validated on the
+        # device (no host sync; the flag is read at the first synchronize()); "always": every batch, with a host sync
+        # per step (debug); "never": the caller guarantees the range.
+        if validate_ids not in ("first", "always", "never"):
+            raise ValueError("validate_ids must be 'first', 'always' or 'never'")
+        self.validate_ids = validate_ids
+        self.n_bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._bad_pending = False
+        self._keep = []
         self.use_graphs = bool(graphs)
+        self.pipe = None
         if self.use_graphs:
+            # native runtime: it owns the three streams (priorities: the step's stream above the plan stream, experimental)
+            h = C.c_void_p()
+            with torch.cuda.device(self.dev):
+                L.check(L.lib().esr_pipeline_create(self.depth, 1 if priorities else 0, C.byref(h)), "esr_pipeline_create")
+            self.pipe = h
+            sc, ss, sm_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            L.check(L.lib().esr_pipeline_streams(self.pipe, C.byref(sc), C.byref(ss), C.byref(sm_)), "esr_pipeline_streams")
+            self.s_copy = torch.cuda.ExternalStream(sc.value, device=self.dev)
+            self.s_side = torch.cuda.ExternalStream(ss.value, device=self.dev)
+            self.s_main = torch.cuda.ExternalStream(sm_.value, device=self.dev)
+            ids_p = (C.c_void_p * self.depth)(*[x.data_ptr() for x in self.ids])
+            cnt_p = (C.c_void_p * self.depth)(*[x.data_ptr() for x in self.counts])
+            L.check(L.lib().esr_pipeline_set_buffers(self.pipe, ids_p, cnt_p, self.ids[0].numel() * 4, self.counts[0].numel() * 4,
+                                                     self.step_fn.scalars.data_ptr() + 4 * L.SC_LOSS, self.loss_log.data_ptr(),
+                                                     self.loss_log.numel(), self.loss_host.data_ptr()),
+                    "esr_pipeline_set_buffers")
+            self.g_plan = [True] * self.depth      # the graphs live in the native object
+            self.g_step = [True] * self.depth
             self._capture()
+        else:
+            self.s_main = torch.cuda.Stream(self.dev, priority=-1 if priorities else 0)
+            self.s_side = torch.cuda.Stream(self.dev)
+            self.s_copy = torch.cuda.Stream(self.dev)
+            self.ev_copy = [torch.cuda.Event() for _ in range(self.depth)]
+            self.ev_plan = [torch.cuda.Event() for _ in range(self.depth)]
+            self.ev_done = [torch.cuda.Event() for _ in range(self.depth)]
+            self.g_plan = [None] * self.depth
+            self.g_step = [None] * self.depth
+
+    def __del__(self):
+        try:
+            if getattr(self, "pipe", None):
+                L.lib().esr_pipeline_destroy(self.pipe)
+                self.pipe = None
+        except Exception:  # pragma: no cover  (interpreter shutdown)
+            pass
 
     # kernels one step launches (libesr only; the radix sort is cub code compiled into libesr)
     LAUNCHES_PLAN = 8    # iota, cub histogram + <=4 onesweep passes (key_bits<=32), head count, scan, head write
-    LAUNCHES_STEP = 4    # prep (+ fused reduction), rows, combine, finish
+    LAUNCHES_STEP = 4    # prep (+ fused reduction and work-list clear), rows, combine, finish
 
-    def _plan_body(self, k):
-        self.plans[k].build(self.ids[k])
+    def _plan_body(self, k, stream=None):
+        self.plans[k].build(self.ids[k], stream=stream)
 
-    def _step_body(self, k):
-        self.step_fn.run(self.plans[k], self.counts[k])
+    def _step_body(self, k, stream=None):
+        self.step_fn.run(self.plans[k], self.counts[k], stream=stream)
 
     def _capture(self):
         # warm up once outside capture (function attributes, lazy module load), on valid ids
+        lib = L.lib()
         for k in range(self.depth):
             self.ids[k].zero_()
             self.ids[k][: self.B] = 1
         snap = self._snapshot()
         torch.cuda.synchronize(self.dev)
         for k in range(self.depth):
-            with torch.cuda.stream(self.s_side):
-                self._plan_body(k)
+            self._plan_body(k, self.s_side)
             self.s_side.synchronize()
-            with torch.cuda.stream(self.s_main):
-                self._step_body(k)
+            self._step_body(k, self.s_main)
             self.s_main.synchronize()
         for k in range(self.depth):
-            gp = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gp, stream=self.s_side):
-                self._plan_body(k)
-            gs = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gs, stream=self.s_main):
-                self._step_body(k)
-            self.g_plan[k], self.g_step[k] = gp, gs
+            L.check(lib.esr_pipeline_capture_begin(self.pipe, 0), "esr_pipeline_capture_begin")
+            try:
+                self._plan_body(k, self.s_side)
+            finally:
+                L.check(lib.esr_pipeline_capture_end(self.pipe, 0, k), "esr_pipeline_capture_end")
+            L.check(lib.esr_pipeline_capture_begin(self.pipe, 1), "esr_pipeline_capture_begin")
+            try:
+                self._step_body(k, self.s_main)
+            finally:
+                L.check(lib.esr_pipeline_capture_end(self.pipe, 1, k), "esr_pipeline_capture_end")
         self._restore(snap)
         torch.cuda.synchronize(self.dev)
 
@@ -107,45 +149,90 @@ class GloveTrainer:
             if x is not None:
                 x[rows] = v
 
-    def submit(self, ids, counts):
+    def _validate(self, k, side_stream):
+        """Count the ids of staging buffer k outside [0, V) on the side stream (after its plan: the buffer is intact)."""
+        L.check(L.lib().esr_check_ids_i32(L.ptr(self.ids[k]), self.ids[k].numel(), self.table.V, L.ptr(self.n_bad),
+                                          L.stream_ptr(side_stream)), "esr_check_ids_i32")
+        if self.validate_ids == "always":
+            side_stream.synchronize()
+            self._raise_if_bad()
+        else:
+            self._bad_pending = True
+
+    def submit(self, ids, counts, read_loss=False):
         """Enqueue one training step.  ``ids``: int32 (2,B) -- the batch layout of
         wikipedia/cooccurrence_matrix.py:103-114 -- and ``counts``: f32 (B,); pinned host tensors
-        (copied H2D asynchronously) or device tensors.  Returns the step number."""
+        (copied H2D asynchronously) or device tensors.  ``read_loss``: also copy the step's loss to the pinned host
+        log (``loss_host[step % len]``, asynchronous).  Returns the step number."""
         k = self.t % self.depth
-        side, main = self.s_side, self.s_main
+        want_check = self.validate_ids == "always" or (self.validate_ids == "first" and self.t == 0)
+        if self.pipe is not None:
+            if ids.dtype != torch.int32 or counts.dtype != torch.float32 or ids.numel() != 2 * self.B or \
+                    counts.numel() != self.B or not ids.is_contiguous() or not counts.is_contiguous():
+                raise ValueError("submit: ids must be contiguous int32 (2,%d), counts contiguous float32 (%d,)" % (self.B, self.B))
+            if not ids.is_cuda and not ids.is_pinned():
+                ids, counts = ids.pin_memory(), counts.pin_memory()      # pageable memory would serialise the copy
+            self._keep.append((ids, counts))                             # alive while the asynchronous copy may still read them
+            if len(self._keep) > 2 * self.depth + 2:
+                self._keep.pop(0)
+            flags = (1 if read_loss else 0) | (2 if ids.is_cuda else 0)  # device inputs: order behind the caller's stream
+            caller = torch.cuda.current_stream(self.dev).cuda_stream if ids.is_cuda else None
+            L.check(L.lib().esr_pipeline_submit(self.pipe, ids.data_ptr(), counts.data_ptr(), caller, flags, None),
+                    "esr_pipeline_submit")
+            if want_check:
+                self._validate(k, self.s_side)
+            self.t += 1
+            return self.t - 1
+        # eager torch-stream version of the same choreography (graphs=False)
+        side, main, copy = self.s_side, self.s_main, self.s_copy
         cur = torch.cuda.current_stream(self.dev)
-        side.wait_stream(cur)                 # inputs produced on the caller's stream
-        side.wait_event(self.ev_done[k])      # staging/plan buffers k are free again
-        with torch.cuda.stream(side):
+        copy.wait_stream(cur)                 # inputs produced on the caller's stream
+        copy.wait_event(self.ev_done[k])      # staging/plan buffers k are free again (step t - depth is done)
+        with torch.cuda.stream(copy):
             self.ids[k].copy_(ids.reshape(-1), non_blocking=True)
             self.counts[k].copy_(counts, non_blocking=True)
-            if self.use_graphs:
-                self.g_plan[k].replay()
-            else:
-                self._plan_body(k)
+            self.ev_copy[k].record(copy)
+        side.wait_event(self.ev_copy[k])
+        with torch.cuda.stream(side):
+            self._plan_body(k)
+            if want_check:
+                self._validate(k, side)
             self.ev_plan[k].record(side)
         main.wait_event(self.ev_plan[k])
         with torch.cuda.stream(main):
-            if self.use_graphs:
-                self.g_step[k].replay()
-            else:
-                self._step_body(k)
+            self._step_body(k)
             slot = self.t % self.loss_log.numel()
             self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
+            if read_loss:
+                self.loss_host[slot: slot + 1].copy_(self.loss_log[slot: slot + 1], non_blocking=True)
             self.ev_done[k].record(main)
         self.t += 1
         return self.t - 1
 
     def read_loss(self, step):
-        """Device->host read of one step's loss (asynchronous copy into pinned memory on the main stream)."""
+        """Device->host read of one step's loss (asynchronous copy into pinned memory on the main stream); prefer
+        ``submit(..., read_loss=True)``, which folds it into the step's call."""
         slot = step % self.loss_log.numel()
         with torch.cuda.stream(self.s_main):
             self.loss_host[slot: slot + 1].copy_(self.loss_log[slot: slot + 1], non_blocking=True)
         return slot
 
+    def _raise_if_bad(self):
+        bad = int(self.n_bad.item())
+        if bad:
+            raise ValueError("GloveTrainer: %d ids outside [0, %d) in a submitted batch; the table may be corrupted "
+                             "(XLA would clamp the gather and drop the scatter -- wikipedia/models.py:31-34)" % (bad, self.table.V))
+
     def synchronize(self):
-        self.s_side.synchronize()
-        self.s_main.synchronize()
+        if self.pipe is not None:
+            L.check(L.lib().esr_pipeline_sync(self.pipe), "esr_pipeline_sync")
+        else:
+            self.s_copy.synchronize()
+            self.s_side.synchronize()
+            self.s_main.synchronize()
+        if self._bad_pending:
+            self._bad_pending = False
+            self._raise_if_bad()
 
     def losses(self, first, last):
         """Losses of steps [first, last) as NumPy (synchronises)."""

@@ -89,14 +89,16 @@ class CooccurrenceGenerator:
         """(:94-107) ``x = [token1 int32 (B,), token2 int32 (B,)]``, ``y = float32 (B,)``.  With ``shuffle_size`` the
         stream is shuffled in windows of that many triples (vectorised; the reference shuffles a Python list)."""
         rng = rng if rng is not None else np.random.default_rng()
-        pend_i, pend_j, pend_c, have = [], [], [], 0
         window = max(int(shuffle_size), batch_size)
+        # one owned buffer per column plus a cursor: a decoded block is appended once (the unread tail, shorter than a
+        # window, is the only thing re-copied), and windows are sliced by offset -- O(triples), not O(triples * batches)
+        bi = np.empty(0, np.int32); bj = np.empty(0, np.int32); bc = np.empty(0, np.float32)
+        pos = 0
         for i, j, c in self.get_arrays():
-            pend_i.append(i); pend_j.append(j); pend_c.append(c)
-            have += i.size
-            while have >= window:
-                ai, aj, ac = np.concatenate(pend_i), np.concatenate(pend_j), np.concatenate(pend_c)
-                wi, wj, wc = ai[:window], aj[:window], ac[:window]
+            bi = np.concatenate([bi[pos:], i]); bj = np.concatenate([bj[pos:], j]); bc = np.concatenate([bc[pos:], c])
+            pos = 0
+            while bi.size - pos >= window:
+                wi, wj, wc = bi[pos:pos + window], bj[pos:pos + window], bc[pos:pos + window]
                 if shuffle_size:
                     perm = rng.permutation(window)
                     wi, wj, wc = wi[perm], wj[perm], wc[perm]
@@ -105,10 +107,12 @@ class CooccurrenceGenerator:
                     s = slice(b * batch_size, (b + 1) * batch_size)
                     yield [wi[s].copy(), wj[s].copy()], wc[s].copy()
                 used = nb * batch_size
-                # the unshuffled remainder of the window goes back in front of the stream
-                pend_i, pend_j, pend_c = [np.concatenate([wi[used:], ai[window:]])], [np.concatenate([wj[used:], aj[window:]])], \
-                    [np.concatenate([wc[used:], ac[window:]])]
-                have = pend_i[0].size
+                if shuffle_size and used < window:
+                    # the (shuffled) remainder of the window goes back in front of the stream
+                    bi[pos + used:pos + window] = wi[used:]
+                    bj[pos + used:pos + window] = wj[used:]
+                    bc[pos + used:pos + window] = wc[used:]
+                pos += used
 
 
 # ---- writer (tests, synthetic corpora): the exact bytes Spark's saveAsTextFile + BZip2Codec part holds ----

@@ -163,10 +163,15 @@ class TokenDictionary:
 
     def get_token_from_embedding_index(self, embedding_index):
         """Inverse of get_embedding_index for printing (:111-118), the reference's bucket label included (it subtracts
-        the bucket-range width, not the dictionary size)."""
-        row = int(embedding_index)
-        if row == 0:
+        the bucket-range width, not the dictionary size).
+
+        The reference tests ``embedding_index is 0`` (:112), which only holds for a Python ``int`` zero; the NumPy / jax
+        scalars its dump_knn passes (train_cooccurence.py:118-123) fall through to ``get_token(0 - 1)``, i.e. row 0 prints
+        as the LAST dictionary token.  Reproduced as is, so logged neighbour lines match the reference's verbatim even
+        when the (untrained) mask row reaches a top-10."""
+        if type(embedding_index) is int and embedding_index == 0:
             return "NULL"
+        row = int(embedding_index)
         if row <= self.get_dictionary_size():
             return self._words[row - 1]
         return "MINHASH %d" % (row - _HASH_SPACE - 1)

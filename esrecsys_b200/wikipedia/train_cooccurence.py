@@ -20,7 +20,7 @@ _cache = {}
 
 
 def _workspace(table, B, bias_mode):
-    key = (table.rows0.data_ptr(), B, bias_mode)
+    key = (table.rows0.data_ptr(), table.bias.data_ptr(), table.V, table.D, B, bias_mode)
     if key not in _cache:
         _cache.clear()
         _cache[key] = (engine.IndexPlan(2 * B, table.V, table.device),
@@ -37,7 +37,12 @@ def apply_model(state: TrainState, inputs, target, bias_mode="reference_broadcas
     ids = ids.reshape(-1).contiguous()
     B = ids.numel() // 2
     target = torch.as_tensor(target).to(table.device, torch.float32).contiguous()
+    fresh = (table.rows0.data_ptr(), table.bias.data_ptr(), table.V, table.D, B, bias_mode) not in _cache
     plan, step = _workspace(table, B, bias_mode)
+    if fresh and engine.check_ids(ids, table.V):
+        # XLA clamps an out-of-range gather and drops the scatter (wikipedia/models.py:31-34); here ids are raw row
+        # offsets, so the first batch of every (table, B) workspace is validated instead of corrupting memory
+        raise ValueError("apply_model: ids outside [0, %d)" % table.V)
     plan.build(ids)
     sc = step.run(plan, target)
     loss = sc[L.SC_LOSS].clone()
@@ -60,16 +65,19 @@ def find_knn(model: Glove, params, token):
 
 
 def dump_knn(model: Glove, params, tokens, token_dictionary=None, k=10):
-    """train_cooccurence.py:114-126: the k nearest neighbours of each query token, read from the tail of the
-    ascending argsort.  Returns ``[(query, [(neighbour, score), ...]), ...]`` (the reference logs them)."""
-    scores, indices = find_knn(model, params, tokens)
-    name = (lambda t: token_dictionary.get_token_from_embedding_index(t)) if token_dictionary is not None else int
-    V = scores.shape[0]
-    tail = indices[V - k:].flip(0).cpu().numpy()                    # (k, T): indices[-j-1][i]
-    sc = scores.cpu().numpy()
+    """train_cooccurence.py:114-126: the k nearest neighbours of each query token.  The reference reads them from the
+    tail of the ascending stable argsort of the (V, T) score matrix (ties therefore come out HIGHER index first); here
+    one fused table scan keeps the running top-k per query (``esr_topk_scan_f32``: no score matrix, no sort of V keys).
+    Returns ``[(query, [(neighbour, score), ...]), ...]`` (the reference logs them)."""
+    t = model.table(params)
+    tok = torch.as_tensor(np.asarray(tokens) if not torch.is_tensor(tokens) else tokens).to(t.device, torch.int32).reshape(-1)
+    val, idx = engine.table_topk(t, t.gather(tok), k, ties_high_index_first=True)          # (T, k) best first
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    # ids reach the dictionary as NumPy scalars, as the reference's jax scalars do (its ``is 0`` test never fires for them)
+    name = (lambda t: token_dictionary.get_token_from_embedding_index(np.int32(t))) if token_dictionary is not None else int
     out = []
-    for i, token in enumerate(np.asarray(tokens).reshape(-1)):
-        out.append((name(int(token)), [(name(int(tail[j, i])), float(sc[tail[j, i], i])) for j in range(k)]))
+    for i, token in enumerate(np.asarray(tok.cpu()).reshape(-1)):
+        out.append((name(int(token)), [(name(int(idx[i, j])), float(val[i, j])) for j in range(k)]))
     return out
 
 

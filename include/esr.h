@@ -40,7 +40,8 @@ enum {
   ESR_EINVAL = -1,     /* bad shape / alignment / null pointer / unknown enum */
   ESR_EWORKSPACE = -2, /* workspace smaller than esr_*_workspace_bytes() */
   ESR_ECUDA = -3,      /* a CUDA call or launch failed; see esr_last_cuda_error() */
-  ESR_ENOTSUP = -4     /* valid request this build does not implement */
+  ESR_ENOTSUP = -4,    /* valid request this build does not implement */
+  ESR_ENOMEM = -5      /* a host decoder could not grow its line buffer (row valid, allocation failed) */
 };
 
 enum { ESR_OPT_ADAGRAD = 0, ESR_OPT_ADAM = 1, ESR_OPT_SGDM = 2 };
@@ -96,6 +97,43 @@ int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float*
 size_t esr_sort_cols_workspace_bytes(int64_t V);
 int esr_sort_cols_f32(const float* scores, int64_t V, int32_t T, int32_t descending, int64_t k, int32_t* out_idx,
                       float* out_val, void* ws, size_t ws_bytes, esr_stream_t stream);
+/* Fused retrieval (csrc/topk_scan.cu): one streaming pass over N candidate rows scores them against T queries and keeps
+ * the running top-k per list in shared memory -- no (N, T) score matrix, no sort of N keys.  Candidate row n is
+ * rows_a[(idx_a ? idx_a[n] : n) % mod_a] (mod_a == 0: no modulus; rows_a1 / ver: the double-buffered EsrTable form)
+ * optionally concatenated with rows_b[idx_b[n]].
+ *   max_over_queries == 0 : T lists, score_t(n) = row_n . queries[t]
+ *       dump_knn (wikipedia/train_cooccurence.py:114-126; ties_high_index_first = 1: the tail of a stable ascending argsort),
+ *       find_top_k (pinterest/make_recommendations.py:49-65; jax.lax.top_k, ties lower index first);
+ *   max_over_queries == 1 : ONE list, score(n) = max_t(row_n . queries[t]) + boost * [idx_a[n] in ctx_a] + boost *
+ *       [idx_b[n] in ctx_b] -- the neg_affinity of eval_step (spotify/models.py:78-80 with album_embed[album % 100000]
+ *       and raw-id isin; spotify/train_spotify.py:113-131, top 500 of 2.26 M tracks).
+ * out_idx[l * k + r] / out_val[l * k + r] = row / score of rank r of list l, best first (out_val may be NULL).
+ * k <= 1024, T <= 64, (Da + Db) <= 512; ESR_ENOTSUP when the lists do not fit shared memory. */
+typedef struct EsrTopkCfg {
+  uint32_t struct_size;
+  int32_t T;                /* queries */
+  const float* rows_a;      /* [Va][Da] */
+  const float* rows_a1;     /* second row buffer of an EsrTable, or NULL */
+  const uint8_t* ver;       /* EsrTable.ver, or NULL */
+  const float* rows_b;      /* [Vb][Db] or NULL */
+  const int32_t* idx_a;     /* [N] or NULL (identity) */
+  const int32_t* idx_b;     /* [N], required with rows_b */
+  const float* queries;     /* [T][Da + Db] */
+  const int32_t* ctx_a;     /* [n_ctx_a] raw ids compared with idx_a (max_over_queries only) */
+  const int32_t* ctx_b;     /* [n_ctx_b] raw ids compared with idx_b */
+  int64_t N;                /* candidate rows */
+  int32_t Da, Db;
+  int32_t mod_a;            /* row of A = idx_a[n] % mod_a when > 0 (spotify/models.py:37: album % 100000) */
+  int32_t max_over_queries;
+  int32_t n_ctx_a, n_ctx_b;
+  float boost;              /* 0.1 in the reference */
+  int32_t k;
+  int32_t ties_high_index_first;
+  int32_t reserved;
+} EsrTopkCfg;
+size_t esr_topk_workspace_bytes(int64_t N, int32_t D, int32_t T, int32_t max_over_queries, int32_t k);
+int esr_topk_scan_f32(const EsrTopkCfg* cfg, int32_t* out_idx, float* out_val, void* ws, size_t ws_bytes,
+                      esr_stream_t stream);
 /* out[k] = uniform integer in [0, hi), k < n, from a counter-based stream keyed by (seed, step, k): the on-device
  * replacement of sample_negative's jax.random.randint(key, [n], 0, N - 1) (spotify/train_spotify.py:139-150; pass
  * hi = N - 1: the reference's upper bound is exclusive).  Bit-exact contract: oracle.index.sample_uniform. */
@@ -123,6 +161,10 @@ typedef struct EsrPlan {
   int32_t* uniq;         /* [n_slots] capacity; first *n_uniq valid */
   int32_t* seg_off;      /* [n_slots+1] capacity; first *n_uniq+1 valid */
   int32_t* n_uniq;       /* device scalar */
+  const int32_t* n_valid; /* optional device scalar: number of REAL slots.  The row-sharded path builds its plan over a
+                           * fixed-capacity slot array whose padding carries a key larger than every row id, so it sorts
+                           * to the end; every consumer (plan, compact plan, prep, row pass, combine) then covers only the
+                           * first *n_valid sorted slots.  NULL: all n_slots are real. */
 } EsrPlan;
 
 size_t esr_plan_workspace_bytes(int64_t n_slots);
@@ -304,6 +346,30 @@ int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const EsrInbatchCfg
 int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out10);
 
 /* ------------------------------------------------------------------------------------------
+ * Native host runtime of the single-GPU training loop (csrc/pipeline.cu): the body of train_epoch
+ * (wikipedia/train_cooccurence.py:103-112) as ONE call per step -- stage the batch on a copy stream, replay the plan
+ * graph on a side stream and the step graph on the main stream, `depth` buffers in flight, events in between.
+ * The object owns its three streams; the caller's buffers (staging ids / counts per parity, the loss scalar, a device
+ * loss log, optionally a pinned host loss log) are registered once.  The stage graphs are captured from whatever the
+ * calling thread launches on the stage's stream between capture_begin and capture_end (which: 0 plan, 1 step).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct EsrPipeline EsrPipeline;
+int esr_pipeline_create(int32_t depth, int32_t main_high_priority, EsrPipeline** out);
+int esr_pipeline_streams(const EsrPipeline* p, esr_stream_t* copy, esr_stream_t* side, esr_stream_t* main_);
+int esr_pipeline_set_buffers(EsrPipeline* p, void* const* ids_dev, void* const* counts_dev, size_t ids_bytes,
+                             size_t counts_bytes, const float* loss_src, float* loss_log, int64_t loss_len,
+                             float* loss_host);
+int esr_pipeline_capture_begin(EsrPipeline* p, int32_t which);
+int esr_pipeline_capture_end(EsrPipeline* p, int32_t which, int32_t k);
+/* ids / counts: pinned host or device memory.  flags bit 0: also copy the step's loss to loss_host[step % loss_len]
+ * (asynchronously, main stream); bit 1: the inputs were produced on caller_stream (NULL = the legacy default stream),
+ * stage them behind it. */
+int esr_pipeline_submit(EsrPipeline* p, const void* ids, const void* counts, esr_stream_t caller_stream, int32_t flags,
+                        int64_t* step_out);
+int esr_pipeline_sync(const EsrPipeline* p);
+int esr_pipeline_destroy(EsrPipeline* p);
+
+/* ------------------------------------------------------------------------------------------
  * Row-sharded table over NVLink peer memory (device pointers of every rank's buffers, e.g. from a
  * symmetric-memory rendezvous; index = rank).  No host-known sizes, no NCCL on the data path; the
  * caller separates fetch / update phases with device barriers.  See csrc/peer_ops.cu.
@@ -347,8 +413,9 @@ int esr_peer_allreduce_f32(void* const* peer_sync, int32_t n_ranks, int32_t me, 
                            int32_t count, uint32_t* seq_counter, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Native decoders of the reference's record formats (HOST pointers).  Re-entrant,
- * allocation-free; a negative return is an ESR_E* code.
+ * Native decoders of the reference's record formats (HOST pointers).  Re-entrant;
+ * allocation-free except for CooccurrenceRow lines longer than 16 KB decoded (heap line buffer, any
+ * --max_row_size); a negative return is an ESR_E* code.
  * ------------------------------------------------------------------------------------------ */
 /* Text of a *.cooccur.pb.b64 part after bz2 decompression: one base64 line per CooccurrenceRow
  * {1: index, 2: packed other_index, 3: packed float count}.  Writes the (i, j, count) triples in the order
@@ -362,6 +429,24 @@ int64_t esr_decode_cooccur_b64(const char* text, size_t n_bytes, int32_t* out_i,
 int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes, int32_t n_keys, const char* const* keys,
                                   int64_t* const* vals, const int64_t* val_cap, int64_t* const* offs,
                                   int64_t max_records, size_t* consumed);
+
+/* OWNER-COMPUTES pair routing (csrc/peer_ops.cu): a pair (i, j, x) is processed by the rank owning row i, so only the
+ * unique partner rows j cross NVLink (4.3x fewer bytes on the bench stream at 8 ranks than keeping the pairs where they
+ * arrived).  esr_peer_route_pairs_i32 (source side; depends on the ids only) partitions the (2,B) batch STABLY by
+ * owner(i) = i % n straight into the owners' pair inboxes: peer_pair_ids[o] -> int32 [n][2][B] (region of source `me`:
+ * its i then its j), peer_pair_cnt[o] -> f32 [n][B], peer_pair_counts[o] -> int32 [n] (entry `me` = pairs I send to o);
+ * my_counts[o] = the same numbers locally.  After a device barrier, esr_peer_collect_pairs_i32 (owner side) concatenates
+ * the regions in source order into keys[2 * B_cap] ([i ; j] halves of capacity B_cap, padding = pad_key, which must
+ * exceed every row id so that it sorts to the end), counts[B_cap] and *n_valid = 2 m for EsrPlan.n_valid;
+ * err |= 2 if m > B_cap (the excess pairs are dropped: the caller must treat it as fatal).
+ * Bit-exact contract: oracle/index.py route_pairs / collect_pairs. */
+size_t esr_peer_route_pairs_workspace_bytes(int64_t B);
+int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts, int64_t B, int32_t n_ranks, int32_t me,
+                             void* const* peer_pair_ids, void* const* peer_pair_cnt, void* const* peer_pair_counts,
+                             int32_t* my_counts, void* ws, size_t ws_bytes, esr_stream_t stream);
+int esr_peer_collect_pairs_i32(const int32_t* in_ids, const float* in_cnt, const int32_t* in_counts, int32_t n_ranks,
+                               int64_t B, int64_t B_cap, int32_t pad_key, int32_t* keys, float* counts, int32_t* n_valid,
+                               int32_t* err, esr_stream_t stream);
 
 /* The two halves of esr_peer_merge_adagrad_f32: resolve depends on the ids only (side stream, overlaps the row
  * pass); apply needs the gradients (after the device barrier). */

@@ -195,3 +195,43 @@ def sample_uniform(seed, step, n, hi):
         r = _splitmix64((base + k) & m)
         out[k] = ((r >> 32) * hi) >> 32
     return out
+
+
+# ---- owner-computes pair routing (esr_peer_route_pairs_i32 / esr_peer_collect_pairs_i32, csrc/peer_ops.cu) ---------------
+def route_pairs(ids, counts, n: int):
+    """Source side.  ``ids`` int32 (2, B) = [i ; j] (wikipedia/cooccurrence_matrix.py:103-114), ``counts`` f32 (B,).
+    Stable partition of the pairs by owner(i) = i % n.  Returns ``(per_owner, send_counts)`` with
+    ``per_owner[o] = (i, j, x)`` arrays in original pair order and ``send_counts[o] = len``."""
+    ids = np.asarray(ids, np.int32)
+    counts = np.asarray(counts, np.float32)
+    own = ids[0].astype(np.int64) % n
+    per_owner, send_counts = [], np.zeros(n, np.int32)
+    for o in range(n):
+        m = own == o                                  # boolean mask keeps the original order: stable
+        per_owner.append((ids[0][m].copy(), ids[1][m].copy(), counts[m].copy()))
+        send_counts[o] = int(m.sum())
+    return per_owner, send_counts
+
+
+def collect_pairs(regions, B_cap: int, pad_key: int):
+    """Owner side.  ``regions[s] = (i, j, x)`` received from source s; concatenated in SOURCE order into the flat
+    [i ; j] key array of capacity 2 * B_cap (padding = pad_key), the counts (padding 0) and n_valid = 2 m.
+    Returns ``(keys, counts, n_valid, overflow)``."""
+    gi = np.concatenate([np.asarray(r[0], np.int32) for r in regions])
+    gj = np.concatenate([np.asarray(r[1], np.int32) for r in regions])
+    gx = np.concatenate([np.asarray(r[2], np.float32) for r in regions])
+    m_all = gi.size
+    m = min(m_all, B_cap)
+    keys = np.full(2 * B_cap, pad_key, np.int32)
+    cnt = np.zeros(B_cap, np.float32)
+    keys[:m] = gi[:m]
+    keys[B_cap:B_cap + m] = gj[:m]
+    cnt[:m] = gx[:m]
+    return keys, cnt, 2 * m, m_all > B_cap
+
+
+def routed_batches(ids_per_rank, counts_per_rank, n: int):
+    """The batch every owner processes after routing: ``out[o] = (i, j, x)`` = pairs of ALL ranks whose row i lives on
+    o, source-major, original order inside a source.  The union over o is the global batch (conservation)."""
+    routed = [route_pairs(ids_per_rank[r], counts_per_rank[r], n)[0] for r in range(n)]
+    return [tuple(np.concatenate([routed[s][o][k] for s in range(n)]) for k in range(3)) for o in range(n)]

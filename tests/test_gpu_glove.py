@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 ATOL = 1e-5
 # Row-pass variants under test (every one has run on a B200; "auto" is the default).
-IMPLS = ["auto", "ldg", "tma", "fifo"]
+IMPLS = ["auto", "ldg", "tma", "fifo", "endfirst"]
 
 
 def _engine():

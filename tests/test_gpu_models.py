@@ -201,6 +201,49 @@ def test_find_knn_matches_oracle_with_ties():
     assert knn[0][0] == 7 and len(knn[0][1]) == 10 and {knn[0][1][j][0] for j in range(3)} == {7, 100, 2000}
 
 
+@pytest.mark.parametrize("V,D,T,k", [(50001, 128, 8, 10), (300, 64, 3, 10), (20000, 32, 1, 1024), (7000, 256, 64, 5),
+                                     (2262, 128, 2, 500)])
+def test_fused_topk_scan_matches_oracle_both_tie_orders(V, D, T, k):
+    """esr_topk_scan_f32 (one table pass, running top-k in shared memory) against the full-sort restatements:
+    oracle.glove.top_k = tail of the stable ascending argsort (dump_knn: ties HIGHER index first) and
+    jax.lax.top_k order (ties LOWER index first), duplicates planted across CTA slabs."""
+    from esrecsys_b200 import engine
+    rng = np.random.default_rng(V + k)
+    E = (rng.standard_normal((V, D)) / np.sqrt(D)).astype(np.float32)
+    for dst, src in ((V - 1, 3), (V // 2, 3), (V // 3, 5), (11, 5)):
+        E[dst] = E[src]                                   # exact ties, far apart
+    tokens = np.concatenate([[3, 5], rng.integers(0, V, T)])[:T].astype(np.int32)
+    table = engine.EmbeddingTable.from_dense(E, np.zeros(V, np.float32), sparse=(V % 2 == 1))
+    q = torch.from_numpy(E[tokens]).cuda()
+    sc64 = E.astype(np.float64) @ E[tokens].astype(np.float64).T            # (V, T)
+    for high_first in (True, False):
+        val, idx = engine.table_topk(table, q, k, ties_high_index_first=high_first)
+        val, idx = _np(val), _np(idx)
+        assert idx.shape == (T, k)
+        for t in range(T):
+            dev_sc = sc64[:, t]
+            # the kernel's own scores order its list exactly: strictly by (score desc, index per the tie rule)
+            assert len(set(idx[t].tolist())) == k
+            v = val[t]
+            assert np.all(v[:-1] >= v[1:])
+            ties = v[:-1] == v[1:]
+            if ties.any():
+                d = np.diff(idx[t].astype(np.int64))[ties]
+                assert np.all(d < 0) if high_first else np.all(d > 0)
+            np.testing.assert_allclose(v, dev_sc[idx[t]], rtol=RTOL, atol=ATOL)
+            # membership: everything clearly above the k-th oracle score is present
+            kth = np.sort(dev_sc)[-k]
+            must = np.flatnonzero(dev_sc > kth + 1e-5)
+            assert set(must.tolist()) <= set(idx[t].tolist())
+    # the planted exact ties at the very top of query 0 (token 3): order is the reference's, bit for bit
+    top, _ = og.top_k(E, tokens[:1], 3)                                      # tail of the stable argsort
+    assert top[0].tolist() == [V - 1, V // 2, 3]
+    _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=True)
+    assert _np(idx)[0][:3].tolist() == [V - 1, V // 2, 3]
+    _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=False)       # jax.lax.top_k order
+    assert _np(idx)[0][:3].tolist() == [3, V // 2, V - 1]
+
+
 def test_spotify_eval_step_matches_oracle():
     from esrecsys_b200.spotify.train_spotify import eval_step
     model, params = _spotify_setup(F=32, VA=1000, VR=3000)

@@ -24,7 +24,7 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from esrecsys_b200 import synth
-        from esrecsys_b200.sharded import PeerShardedGloveTrainer, ShardedGloveTrainer
+        from esrecsys_b200.sharded import OwnerRoutedGloveTrainer, PeerShardedGloveTrainer, ShardedGloveTrainer
         from oracle import glove as og
         from oracle import optim as oopt
         E, b = synth.init_glove_tables(V, D, 0)
@@ -33,7 +33,10 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
         # experimental switches of the peer path: libesr peer all-reduce / barrier kernels; id phases on a side stream
         kw = {"fast": {"fast_sync": True}, "overlap": {"overlap_ids": True},
               "fast_overlap": {"fast_sync": True, "overlap_ids": True}}.get(peer, {})
-        tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode, **kw)
+        if peer == "routed":    # owner-computes pair routing (bench default for N > 1); CUDA graphs from step 4 on
+            tr = OwnerRoutedGloveTrainer(V, D, B_loc, lr=0.05, bias_mode=bias_mode)
+        else:
+            tr = (PeerShardedGloveTrainer if peer else ShardedGloveTrainer)(V, D, B_loc, lr=0.05, bias_mode=bias_mode, **kw)
         tr.load_dense(E, b)
         Eo, bo = E.copy(), b.copy()
         aE, ab = np.full_like(Eo, oopt.ADAGRAD_INIT_ACC), np.full_like(bo, oopt.ADAGRAD_INIT_ACC)
@@ -54,9 +57,8 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("peer", [False, True] + (["fast", "overlap", "fast_overlap"] if os.environ.get("ESR_TEST_EXPERIMENTAL") else []),
-                         ids=["nccl_a2a", "peer_memory"] + (["peer_fast_sync", "peer_overlap_ids", "peer_fast_sync_overlap_ids"]
-                                                            if os.environ.get("ESR_TEST_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("peer", [False, True, "fast_overlap", "routed"],
+                         ids=["nccl_a2a", "peer_memory", "peer_fast_sync_overlap_ids", "owner_routed_graphs"])
 @pytest.mark.parametrize("bias_mode", ["reference_broadcast", "per_pair"])
 @pytest.mark.parametrize("V,D,B_loc", [(5000, 64, 1024), (300, 128, 512)])
 def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode, peer):
@@ -64,7 +66,8 @@ def test_sharded_matches_single_table_oracle(V, D, B_loc, bias_mode, peer):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 200) + (V % 7) + (50 if peer else 0)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, V, D, B_loc, 3, bias_mode, q, peer)) for r in range(world)]
+    steps = 7 if peer == "routed" else 3        # the routed trainer captures its CUDA graphs before step 4
+    procs = [ctx.Process(target=_worker, args=(r, world, port, V, D, B_loc, steps, bias_mode, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=500) for _ in procs]

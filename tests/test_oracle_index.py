@@ -131,3 +131,34 @@ def test_peer_scatter_merge_conserves_every_gradient():
                 seen.add(g)
             assert (desc[~own] == -1).all()
         assert seen == set(expect)
+
+
+def test_route_pairs_hand_case_and_conservation():
+    """Owner-computes pair routing (oracle side of esr_peer_route_pairs_i32 / esr_peer_collect_pairs_i32)."""
+    ids = np.array([[5, 4, 9, 2, 7, 4], [1, 3, 2, 1, 6, 0]], np.int32)
+    x = np.array([.5, 1., 2., 4., 8., 16.], np.float32)
+    per, sc = oidx.route_pairs(ids, x, 2)                        # owner = i % 2
+    assert sc.tolist() == [3, 3]
+    assert per[0][0].tolist() == [4, 2, 4] and per[0][1].tolist() == [3, 1, 0] and per[0][2].tolist() == [1., 4., 16.]
+    assert per[1][0].tolist() == [5, 9, 7] and per[1][1].tolist() == [1, 2, 6] and per[1][2].tolist() == [.5, 2., 8.]
+    keys, cnt, nv, over = oidx.collect_pairs([per[0], per[1]], 8, 100)
+    assert nv == 12 and not over
+    assert keys.tolist() == [4, 2, 4, 5, 9, 7, 100, 100] + [3, 1, 0, 1, 2, 6, 100, 100]
+    assert cnt.tolist() == [1., 4., 16., .5, 2., 8., 0., 0.]
+    keys, cnt, nv, over = oidx.collect_pairs([per[0], per[1]], 4, 100)
+    assert nv == 8 and over and keys.tolist() == [4, 2, 4, 5, 3, 1, 0, 1]
+    # conservation over n ranks: the routed batches are a permutation of the global batch, every i on its owner
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 8):
+        B = 257
+        idr = [rng.integers(1, 5000, (2, B)).astype(np.int32) for _ in range(n)]
+        xr = [rng.random(B).astype(np.float32) for _ in range(n)]
+        out = oidx.routed_batches(idr, xr, n)
+        assert sum(o[0].size for o in out) == n * B
+        for o, (i, j, c) in enumerate(out):
+            assert (i % n == o).all()
+        got = sorted(zip(np.concatenate([o[0] for o in out]).tolist(), np.concatenate([o[1] for o in out]).tolist(),
+                         np.concatenate([o[2] for o in out]).tolist()))
+        want = sorted(zip(np.concatenate([a[0] for a in idr]).tolist(), np.concatenate([a[1] for a in idr]).tolist(),
+                          np.concatenate(xr).tolist()))
+        assert got == want

@@ -52,6 +52,15 @@ def test_cooccur_resume_small_cap_and_partial_line():
     assert i.tolist() == [7, 7] and j.tolist() == [1, 2] and c.tolist() == [1.5, 2.5]
     with pytest.raises(L.EsrError):
         cm.decode_text(b"!!!not base64!!!\n")
+    # a row far beyond the reference's default --max_row_size (wikipedia/make_cooccurrence.py:87) with 5-byte varints:
+    # > 16 KB decoded, which the reference's reader parses fine -- so must we (heap line buffer, no length limit)
+    big_j = [(1 << 30) + k for k in range(6000)]
+    big_c = [float(k % 97) * 0.25 for k in range(6000)]
+    line = base64.b64encode(cm.encode_row(123456, big_j, big_c)) + b"\n"
+    assert len(line) > 3 * 16384
+    i, j, c, used = cm.decode_text(line + base64.b64encode(cm.encode_row(2, [1], [0.5])) + b"\n", cap=8000)
+    assert used == len(line) + 17 and i.tolist() == [123456] * 6000 + [2]
+    assert j[:6000].tolist() == big_j and c[:6000].tolist() == big_c
 
 
 def test_generator_batches(tmp_path):
@@ -131,6 +140,10 @@ def test_token_dictionary_matches_reference_golden():
     for i, name in want["from_embedding_index"].items():
         assert td.get_token_from_embedding_index(int(i)) == name
     assert td.get_token_from_embedding_index(0) == "NULL" and td.get_doc_frequency(3) == 497
+    # the reference's ``embedding_index is 0`` (token_dictionary.py:112) is False for the NumPy / jax scalars dump_knn passes:
+    # row 0 then prints as get_token(-1), the last dictionary token -- mirrored, so logged neighbour lines stay verbatim
+    assert td.get_token_from_embedding_index(np.int32(0)) == td.get_token(td.get_dictionary_size() - 1)
+    assert td.get_token_from_embedding_index(np.int64(1)) == td.get_token(0)
     # writer round trip (proto3: zero / empty fields are omitted)
     msg = encode_token_stat(token="naïve", url="", frequency=7, doc_frequency=0, index=3)
     assert parse_token_stat(msg) == {"token": "naïve", "url": "", "frequency": 7, "doc_frequency": 0, "index": 3}

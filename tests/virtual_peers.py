@@ -17,7 +17,7 @@ import torch
 
 from esrecsys_b200 import _lib as L
 from esrecsys_b200.engine import EmbeddingTable, GloveStep, IndexPlan
-from esrecsys_b200.sharded import LibesrOps, shard_rows
+from esrecsys_b200.sharded import LibesrOps, pair_capacity, shard_rows
 
 
 def _ptr_array(tensors):
@@ -29,12 +29,15 @@ class _Rank:
 
 
 class VirtualPeerGlove:
-    def __init__(self, V, D, B_local, n_ranks, lr=0.05, bias_mode="reference_broadcast", device="cuda"):
+    def __init__(self, V, D, B_local, n_ranks, lr=0.05, bias_mode="reference_broadcast", device="cuda", B_cap=None):
+        """``B_cap``: owner-computes routing (VirtualOwnerRoutedGlove) -- the step runs over a padded slot array of capacity
+        2 * B_cap whose real length is only known on the device (EsrPlan.n_valid)."""
         L.require_cuda()
         assert 1 <= n_ranks <= 8
         self.V, self.D, self.B, self.n, self.lr = int(V), int(D), int(B_local), int(n_ranks), float(lr)
         self.dev = torch.device(device)
-        n, n_slots = self.n, 2 * self.B
+        self.B_cap = int(B_cap) if B_cap is not None else None
+        n, n_slots = self.n, 2 * (self.B_cap if B_cap is not None else self.B)
         i32 = dict(dtype=torch.int32, device=self.dev)
         V_max = shard_rows(V, 0, n)
         self.inbox_cap = n_slots * n
@@ -55,9 +58,10 @@ class VirtualPeerGlove:
             k.inbox_db = torch.zeros(self.inbox_cap, device=self.dev)
             k.emit_map = torch.zeros(n_slots, **i32)
             k.err = torch.zeros(1, **i32)
-            k.plan = IndexPlan(n_slots, V, self.dev)
+            k.n_valid = torch.zeros(1, **i32) if B_cap is not None else None
+            k.plan = IndexPlan(n_slots, V + (1 if B_cap is not None else 0), self.dev, n_valid=k.n_valid)   # pad key = V
             k.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
-            k.cplan = IndexPlan(n_slots, n_slots, self.dev)
+            k.cplan = IndexPlan(n_slots, n_slots, self.dev, n_valid=k.n_valid)
             cs, ps = k.cplan.s, k.plan.s
             cs.n_slots = n_slots
             cs.perm, cs.useg, cs.seg_off, cs.n_uniq = ps.perm, ps.useg, ps.seg_off, ps.n_uniq
@@ -75,8 +79,8 @@ class VirtualPeerGlove:
         self.p_inbox_dE = _ptr_array([k.inbox_dE for k in self.ranks])
         self.p_inbox_db = _ptr_array([k.inbox_db for k in self.ranks])
         for k in self.ranks:
-            k.step_fn = GloveStep(k.compact, self.B, lr=lr, bias_mode=bias_mode, emit_grads=True, B_global=self.B * n,
-                                  dE=k.inbox_dE, db=k.inbox_db)
+            k.step_fn = GloveStep(k.compact, self.B_cap if B_cap is not None else self.B, lr=lr, bias_mode=bias_mode,
+                                  emit_grads=True, B_global=self.B * n, dE=k.inbox_dE, db=k.inbox_db)
             cfg = k.step_fn.cfg
             cfg.emit_map = L.ptr(k.emit_map)
             cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
@@ -157,6 +161,61 @@ class VirtualPeerGlove:
         """ids[r]: int32 (2, B_local) global rows of virtual rank r; counts[r]: f32 (B_local,).  Returns the GLOBAL loss."""
         self.plan_phase(ids)
         self.fetch_phase(counts)
+        self.resolve_phase()
+        self.rows_phase()
+        self.apply_phase()
+        self.loss = self.ranks[0].step_fn.scalars[L.SC_LOSS].clone()
+        return self.loss
+
+
+class VirtualOwnerRoutedGlove(VirtualPeerGlove):
+    """OwnerRoutedGloveTrainer (esrecsys_b200/sharded.py) with N virtual ranks on one GPU: the pairs are first routed to
+    the rank owning row i (esr_peer_route_pairs_i32 -> esr_peer_collect_pairs_i32), then the step runs exactly as in
+    VirtualPeerGlove over each rank's RECEIVED pairs (padded capacity, device-side slot count)."""
+
+    def __init__(self, V, D, B_local, n_ranks, lr=0.05, bias_mode="reference_broadcast", device="cuda", pair_cap=None):
+        cap = int(pair_cap) if pair_cap is not None else pair_capacity(B_local, n_ranks)
+        super().__init__(V, D, B_local, n_ranks, lr=lr, bias_mode=bias_mode, device=device, B_cap=cap)
+        n, B = self.n, self.B
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        for k in self.ranks:
+            k.pin_ids = torch.zeros(n, 2, B, **i32)
+            k.pin_cnt = torch.zeros(n, B, dtype=torch.float32, device=self.dev)
+            k.pin_counts = torch.zeros(16, **i32)
+            k.my_counts = torch.zeros(16, **i32)
+            k.keys = torch.full((2 * cap,), V, **i32)
+            k.cnt_l = torch.zeros(cap, dtype=torch.float32, device=self.dev)
+            k.route_ws = torch.empty(int(L.lib().esr_peer_route_pairs_workspace_bytes(B)), dtype=torch.uint8, device=self.dev)
+        self.p_pin_ids = _ptr_array([k.pin_ids for k in self.ranks])
+        self.p_pin_cnt = _ptr_array([k.pin_cnt for k in self.ranks])
+        self.p_pin_counts = _ptr_array([k.pin_counts for k in self.ranks])
+
+    def route_phase(self, ids, counts):
+        lib, n, sp = L.lib(), self.n, L.stream_ptr()
+        for r, k in enumerate(self.ranks):
+            k.ids_dev = ids[r].to(self.dev).reshape(-1).contiguous()
+            k.cnt_dev = counts[r].to(self.dev).contiguous()
+            L.check(lib.esr_peer_route_pairs_i32(L.ptr(k.ids_dev), L.ptr(k.cnt_dev), self.B, n, r, self.p_pin_ids,
+                                                 self.p_pin_cnt, self.p_pin_counts, L.ptr(k.my_counts), L.ptr(k.route_ws),
+                                                 k.route_ws.numel(), sp), "esr_peer_route_pairs_i32")
+        for k in self.ranks:                                      # (side-stream barrier here in the product)
+            L.check(lib.esr_peer_collect_pairs_i32(L.ptr(k.pin_ids), L.ptr(k.pin_cnt), L.ptr(k.pin_counts), n, self.B,
+                                                   self.B_cap, self.V, L.ptr(k.keys), L.ptr(k.cnt_l), L.ptr(k.n_valid),
+                                                   L.ptr(k.err), sp), "esr_peer_collect_pairs_i32")
+
+    def plan_phase(self, ids=None):
+        lib = L.lib()
+        for k in self.ranks:
+            k.plan.build(k.keys)
+            self.ops.route_plan(k.plan.uniq, k.plan.n_uniq, self.n, out=(k.order, k.send_local, k.counts, k.inv_order))
+            k.cplan.s.n_slots = k.plan.n_slots
+            L.check(lib.esr_plan_compact_i32(C.byref(k.plan.s), L.ptr(k.cplan.sorted_keys), L.ptr(k.cplan.partner),
+                                             L.ptr(k.cplan.uniq), L.ptr(k.scratch), L.stream_ptr()), "esr_plan_compact_i32")
+
+    def step(self, ids, counts):
+        self.route_phase(ids, counts)
+        self.plan_phase()
+        self.fetch_phase([k.cnt_l for k in self.ranks])
         self.resolve_phase()
         self.rows_phase()
         self.apply_phase()
