@@ -269,6 +269,8 @@ def make_sharded_trainer(a, V, D, B):
     from esrecsys_b200.sharded import OwnerRoutedGloveTrainer, PeerShardedGloveTrainer, ShardedGloveTrainer
     if a.exchange == "routed":
         kw = {"impl": a.kernel} if a.kernel != "auto" else {}
+        if a.row_blocks >= 0:
+            kw["row_blocks"] = a.row_blocks
         return OwnerRoutedGloveTrainer(V, D, B, lr=a.lr, **kw)
     if a.exchange == "peer":
         kw = {"fast_sync": a.fast_sync, "graphs": a.step_graphs, "overlap_ids": a.overlap_ids}
@@ -401,12 +403,76 @@ def run_sharded(a, rank, world, local):
                                                "on the wire"}}
     del tr
     torch.cuda.empty_cache()
+    wd = Watchdog(line, rank, 420.0)
     if not a.no_table_100m:
+        wd.pending = "table_100m"
         line["table_100m"] = guarded(lambda: table_100m_leg(a, rank, world), "table_100m")
+    if not a.no_inbatch:
+        wd.pending = "inbatch_sharded"
+        line["inbatch_sharded"] = guarded(lambda: inbatch_sharded_leg(a, rank, world), "inbatch_sharded")
+    wd.pending = None
+    wd.cancel()
     if rank == 0:
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+class Watchdog:
+    """Sub-records (100M-row table, sharded in-batch trainers) run AFTER the headline numbers are final.  If one of them
+    hangs (a collective that never completes), every rank leaves on its own after ``deadline_s``: rank 0 prints the line it
+    has -- the sub-record marked as timed out -- so the headline measurement is never lost with it."""
+
+    def __init__(self, line, rank, deadline_s):
+        self.line, self.rank, self.pending = line, rank, None
+        self.t = threading.Timer(deadline_s, self._fire)
+        self.t.daemon = True
+        self.t.start()
+
+    def _fire(self):  # pragma: no cover
+        if self.rank == 0:
+            if self.pending:
+                self.line[self.pending] = {"error": "timed out (watchdog); headline numbers above are unaffected"}
+            print(json.dumps(self.line), flush=True)
+        os._exit(0)
+
+    def cancel(self):
+        self.t.cancel()
+
+
+def inbatch_sharded_leg(a, rank, world):
+    """BASELINE configs[2] across the ranks: 2M-row x 128 table row-sharded (cyclic), GLOBAL in-batch batch 8192 (every
+    query scored against the items of all ranks: all-gather of K, tcgen05 scores, reduce-scatter of dK), hinge loss,
+    sparse Adagrad at the owners.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from esrecsys_b200 import synth
+    from esrecsys_b200.inbatch import ShardedSharedTableInBatch
+    V, D, Bg = 2_000_000, 128, 8192
+    B = Bg // world
+    tr = ShardedSharedTableInBatch(V, D, B, lr=0.05, loss="hinge")
+    tr.shard.rows0.normal_(0.0, 1.0 / D ** 0.25)
+    qs, ks = synth.pair_batches(V, V, Bg, 4, 5)
+    lo, hi = rank * B, (rank + 1) * B
+    batches = [torch.from_numpy(np.stack([qs[k][lo:hi], ks[k][lo:hi]])).cuda() for k in range(4)]
+    steps, warm = 20, 5
+    for k in range(warm):
+        tr.step(batches[k % 4])
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        loss = tr.step(batches[k % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"workload": "BASELINE configs[2]: 2M x 128 table row-sharded over %d GPUs, global in-batch B=8192, hinge" % world,
+            "ms_per_step": ms, "pairs_per_s": Bg / (ms * 1e-3), "final_loss": float(loss.item()),
+            "useful_tflops_all_ranks": 6.0 * Bg * Bg * D / (ms * 1e-3) / 1e12,
+            "exchange": "NCCL all-to-all of ids / rows / gradients + all-gather K + reduce-scatter dK"}
 
 
 def guarded(fn, name):
@@ -448,7 +514,7 @@ def table_100m_leg(a, rank, world):
     out.update({"ms_per_step": ms / steps, "pairs_per_s": world * B * steps / (ms * 1e-3),
                 "e2e_pairs_per_s": world * B * steps / (ms_e2e * 1e-3), "shard_gb": tr.shard.V * D * 4 / 1e9,
                 "final_loss": float(tr.loss.item()), "exchange": a.exchange})
-    if uniq_rows is not None and hasattr(tr, "plans"):
+    if uniq_rows is not None and hasattr(tr, "fetch_rows"):
         # the lookup alone (esr_peer_gather_f32 of the last step's unique rows), all ranks at once: NVLink GB/s per direction
         k = (tr.t - 1) % tr.DEPTH
         plan = tr.plans[k]
@@ -459,9 +525,10 @@ def table_100m_leg(a, rank, world):
             tr.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            L.check(L.lib().esr_peer_gather_f32(tr.p_rows, tr.p_bias, world, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
-                                                D, L.ptr(tr.compact.rows0), L.ptr(tr.compact.bias), L.stream_ptr()),
-                    "esr_peer_gather_f32")
+            pub = tr.pub[k]
+            L.check(L.lib().esr_peer_gather_remote_f32(tr.p_rows, tr.p_bias, world, tr.rank, L.ptr(plan.uniq), L.ptr(pub["order"]),
+                                                       L.ptr(pub["counts"]), plan.capacity, D, L.ptr(tr.fetch_rows),
+                                                       L.ptr(tr.fetch_bias), L.stream_ptr()), "esr_peer_gather_remote_f32")
             e1.record()
             torch.cuda.synchronize()
             if it >= 1:
@@ -541,6 +608,58 @@ def inbatch_leg(peaks):
                      "peak": peak, "frac": tf / peak, "dtype": "bf16 operands, f32 accumulate (tcgen05)",
                      "kernels_per_step": 4 if loss == "hinge" else 6}
         del sc
+    out.update(guarded(inbatch_trainer_steps, "inbatch_trainers"))
+    return out
+
+
+def inbatch_trainer_steps():
+    """The FULL trainer step of configs[2] / configs[3] at one GPU (not just the scorer): id gather -> [MLP towers] ->
+    tcgen05 B x B scores + loss + dQ / dK -> per-row gradient sums -> sparse Adagrad on the table(s) [+ Adam on the towers]."""
+    import torch
+    from esrecsys_b200 import engine, synth
+    from esrecsys_b200.inbatch import SharedTableInBatch, TwoTowerInBatch
+    out = {}
+
+    def timeit(fn, n=30):
+        for k in range(5):
+            fn(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n):
+            fn(k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    V, D, B = 2_000_000, 128, 8192
+    table = engine.EmbeddingTable(V, D, sparse=False, adagrad=True)
+    table.rows0.normal_(0.0, 1.0 / D ** 0.25)
+    qs, ks = synth.pair_batches(V, V, B, 4, 5)
+    ids = [torch.from_numpy(np.stack([qs[k], ks[k]])).cuda() for k in range(4)]
+    for loss in ("hinge", "softmax"):
+        tr = SharedTableInBatch(table, B, lr=0.05, loss=loss)
+        ms = timeit(lambda k: tr.step(ids[k % 4]))
+        out["spotify_inbatch_%s_TRAINER_step_V2M_D128_B8192" % loss] = {
+            "ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3), "useful_tflops": 6.0 * B * B * D / (ms * 1e-3) / 1e12,
+            "includes": "gather 2B rows, scores + loss + dQ/dK (tcgen05), segment sum of 2B gradient rows, sparse Adagrad"}
+        del tr
+    del table
+    torch.cuda.empty_cache()
+    V, D, B = 1_000_000, 256, 4096
+    ts = engine.EmbeddingTable(V, D, sparse=False, adagrad=True)
+    tp = engine.EmbeddingTable(V, D, sparse=False, adagrad=True)
+    ts.rows0.normal_(0.0, 1.0 / D ** 0.5)
+    tp.rows0.normal_(0.0, 1.0 / D ** 0.5)
+    qs, ks = synth.pair_batches(V, V, B, 4, 6)
+    sid = [torch.from_numpy(qs[k]).cuda() for k in range(4)]
+    pid = [torch.from_numpy(ks[k]).cuda() for k in range(4)]
+    tr = TwoTowerInBatch(ts, tp, B, loss="softmax")
+    ms = timeit(lambda k: tr.step(sid[k % 4], pid[k % 4]))
+    out["two_tower_softmax_TRAINER_step_V1M_D256_B4096"] = {
+        "ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3),
+        "includes": "2 id gathers, 2 x (Linear-ReLU-Linear) towers fwd + bwd + Adam (cuBLAS GEMMs through torch), scores + "
+                    "loss + dQ/dK (tcgen05), sparse Adagrad on both tables"}
     return out
 
 
@@ -621,10 +740,15 @@ def run_ours(a):
     ids, counts = synth.glove_batches(V, B, a.nbatch, a.seed + 17 * rank)
     ids_dev = [torch.from_numpy(ids[k].reshape(-1)).cuda() for k in range(a.nbatch)]
     cnt_dev = [torch.from_numpy(counts[k]).cuda() for k in range(a.nbatch)]
-    ids_pin = [torch.from_numpy(ids[k]).pin_memory() for k in range(a.nbatch)]
-    cnt_pin = [torch.from_numpy(counts[k]).pin_memory() for k in range(a.nbatch)]
     tr = GloveTrainer(table, B, lr=a.lr, impl=a.kernel, depth=a.depth, row_blocks=None if a.row_blocks < 0 else a.row_blocks,
                       priorities=a.stream_priority)
+    ids_pin, cnt_pin = [], []
+    for k in range(a.nbatch):        # host batches as a loader would leave them: (2,B) int32 + (B,) f32 in one pinned block
+        hi, hc = tr.pinned_batch()
+        hi.copy_(torch.from_numpy(ids[k]))
+        hc.copy_(torch.from_numpy(counts[k]))
+        ids_pin.append(hi)
+        cnt_pin.append(hc)
 
     clocks = ClockSampler(local)
     clocks.start()

@@ -55,7 +55,8 @@ class EsrGloveCfg(C.Structure):
                 ("lr", C.c_float), ("eps", C.c_float), ("x_max", C.c_float), ("alpha", C.c_float),
                 ("chunk", C.c_int32), ("reserved", C.c_int32), ("emit_map", C.c_void_p),
                 ("emit_peers_dE", C.c_void_p), ("emit_peers_db", C.c_void_p), ("n_emit_peers", C.c_int32),
-                ("row_blocks", C.c_int32)]
+                ("row_blocks", C.c_int32), ("loss_log", C.c_void_p), ("loss_step", C.c_void_p),
+                ("loss_log_len", C.c_int32), ("reserved2", C.c_int32), ("loss_host", C.c_void_p)]
 
 
 class EsrInbatchCfg(C.Structure):
@@ -117,10 +118,14 @@ _SIGNATURES = {
     "esr_pipeline_capture_begin": (C.c_int, [_P, C.c_int32]),
     "esr_pipeline_capture_end": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "esr_pipeline_submit": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int64)]),
+    "esr_pipeline_trace": (C.c_int, [_P, C.c_int32]),
+    "esr_pipeline_trace_read": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "esr_pipeline_sync": (C.c_int, [_P]),
     "esr_pipeline_destroy": (C.c_int, [_P]),
     "esr_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "esr_topk_scan_f32": (C.c_int, [C.POINTER(EsrTopkCfg), _P, _P, _P, C.c_size_t, _P]),
+    "esr_peer_gather_remote_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "esr_plan_compact_owner_i32": (C.c_int, [C.POINTER(EsrPlan), C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "esr_peer_route_pairs_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "esr_peer_route_pairs_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "esr_peer_collect_pairs_i32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),

@@ -22,6 +22,7 @@
 //   k_glove_combine adds in a fixed order, so the result is bit-reproducible run to run.
 #include <algorithm>
 #include <climits>
+#include <cstddef>
 #include <cstdint>
 
 #include "esr_common.cuh"
@@ -1449,6 +1450,10 @@ struct FinishArgs {
   int32_t emit;
   float B;  // B_global
   float lr, eps;
+  float* loss_log;
+  int32_t* loss_step;
+  int32_t loss_log_len;
+  float* loss_host;
 };
 
 __global__ void __launch_bounds__(kThreads) k_glove_finish(const FinishArgs a) {
@@ -1485,6 +1490,12 @@ __global__ void __launch_bounds__(kThreads) k_glove_finish(const FinishArgs a) {
       loss = (S2 - 2.f * mbs * S1 + mbs2 * S0) / a.B;  // App. A.1 closed form of the (B,B) mean
     }
     a.scalars[ESR_SC_LOSS] = loss;
+    if (a.loss_log != nullptr) {  // device-side slot: a replayed graph logs every step
+      const int32_t t = *a.loss_step;
+      a.loss_log[t % a.loss_log_len] = loss;
+      if (a.loss_host != nullptr) a.loss_host[t % a.loss_log_len] = loss;  // pinned host mirror (posted PCIe write)
+      *a.loss_step = t + 1;
+    }
   }
 }
 
@@ -1739,6 +1750,11 @@ extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrG
   a.B = (float)cfg->B_global;
   a.lr = cfg->lr;
   a.eps = cfg->eps;
+  const bool has_log = cfg->struct_size >= offsetof(EsrGloveCfg, reserved2) && cfg->loss_log && cfg->loss_step && cfg->loss_log_len > 0;
+  a.loss_log = has_log ? cfg->loss_log : nullptr;
+  a.loss_step = has_log ? cfg->loss_step : nullptr;
+  a.loss_log_len = has_log ? cfg->loss_log_len : 0;
+  a.loss_host = (has_log && cfg->struct_size >= sizeof(EsrGloveCfg)) ? cfg->loss_host : nullptr;
   k_glove_finish<<<(unsigned)ceil_div(plan->n_slots, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(a);
   ESR_LAUNCH_CHECK();
   return ESR_OK;

@@ -78,6 +78,59 @@ __global__ void __launch_bounds__(kThreads) k_peer_gather(const __grid_constant_
   }
 }
 
+// Remote rows only (owner-routed step: the rows this rank owns are read where they live).  Walks the route plan's bucket
+// order -- unique rows grouped by owner -- and skips my own bucket as one contiguous range, so every group has work.
+template <int TPR, int ROWS>
+__global__ void __launch_bounds__(kThreads) k_peer_gather_remote(const __grid_constant__ PeerPtrs rows, const __grid_constant__ PeerPtrs bias,
+                                                                 const int32_t* __restrict__ uniq, const int32_t* __restrict__ order,
+                                                                 const int32_t* __restrict__ counts, int me, Cyclic cyc, int D4,
+                                                                 float4* __restrict__ out, float* __restrict__ out_bias) {
+  const int lane = threadIdx.x % TPR;
+  int before = 0, mine = 0, total = 0;
+  for (int o = 0; o < cyc.n; ++o) {
+    const int c = counts[o];
+    if (o < me) before += c;
+    if (o == me) mine = c;
+    total += c;
+  }
+  const int64_t n = total - mine;
+  const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
+  for (int64_t first = ((blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR) * ROWS; first < n; first += groups * ROWS) {
+    const float4* src[ROWS];
+    int32_t u[ROWS];
+    float bv[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int64_t k = first + r;
+      src[r] = nullptr;
+      bv[r] = 0.f;
+      u[r] = 0;
+      if (k < n) {
+        u[r] = order[k < before ? k : k + mine];
+        const int32_t row = uniq[u[r]];
+        const int owner = cyc.owner(row);
+        const int64_t local = cyc.local(row);
+        src[r] = reinterpret_cast<const float4*>(rows.p[owner]) + local * D4;
+        if (lane == 0) bv[r] = reinterpret_cast<const float*>(bias.p[owner])[local];
+      }
+    }
+    for (int c = lane; c < D4; c += TPR) {
+      float4 v[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) v[r] = src[r][c];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) out[(int64_t)u[r] * D4 + c] = v[r];  // default caching: the row pass re-reads these from L2
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        if (src[r]) out_bias[u[r]] = bv[r];
+    }
+  }
+}
+
 // src_meta[s] = {offset of source s in recv_ids, count, displacement inside source s's bucket list}
 // slot_map[s][x] = position of owner-local row x in source s's list (-1: source s does not name x)
 __global__ void __launch_bounds__(kThreads) k_peer_pull_ids(const __grid_constant__ PeerPtrs counts, const __grid_constant__ PeerPtrs send_local, int n_ranks, int me,
@@ -150,7 +203,8 @@ __global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const in
   const int64_t span = (int64_t)gridDim.x * kThreads;
   for (int64_t k0 = blockIdx.x * (int64_t)kThreads; k0 < total; k0 += span) {
     const int64_t k = k0 + threadIdx.x;
-    bool own = false;
+    bool own = false, multi = false;
+    int32_t xk = 0;
     if (k < total) {
     int s = 0;
     while (s + 1 < n_ranks && k >= src_meta[(s + 1) * 3]) ++s;
@@ -166,120 +220,122 @@ __global__ void __launch_bounds__(kThreads) k_peer_resolve(int n_ranks, const in
     for (int q = 0; q < ESR_MAX_PEERS; ++q)
       if (q < n_ranks) desc[k * n_ranks + q] = (first && q >= s && pos[q] >= 0) ? src_meta[q * 3 + 0] + pos[q] : -1;
     own = first;
+    xk = x;
+#pragma unroll
+    for (int q = 0; q < ESR_MAX_PEERS; ++q)
+      if (q > s && q < n_ranks && pos[q] >= 0) multi = true;
     }
     // compact the entries that own their row (warp-aggregated append; the order of the list only decides which
-    // group processes which row, never a summation order)
+    // group processes which row, never a summation order).  Record = {entry k | several sources << 31, owner-local row}:
+    // one coalesced 8-byte load per row in the merge instead of three dependent gathers.
     const unsigned m = __ballot_sync(FULL, own);
     if (m) {
       const int lane = threadIdx.x & 31;
       int base = 0;
       if (lane == __ffs(m) - 1) base = atomicAdd(src_meta + n_ranks * 3 + 1, __popc(m));
       base = __shfl_sync(FULL, base, __ffs(m) - 1);
-      if (own) own_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)k;
+      if (own)
+        reinterpret_cast<int2*>(own_list)[base + __popc(m & ((1u << lane) - 1u))] =
+            make_int2((int32_t)((uint32_t)k | (multi ? 0x80000000u : 0u)), xk);
     }
   }
 }
 
-// One group of TPR lanes per OWNER entry (compacted list), EB entries per iteration: sum the row's gradients over the
-// sources in source order (from my inbox, where the sources' row passes scattered them), then optax.adagrad on the local
-// shard row.  Every entry has at least one source (the first one naming the row); its gradient row, the shard row and the
-// accumulator row of all EB entries are issued before the first use.  Further sources -- rare: only rows that several
-// ranks touched in the same step -- are added in source order, four independent loads at a time.  No per-source register
-// arrays sized for the worst case: 60-70 registers, no spills for any rank count (round 1's compile-time NR version
-// spilled 10-50 words per thread at its 80 / 128-register caps).
+// One group of TPR lanes per OWNER record, EB records per iteration: the row's gradient from the first source naming it is
+// inbox row k itself (recv order == inbox order); shard row, accumulator row and that gradient row of all EB records are
+// issued before the first use, and the records of the NEXT iteration are fetched while this one is in flight.  Further
+// sources -- rare: only rows several ranks touched in the same step -- are added in source order, four independent
+// loads at a time.  Sum order: source order (a missing source adds +0.0) -> deterministic.
 template <int TPR, int EB>
-__global__ void __launch_bounds__(kThreads, 2) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE,
-                                                                    const float* __restrict__ inbox_db, int n_ranks,
-                                                                    const int32_t* __restrict__ recv_ids,
+__global__ void __launch_bounds__(kThreads, 2) k_peer_merge_adagrad(const float4* __restrict__ inbox_dE, int n_ranks,
                                                                     const int32_t* __restrict__ src_meta,
                                                                     const int32_t* __restrict__ desc,
-                                                                    const int32_t* __restrict__ own_list, int D4,
+                                                                    const int2* __restrict__ own_rec, int D4,
                                                                     float* __restrict__ rows, float* __restrict__ acc,
-                                                                    float* __restrict__ bias, float* __restrict__ bias_acc,
                                                                     float lr, float eps) {
   const int lane = threadIdx.x % TPR;
   const int64_t total = src_meta[n_ranks * 3 + 1];
   const int64_t groups = (int64_t)gridDim.x * (kThreads / TPR);
-  for (int64_t i0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR; i0 < total; i0 += groups * EB) {
-    int64_t x[EB], k[EB];
-    int first[EB];   // inbox row of the first source naming the row
-    int q0[EB];      // that source
-    bool on[EB];
+  const int64_t g0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
+  int2 rec[EB], nxt[EB];
 #pragma unroll
-    for (int e = 0; e < EB; ++e) {
-      const int64_t i = i0 + e * groups;
-      on[e] = i < total;
-      k[e] = on[e] ? own_list[i] : 0;
-      x[e] = on[e] ? recv_ids[k[e]] : 0;
-    }
-#pragma unroll
-    for (int e = 0; e < EB; ++e) {
-      first[e] = -1;
-      q0[e] = n_ranks;
-      if (on[e]) {
-        for (int q = 0; q < n_ranks; ++q) {
-          const int d = desc[k[e] * n_ranks + q];
-          if (d >= 0) {
-            first[e] = d;
-            q0[e] = q;
-            break;
-          }
-        }
-      }
-    }
-    // bias scalars (lane 0): every source's share, source order
-    float bp[EB], ba[EB], bg[EB];
-#pragma unroll
-    for (int e = 0; e < EB; ++e) {
-      bp[e] = ba[e] = bg[e] = 0.f;
-      if (on[e] && lane == 0) {
-        bp[e] = bias[x[e]];
-        ba[e] = bias_acc[x[e]];
-        for (int q = q0[e]; q < n_ranks; ++q) {
-          const int d = desc[k[e] * n_ranks + q];
-          if (d >= 0) bg[e] += inbox_db[d];
-        }
-      }
-    }
+  for (int e = 0; e < EB; ++e) {
+    const int64_t i = g0 + e * groups;
+    rec[e] = i < total ? own_rec[i] : make_int2(-1, 0);
+  }
+  for (int64_t i0 = g0; i0 < total; i0 += groups * EB) {
     for (int c = lane; c < D4; c += TPR) {
       float4 g[EB], pv[EB], av[EB];
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
-        g[e] = f4_zero();
-        if (on[e]) {
-          pv[e] = reinterpret_cast<const float4*>(rows)[x[e] * D4 + c];
-          av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + x[e] * D4 + c);
-          if (first[e] >= 0) g[e] = ld_stream(inbox_dE + (int64_t)first[e] * D4 + c);
+        const bool on = i0 + e * groups < total;
+        if (on) {
+          const int64_t k = rec[e].x & 0x7fffffff, x = rec[e].y;
+          pv[e] = reinterpret_cast<const float4*>(rows)[x * D4 + c];
+          av[e] = ld_stream(reinterpret_cast<const float4*>(acc) + x * D4 + c);
+          g[e] = ld_stream(inbox_dE + k * D4 + c);
+        }
+      }
+      if (c == lane) {  // next iteration's records: in flight behind the row loads
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+          const int64_t i = i0 + (e + EB) * groups;
+          nxt[e] = i < total ? own_rec[i] : make_int2(-1, 0);
         }
       }
 #pragma unroll
       for (int e = 0; e < EB; ++e) {
-        if (on[e]) {
-          // further sources in source order, 4 independent loads per round
-          for (int qb = q0[e] + 1; qb < n_ranks; qb += 4) {
-            int d[4];
-            float4 t[4];
+        if (i0 + e * groups < total) {
+          const int64_t k = rec[e].x & 0x7fffffff, x = rec[e].y;
+          if (rec[e].x < 0) {  // several sources: add the others in source order
+            int q0 = 0;
+            while (q0 < n_ranks && desc[k * n_ranks + q0] < 0) ++q0;
+            for (int qb = q0 + 1; qb < n_ranks; qb += 4) {
+              int d[4];
+              float4 t[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = qb + j < n_ranks ? desc[k[e] * n_ranks + qb + j] : -1;
+              for (int j = 0; j < 4; ++j) d[j] = qb + j < n_ranks ? desc[k * n_ranks + qb + j] : -1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) t[j] = d[j] >= 0 ? ld_stream(inbox_dE + (int64_t)d[j] * D4 + c) : f4_zero();
+              for (int j = 0; j < 4; ++j) t[j] = d[j] >= 0 ? ld_stream(inbox_dE + (int64_t)d[j] * D4 + c) : f4_zero();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) f4_add(g[e], t[j]);   // a missing source adds +0.0
+              for (int j = 0; j < 4; ++j) f4_add(g[e], t[j]);
+            }
           }
           adagrad4(pv[e], av[e], g[e], lr, eps);
-          reinterpret_cast<float4*>(rows)[x[e] * D4 + c] = pv[e];
-          st_stream(reinterpret_cast<float4*>(acc) + x[e] * D4 + c, av[e]);
+          reinterpret_cast<float4*>(rows)[x * D4 + c] = pv[e];
+          st_stream(reinterpret_cast<float4*>(acc) + x * D4 + c, av[e]);
         }
       }
     }
 #pragma unroll
-    for (int e = 0; e < EB; ++e) {
-      if (on[e] && lane == 0) {
-        adagrad1(bp[e], ba[e], bg[e], lr, eps);
-        bias[x[e]] = bp[e];
-        bias_acc[x[e]] = ba[e];
+    for (int e = 0; e < EB; ++e) rec[e] = nxt[e];
+  }
+}
+
+// Bias of the owned rows: one thread per owner record (the per-row scalars would otherwise put dependent 4-byte loads of
+// one lane in front of every row of the kernel above).
+__global__ void __launch_bounds__(kThreads) k_peer_merge_bias(const float* __restrict__ inbox_db, int n_ranks,
+                                                              const int32_t* __restrict__ src_meta,
+                                                              const int32_t* __restrict__ desc,
+                                                              const int2* __restrict__ own_rec, float* __restrict__ bias,
+                                                              float* __restrict__ bias_acc, float lr, float eps) {
+  const int64_t total = src_meta[n_ranks * 3 + 1];
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int2 r = own_rec[i];
+    const int64_t k = r.x & 0x7fffffff, x = r.y;
+    float g = inbox_db[k];
+    if (r.x < 0) {
+      int q0 = 0;
+      while (q0 < n_ranks && desc[k * n_ranks + q0] < 0) ++q0;
+      for (int q = q0 + 1; q < n_ranks; ++q) {
+        const int d = desc[k * n_ranks + q];
+        if (d >= 0) g += inbox_db[d];
       }
     }
+    float p = bias[x], a = bias_acc[x];
+    adagrad1(p, a, g, lr, eps);
+    bias[x] = p;
+    bias_acc[x] = a;
   }
 }
 
@@ -337,6 +393,31 @@ extern "C" int esr_peer_gather_f32(const void* const* peer_rows, const void* con
   return ESR_OK;
 }
 
+extern "C" int esr_peer_gather_remote_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks, int32_t me,
+                                          const int32_t* uniq, const int32_t* order, const int32_t* counts, int64_t cap,
+                                          int32_t D, float* out, float* out_bias, esr_stream_t stream_) {
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && cap >= 0 && D > 0 && (D % 4) == 0);
+  if (cap == 0 || n_ranks == 1) return ESR_OK;  // one rank: nothing is remote
+  PeerPtrs pr, pb;
+  ESR_REQUIRE(load_ptrs(&pr, peer_rows, n_ranks) && load_ptrs(&pb, peer_bias, n_ranks));
+  ESR_REQUIRE(uniq && order && counts && out && out_bias && (reinterpret_cast<uintptr_t>(out) % 16) == 0);
+  const int D4 = D / 4;
+  const int tpr = tpr_for(D4);
+  constexpr int ROWS = 4;
+  const int64_t want = ceil_div(ceil_div(cap, ROWS) * tpr, kThreads);
+  const int64_t persistent = (int64_t)sm_count() * 8;
+  const unsigned grid = (unsigned)(want < persistent ? want : persistent);
+  Cyclic cyc;
+  cyc.n = n_ranks;
+  cyc.shift = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == n_ranks) cyc.shift = b;
+  ESR_DISPATCH_TPR(tpr, (k_peer_gather_remote<TPR, ROWS><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+                            pr, pb, uniq, order, counts, me, cyc, D4, reinterpret_cast<float4*>(out), out_bias)));
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
 extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* peer_send_local, int32_t n_ranks,
                                      int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, int32_t* slot_map,
                                      int64_t map_stride, esr_stream_t stream_) {
@@ -353,11 +434,12 @@ extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void*
 
 // Owner side, step 1 (ids only -- can run on a side stream while the row pass is still producing gradients):
 // per received entry, where every source keeps that row's gradient (desc), and the compacted list of the entries
-// that own their row (own_list = desc + recv_cap * n_ranks, counter in src_meta[3n + 1]).
+// that own their row, as 8-byte records {entry k | several-sources flag << 31, owner-local row} at desc + recv_cap * n_ranks
+// (so desc holds recv_cap * (n_ranks + 2) ints; counter in src_meta[3n + 1]).
 extern "C" int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_meta, const int32_t* slot_map,
                                     int64_t map_stride, int32_t* desc, int64_t recv_cap, esr_stream_t stream_) {
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && desc &&
-              recv_cap > 0);
+              recv_cap > 0 && ((recv_cap * n_ranks) % 2) == 0 && (reinterpret_cast<uintptr_t>(desc) % 8) == 0);
   k_peer_resolve<<<4 * sm_count(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(n_ranks, recv_ids, src_meta, slot_map,
                                                                                      map_stride, desc, desc + recv_cap * n_ranks);
   ESR_LAUNCH_CHECK();
@@ -376,12 +458,15 @@ extern "C" int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE
   ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D4 = shard->D / 4;
-  const int32_t* own_list = desc + recv_cap * n_ranks;
+  const int2* own_rec = reinterpret_cast<const int2*>(desc + recv_cap * n_ranks);  // 8-byte aligned: recv_cap * n is even or padded by the caller
   const int tpr = tpr_for(D4);
   const int grid = 8 * sm_count();
   ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 4><<<grid, kThreads, 0, stream>>>(
-                            reinterpret_cast<const float4*>(inbox_dE), inbox_db, n_ranks, recv_ids, src_meta, desc, own_list, D4,
-                            shard->rows[0], shard->acc, shard->bias, shard->bias_acc, lr, eps)));
+                            reinterpret_cast<const float4*>(inbox_dE), n_ranks, src_meta, desc, own_rec, D4, shard->rows[0],
+                            shard->acc, lr, eps)));
+  ESR_LAUNCH_CHECK();
+  k_peer_merge_bias<<<2 * sm_count(), kThreads, 0, stream>>>(inbox_db, n_ranks, src_meta, desc, own_rec, shard->bias,
+                                                             shard->bias_acc, lr, eps);
   ESR_LAUNCH_CHECK();
   k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
   ESR_LAUNCH_CHECK();

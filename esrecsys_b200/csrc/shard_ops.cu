@@ -81,6 +81,28 @@ __global__ void __launch_bounds__(kThreads) k_plan_compact2(const int32_t* __res
   uniq[u] = u;  // every slot of a segment writes the same value
 }
 
+// Owner-aware form (unified table of the owner-routed sharded step): a unique row this rank OWNS is addressed where it
+// lives in the shard (row / n), a fetched one in the fetch region behind the shard (base + u) -- so local rows are never
+// copied.  Equal rows still get equal keys, which is all the row pass needs from a key (address + segment equality).
+__global__ void __launch_bounds__(kThreads) k_plan_compact_owner(const int32_t* __restrict__ perm,
+                                                                 const int32_t* __restrict__ useg,
+                                                                 const int32_t* __restrict__ slot_u,
+                                                                 const int32_t* __restrict__ uniq, int64_t n_cap,
+                                                                 const int32_t* __restrict__ n_valid, int n_ranks, int me,
+                                                                 int32_t base, int32_t* __restrict__ sorted_keys,
+                                                                 int32_t* __restrict__ partner) {
+  const int64_t n = n_valid ? min(n_cap, (int64_t)__ldg(n_valid)) : n_cap;
+  const int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (p >= n) return;
+  const int64_t half = n_cap >> 1;
+  const int64_t s = perm[p];
+  const int32_t u = useg[p];
+  const int32_t u2 = slot_u[s < half ? s + half : s - half];
+  const int32_t r = uniq[u], r2 = uniq[u2];
+  sorted_keys[p] = (r % n_ranks == me) ? r / n_ranks : base + u;
+  partner[p] = (r2 % n_ranks == me) ? r2 / n_ranks : base + u2;
+}
+
 __global__ void __launch_bounds__(kThreads) k_gather_scalar(const float* __restrict__ src, const int32_t* __restrict__ ids,
                                                             int64_t n, float* __restrict__ out) {
   const int64_t k = blockIdx.x * (int64_t)kThreads + threadIdx.x;
@@ -197,6 +219,24 @@ extern "C" int esr_plan_compact_i32(const EsrPlan* plan, int32_t* sorted_keys, i
   ESR_LAUNCH_CHECK();
   k_plan_compact2<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, scratch, n, plan->n_valid, sorted_keys, partner,
                                                  uniq);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+extern "C" int esr_plan_compact_owner_i32(const EsrPlan* plan, int32_t n_ranks, int32_t me, int32_t base, int32_t* sorted_keys,
+                                          int32_t* partner, int32_t* scratch, esr_stream_t stream_) {
+  ESR_REQUIRE(plan && plan->struct_size >= sizeof(EsrPlan) && sorted_keys && partner && scratch);
+  ESR_REQUIRE(n_ranks >= 1 && me >= 0 && me < n_ranks && base >= 0);
+  const int64_t n = plan->n_slots;
+  ESR_REQUIRE(n >= 0 && (n % 2) == 0 && (int64_t)base + n < ((int64_t)1 << 30));
+  if (n == 0) return ESR_OK;
+  ESR_REQUIRE(plan->perm && plan->useg && plan->uniq);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const unsigned grid = (unsigned)ceil_div(n, kThreads);
+  k_plan_compact<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, n, plan->n_valid, scratch);
+  ESR_LAUNCH_CHECK();
+  k_plan_compact_owner<<<grid, kThreads, 0, stream>>>(plan->perm, plan->useg, scratch, plan->uniq, n, plan->n_valid, n_ranks, me,
+                                                      base, sorted_keys, partner);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

@@ -100,17 +100,39 @@ __device__ void compact_list(uint64_t* keys, int* cnt, uint64_t* thr, int cap, i
   __syncthreads();
 }
 
+// Sum G per-lane partial values of G different queries over the G lanes of a group so that lane gl ends up with the total of
+// query gl: log2(G) exchange steps that halve the number of live values (G - 1 shuffles instead of G * log2(G)).
+template <int G>
+__device__ __forceinline__ float transpose_sum(float (&v)[G], int gl) {
+#pragma unroll
+  for (int o = G / 2, n = G; o > 0; o >>= 1, n >>= 1) {
+    const bool up = (gl & o) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL, send, o);
+    }
+  }
+  return v[0];
+}
+
+// R rows per group and iteration (2 * NV independent 16-byte loads in flight per lane), G queries per pass: the query
+// vectors are read from shared memory once per pass for all R rows.
 template <int G, int NV>
 __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int R = 2;
   const int D4 = a.DA4 + a.DB4;
   const int L = a.maxq ? 1 : a.T;
-  float4* qs = reinterpret_cast<float4*>(smem_raw);                                   // [T][D4]
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (size_t)a.T * D4 * 16);     // [L][cap]
+  const int Tp = (a.T + G - 1) / G * G;                                               // queries padded to whole passes
+  float4* qs = reinterpret_cast<float4*>(smem_raw);                                   // [Tp][D4]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (size_t)Tp * D4 * 16);      // [L][cap]
   __shared__ int cnt[kMaxT];
   __shared__ uint64_t thr[kMaxT];
   __shared__ int32_t ctx[2 * kMaxCtx];
-  for (int i = threadIdx.x; i < a.T * D4; i += kThreads) qs[i] = reinterpret_cast<const float4*>(a.Q)[i];
+  for (int i = threadIdx.x; i < Tp * D4; i += kThreads)
+    qs[i] = i < a.T * D4 ? reinterpret_cast<const float4*>(a.Q)[i] : f4_zero();
   if (threadIdx.x < L) {
     cnt[threadIdx.x] = 0;
     thr[threadIdx.x] = 0ull;
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
   if (threadIdx.x < a.nA) ctx[threadIdx.x] = a.ctxA[threadIdx.x];
   if (threadIdx.x < a.nB) ctx[kMaxCtx + threadIdx.x] = a.ctxB[threadIdx.x];
   __syncthreads();
-  constexpr int GP = kThreads / G;  // rows per block iteration
+  constexpr int GP = kThreads / G;  // groups per block; a block iteration covers GP * R rows
   const int gl = threadIdx.x % G, grp = threadIdx.x / G;
   const int64_t r0 = blockIdx.x * a.slab, r1 = min(a.N, r0 + a.slab);
   const float4* const A0 = reinterpret_cast<const float4*>(a.A0);
@@ -127,51 +149,87 @@ __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
 
   for (int64_t t0 = r0; t0 < r1; t0 += a.tile_rows) {
     const int64_t t1 = min(r1, t0 + a.tile_rows);
-    for (int64_t base = t0; base < t1; base += GP) {
-      const int64_t n = base + grp;
-      const bool on = n < t1;
-      float4 x[NV];
-      int32_t ia = 0, ib = 0;
-      if (on) {
-        ia = a.idxA ? a.idxA[n] : (int32_t)n;
-        if (Bt) ib = a.idxB[n];
-        const int64_t ra = a.modA > 0 ? ia % a.modA : ia;
-        const float4* pa = ((a.ver != nullptr && a.ver[ra]) ? A1 : A0) + ra * a.DA4;
-        const float4* pb = Bt ? Bt + (int64_t)ib * a.DB4 : nullptr;
+    for (int64_t base = t0; base < t1; base += GP * R) {
+      float4 x[R][NV];
+      int32_t ia[R], ib[R];
+      bool on[R];
+      int64_t n[R];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int c = k * G + gl;
-          x[k] = c < a.DA4 ? ld_stream(pa + c) : (c < D4 ? ld_stream(pb + (c - a.DA4)) : f4_zero());
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) x[k] = f4_zero();
-      }
-      float best = -INFINITY;
-      for (int q = 0; q < a.T; ++q) {
-        float d = 0.f;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int c = k * G + gl;
-          if (c < D4) d += f4_dot(x[k], qs[q * D4 + c]);
-        }
-        d = group_sum<G>(d);
-        if (a.maxq) {
-          best = fmaxf(best, d);
-        } else if (on && gl == 0) {
-          const uint64_t key = make_key(d, (uint32_t)n, a.order);
-          if (key >= thr[q]) keys[(size_t)q * a.cap + atomicAdd(&cnt[q], 1)] = key;
+      for (int r = 0; r < R; ++r) {
+        n[r] = base + (int64_t)r * GP + grp;
+        on[r] = n[r] < t1;
+        ia[r] = ib[r] = 0;
+        if (on[r]) {
+          ia[r] = a.idxA ? a.idxA[n[r]] : (int32_t)n[r];
+          if (Bt) ib[r] = a.idxB[n[r]];
         }
       }
-      if (a.maxq && on && gl == 0) {
-        // spotify/models.py:78-80: + 0.1 isin(album, album_context) + 0.1 isin(artist, artist_context), raw ids
-        bool inA = false, inB = false;
-        for (int j = 0; j < a.nA; ++j) inA |= ctx[j] == ia;
-        for (int j = 0; j < a.nB; ++j) inB |= ctx[kMaxCtx + j] == ib;
-        float s = best + a.boost * (inA ? 1.f : 0.f);
-        s = s + a.boost * (inB ? 1.f : 0.f);
-        const uint64_t key = make_key(s, (uint32_t)n, a.order);
-        if (key >= thr[0]) keys[atomicAdd(&cnt[0], 1)] = key;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (on[r]) {
+          const int64_t ra = a.modA > 0 ? ia[r] % a.modA : ia[r];
+          const float4* pa = ((a.ver != nullptr && a.ver[ra]) ? A1 : A0) + ra * a.DA4;
+          const float4* pb = Bt ? Bt + (int64_t)ib[r] * a.DB4 : nullptr;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int c = k * G + gl;
+            x[r][k] = c < a.DA4 ? ld_stream(pa + c) : (c < D4 ? ld_stream(pb + (c - a.DA4)) : f4_zero());
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) x[r][k] = f4_zero();
+        }
+      }
+      float best[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) best[r] = -INFINITY;
+      for (int q0 = 0; q0 < Tp; q0 += G) {
+        float d[R][G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          float4 qv[NV];
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const int c = k * G + gl;
+            qv[k] = c < D4 ? qs[(q0 + j) * D4 + c] : f4_zero();
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc += f4_dot(x[r][k], qv[k]);
+            d[r][j] = acc;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float s = transpose_sum<G>(d[r], gl);   // lane gl: score of query q0 + gl
+          const int q = q0 + gl;
+          if (a.maxq) {
+            if (q < a.T) best[r] = fmaxf(best[r], s);
+          } else if (on[r] && q < a.T) {
+            const uint64_t key = make_key(s, (uint32_t)n[r], a.order);
+            if (key >= thr[q]) keys[(size_t)q * a.cap + atomicAdd(&cnt[q], 1)] = key;
+          }
+        }
+      }
+      if (a.maxq) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float m = best[r];
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+          if (on[r] && gl == 0) {
+            // spotify/models.py:78-80: + 0.1 isin(album, album_context) + 0.1 isin(artist, artist_context), raw ids
+            bool inA = false, inB = false;
+            for (int j = 0; j < a.nA; ++j) inA |= ctx[j] == ia[r];
+            for (int j = 0; j < a.nB; ++j) inB |= ctx[kMaxCtx + j] == ib[r];
+            float s = m + a.boost * (inA ? 1.f : 0.f);
+            s = s + a.boost * (inB ? 1.f : 0.f);
+            const uint64_t key = make_key(s, (uint32_t)n[r], a.order);
+            if (key >= thr[0]) keys[atomicAdd(&cnt[0], 1)] = key;
+          }
+        }
       }
     }
     __syncthreads();
@@ -233,17 +291,19 @@ struct TopkGeom {
 bool topk_geom(int64_t N, int D4, int T, int maxq, int k, TopkGeom* g) {
   if (N <= 0 || D4 <= 0 || D4 > 128 || T <= 0 || T > kMaxT || k <= 0 || k > kMaxK || k > N) return false;
   g->lists = maxq ? 1 : T;
-  int cap = pow2_ceil(4 * k);
-  if (cap < 256) cap = 256;
-  if (cap > 4096) cap = 4096;
-  // shared memory: queries + lists * cap keys; shrink the buffers (never below 2k rounded up) before giving up
-  while ((size_t)T * D4 * 16 + (size_t)g->lists * cap * 8 > 160 * 1024 && cap / 2 >= pow2_ceil(2 * k) && cap > 128) cap >>= 1;
-  if ((size_t)T * D4 * 16 + (size_t)g->lists * cap * 8 > 200 * 1024) return false;
-  g->cap = cap;
   int G = 1;
   while (G * 4 < D4 && G < 32) G <<= 1;
   g->G = G;
-  const int rows_per_iter = kThreads / G;
+  const int Tp = (T + G - 1) / G * G;  // queries padded to whole passes of G
+  int cap = pow2_ceil(4 * k);
+  if (cap < 512) cap = 512;
+  if (cap < 4 * (kThreads / G)) cap = 4 * (kThreads / G);  // at least two block iterations per tile
+  if (cap > 4096) cap = 4096;
+  // shared memory: queries + lists * cap keys; shrink the buffers (never below 2k rounded up) before giving up
+  while ((size_t)Tp * D4 * 16 + (size_t)g->lists * cap * 8 > 100 * 1024 && cap / 2 >= pow2_ceil(2 * k) && cap > 128) cap >>= 1;
+  if ((size_t)Tp * D4 * 16 + (size_t)g->lists * cap * 8 > 200 * 1024) return false;
+  g->cap = cap;
+  const int rows_per_iter = 2 * (kThreads / G);  // R = 2 rows per group
   int tile = cap / 2 < 256 ? cap / 2 : 256;
   tile = tile / rows_per_iter * rows_per_iter;
   if (tile < rows_per_iter) tile = rows_per_iter;
@@ -254,7 +314,7 @@ bool topk_geom(int64_t N, int D4, int T, int maxq, int k, TopkGeom* g) {
   g->grid = (int)(want < 1 ? 1 : (want < cap_grid ? want : cap_grid));
   g->slab = ceil_div(ceil_div(N, (int64_t)g->grid), (int64_t)rows_per_iter) * rows_per_iter;
   g->grid = (int)ceil_div(N, g->slab);
-  g->smem_scan = (size_t)T * D4 * 16 + (size_t)g->lists * cap * 8;
+  g->smem_scan = (size_t)Tp * D4 * 16 + (size_t)g->lists * cap * 8;
   g->smem_merge = (size_t)cap * 8;
   return true;
 }

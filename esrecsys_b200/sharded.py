@@ -312,7 +312,7 @@ class PeerShardedGloveTrainer:
         self.src_meta = torch.zeros(3 * 8 + 4, **i32)
         self.map_stride = V_max
         self.slot_map = torch.full((self.n, V_max), -1, **i32)
-        self.desc = torch.empty(self.recv_cap * (self.n + 1), **i32)
+        self.desc = torch.empty(self.recv_cap * (self.n + 2), **i32)   # per entry: n source rows; then 8-byte owner records
         self.s_side = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
@@ -510,7 +510,7 @@ def pair_capacity(B_local, n):
     times over; data that concentrates row i on one owner overflows and is reported by check()."""
     if n == 1:
         return int(B_local)
-    cap = int(B_local) + max(int(B_local) // 8, 512)
+    cap = int(B_local) + max(int(B_local) // 16, 512)
     return (cap + 255) // 256 * 256
 
 
@@ -537,7 +537,7 @@ class OwnerRoutedGloveTrainer:
     LAUNCHES_PER_STEP = 34
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
-                 graphs=True, pair_cap=None, impl="auto"):
+                 graphs=True, pair_cap=None, impl="auto", row_blocks=None):
         import torch.distributed._symmetric_memory as symm_mem
         L.require_cuda()
         self.group = group if group is not None else dist.group.WORLD
@@ -561,12 +561,18 @@ class OwnerRoutedGloveTrainer:
 
         i32 = dict(dtype=torch.int32, device=self.dev)
         V_loc, V_max = shard_rows(V, self.rank, n), shard_rows(V, 0, n)
-        rows, self.p_rows = symm((V_max, D), torch.float32)
-        bias, self.p_bias = symm((V_max,), torch.float32)
+        # ONE allocation per rank: [shard rows (V_max) ; fetch region (n_slots)].  The row pass addresses a unique row of the
+        # step either where it lives in the shard (rows this rank owns: every i, 1/n of the j) or in the fetch region
+        # (rows pulled from their owners), so local rows are never copied (esr_plan_compact_owner_i32).
+        rows, self.p_rows = symm((V_max + n_slots, D), torch.float32)
+        bias, self.p_bias = symm((V_max + n_slots,), torch.float32)
         rows.zero_()
         bias.zero_()
+        self.V_max = V_max
         self.shard = EmbeddingTable.wrap(rows[:V_loc], bias=bias[:V_loc], acc=torch.full((V_loc, D), 0.1, device=self.dev),
                                          bias_acc=torch.full((V_loc,), 0.1, device=self.dev))
+        self.unified = EmbeddingTable.wrap(rows, bias=bias)
+        self.fetch_rows, self.fetch_bias = rows[V_max:], bias[V_max:]
         self.pub, self.pin = [], []
         for _ in range(self.DEPTH):
             counts, p_counts = symm((16,), torch.int32)
@@ -598,14 +604,19 @@ class OwnerRoutedGloveTrainer:
         self.cnt_l = [torch.zeros(B_cap, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
         self.n_valid = [torch.zeros(1, **i32) for _ in range(self.DEPTH)]
         self.plans = [IndexPlan(n_slots, V + 1, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]   # pad key = V
-        self.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
-        self.cplans = [IndexPlan(n_slots, n_slots, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]
+        self.cplans = [IndexPlan(n_slots, V_max + n_slots, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]
         for cp, pl in zip(self.cplans, self.plans):
             cp.s.n_slots = n_slots
             cp.s.perm, cp.s.useg, cp.s.seg_off, cp.s.n_uniq = pl.s.perm, pl.s.useg, pl.s.seg_off, pl.s.n_uniq
         self.scratch = torch.empty(n_slots, **i32)
-        self.step_fn = GloveStep(self.compact, B_cap, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
-                                 B_global=B * n, dE=self.inbox_dE, db=self.inbox_db, impl=impl)
+        if row_blocks is None:
+            # as GloveTrainer: the persistent row pass leaves 1/9 of its CTA slots to the side stream (pair routing + plan of
+            # the next batch: ~190 us of kernels that otherwise only run in the gaps of the main chain)
+            sm = C.c_int(0)
+            L.check(L.lib().esr_device_info(C.byref(sm), None, None), "esr_device_info")
+            row_blocks = max(1, (2 * sm.value * 8) // 9)
+        self.step_fn = GloveStep(self.unified, B_cap, lr=lr, bias_mode=bias_mode, chunk=chunk, emit_grads=True,
+                                 B_global=B * n, dE=self.inbox_dE, db=self.inbox_db, impl=impl, row_blocks=row_blocks)
         cfg = self.step_fn.cfg
         cfg.emit_map = L.ptr(self.emit_map)
         cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
@@ -616,7 +627,7 @@ class OwnerRoutedGloveTrainer:
         self.src_meta = torch.zeros(3 * 8 + 4, **i32)
         self.map_stride = V_max
         self.slot_map = torch.full((n, V_max), -1, **i32)
-        self.desc = torch.empty(self.recv_cap * (n + 1), **i32)
+        self.desc = torch.empty(self.recv_cap * (n + 2), **i32)   # per entry: n source rows; then 8-byte owner records
         self.s_side = torch.cuda.Stream(self.dev)
         self.s_ids = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
@@ -661,8 +672,8 @@ class OwnerRoutedGloveTrainer:
         plan.build(self.keys[k])
         self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
         cplan.s.n_slots = plan.n_slots
-        L.check(lib.esr_plan_compact_i32(C.byref(plan.s), L.ptr(cplan.sorted_keys), L.ptr(cplan.partner),
-                                         L.ptr(cplan.uniq), L.ptr(self.scratch), sp), "esr_plan_compact_i32")
+        L.check(lib.esr_plan_compact_owner_i32(C.byref(plan.s), n, self.rank, self.V_max, L.ptr(cplan.sorted_keys),
+                                               L.ptr(cplan.partner), L.ptr(self.scratch), sp), "esr_plan_compact_owner_i32")
 
     def _ids_body(self, k, sp):
         lib, n = L.lib(), self.n
@@ -687,8 +698,10 @@ class OwnerRoutedGloveTrainer:
         with torch.cuda.stream(self.s_ids):
             self._ids_body(k, L.stream_ptr())
             self.ev_ids.record(self.s_ids)
-        L.check(lib.esr_peer_gather_f32(self.p_rows, self.p_bias, n, L.ptr(plan.uniq), L.ptr(plan.n_uniq), plan.capacity,
-                                        self.D, L.ptr(self.compact.rows0), L.ptr(self.compact.bias), sp), "esr_peer_gather_f32")
+        pub = self.pub[k]
+        L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, self.rank, L.ptr(plan.uniq), L.ptr(pub["order"]),
+                                               L.ptr(pub["counts"]), plan.capacity, self.D, L.ptr(self.fetch_rows),
+                                               L.ptr(self.fetch_bias), sp), "esr_peer_gather_remote_f32")
         st.prep(cplan, self.cnt_l[k])
         self._sync(st.scalars[0:3])         # global sum(bs), sum(bs^2), S0; also: all fetches done
         main.wait_event(self.ev_ids)

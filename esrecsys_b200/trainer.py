@@ -42,11 +42,19 @@ class GloveTrainer:
         if not 1 <= self.depth <= 4:
             raise ValueError("depth must be 1..4")
         self.step_fn = GloveStep(table, B, lr=lr, bias_mode=bias_mode, chunk=chunk, impl=impl, row_blocks=row_blocks)
-        self.plans = [IndexPlan(2 * self.B, table.V, self.dev) for _ in range(self.depth)]
-        self.ids = [torch.zeros(2 * self.B, dtype=torch.int32, device=self.dev) for _ in range(self.depth)]
-        self.counts = [torch.ones(self.B, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
         self.loss_log = torch.zeros(loss_log, dtype=torch.float32, device=self.dev)
+        self.loss_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        cfg = self.step_fn.cfg           # the finish kernel logs every step's loss itself (device-side slot counter)
+        cfg.loss_log, cfg.loss_step, cfg.loss_log_len = L.ptr(self.loss_log), L.ptr(self.loss_step), int(loss_log)
         self.loss_host = torch.zeros(loss_log, dtype=torch.float32).pin_memory()
+        cfg.loss_host = self.loss_host.data_ptr()      # pinned host mirror: every step's loss arrives as a 4-byte PCIe write
+        self.plans = [IndexPlan(2 * self.B, table.V, self.dev) for _ in range(self.depth)]
+        # staging: ids and counts of a parity share one allocation, so an adjacent host batch uploads in ONE copy
+        self._stage = [torch.zeros(3 * self.B, dtype=torch.int32, device=self.dev) for _ in range(self.depth)]
+        self.ids = [b[: 2 * self.B] for b in self._stage]
+        self.counts = [b[2 * self.B:].view(torch.float32) for b in self._stage]
+        for c in self.counts:
+            c.fill_(1.0)
         self.t = 0
         # The plan sorts ceil(log2 V) key bits and the row pass uses ids as raw row offsets, so an id outside [0, V) would
         # corrupt memory where XLA clamps / drops it.  "first": the first batch is validated on the
@@ -75,7 +83,7 @@ class GloveTrainer:
             cnt_p = (C.c_void_p * self.depth)(*[x.data_ptr() for x in self.counts])
             L.check(L.lib().esr_pipeline_set_buffers(self.pipe, ids_p, cnt_p, self.ids[0].numel() * 4, self.counts[0].numel() * 4,
                                                      self.step_fn.scalars.data_ptr() + 4 * L.SC_LOSS, self.loss_log.data_ptr(),
-                                                     self.loss_log.numel(), self.loss_host.data_ptr()),
+                                                     self.loss_log.numel(), None),
                     "esr_pipeline_set_buffers")
             self.g_plan = [True] * self.depth      # the graphs live in the native object
             self.g_step = [True] * self.depth
@@ -133,6 +141,7 @@ class GloveTrainer:
             finally:
                 L.check(lib.esr_pipeline_capture_end(self.pipe, 1, k), "esr_pipeline_capture_end")
         self._restore(snap)
+        self.loss_step.zero_()            # the warm-up / capture steps advanced the device-side step counter
         torch.cuda.synchronize(self.dev)
 
     def _snapshot(self):
@@ -176,6 +185,10 @@ class GloveTrainer:
             if len(self._keep) > 2 * self.depth + 2:
                 self._keep.pop(0)
             flags = (1 if read_loss else 0) | (2 if ids.is_cuda else 0)  # device inputs: order behind the caller's stream
+            if ids.untyped_storage().data_ptr() == counts.untyped_storage().data_ptr():
+                flags |= 4                                               # one allocation (pinned_batch()): single upload
+            if not ids.is_cuda:
+                flags |= 8                                               # pinned host memory: staged by a kernel over PCIe
             caller = torch.cuda.current_stream(self.dev).cuda_stream if ids.is_cuda else None
             L.check(L.lib().esr_pipeline_submit(self.pipe, ids.data_ptr(), counts.data_ptr(), caller, flags, None),
                     "esr_pipeline_submit")
@@ -202,12 +215,18 @@ class GloveTrainer:
         with torch.cuda.stream(main):
             self._step_body(k)
             slot = self.t % self.loss_log.numel()
-            self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
             if read_loss:
                 self.loss_host[slot: slot + 1].copy_(self.loss_log[slot: slot + 1], non_blocking=True)
             self.ev_done[k].record(main)
         self.t += 1
         return self.t - 1
+
+    def pinned_batch(self):
+        """A pinned host batch in the layout of wikipedia/cooccurrence_matrix.py:103-114 -- ``(ids int32 (2,B), counts f32
+        (B,))`` -- whose two arrays are adjacent in ONE pinned block, so ``submit`` uploads it with a single copy.  For
+        loaders to fill in place."""
+        buf = torch.empty(3 * self.B, dtype=torch.int32).pin_memory()
+        return buf[: 2 * self.B].view(2, self.B), buf[2 * self.B:].view(torch.float32)
 
     def read_loss(self, step):
         """Device->host read of one step's loss (asynchronous copy into pinned memory on the main stream); prefer

@@ -200,6 +200,15 @@ typedef struct EsrGloveCfg {
   void* const* emit_peers_db;
   int32_t n_emit_peers;
   int32_t row_blocks;  /* persistent row-pass grid; 0 => 2 CTAs per SM.  Fewer leaves SM room for the plan stream */
+  /* Optional device-side loss log: esr_glove_finish also writes the step's loss to loss_log[*loss_step % loss_log_len] and
+   * increments *loss_step -- the slot is chosen on the device, so a replayed CUDA graph logs every step without a copy
+   * node on the step's stream. */
+  float* loss_log;
+  int32_t* loss_step;
+  int32_t loss_log_len;
+  int32_t reserved2;
+  float* loss_host;    /* optional PINNED HOST mirror of loss_log (device-accessible pointer): the step's loss reaches the
+                        * host as a 4-byte posted write of the finish kernel, readable after a stream synchronise */
 } EsrGloveCfg;
 
 /* Scalars block (device float[ESR_GLOVE_NSCAL]) shared by the three phases.  After
@@ -363,9 +372,15 @@ int esr_pipeline_capture_begin(EsrPipeline* p, int32_t which);
 int esr_pipeline_capture_end(EsrPipeline* p, int32_t which, int32_t k);
 /* ids / counts: pinned host or device memory.  flags bit 0: also copy the step's loss to loss_host[step % loss_len]
  * (asynchronously, main stream); bit 1: the inputs were produced on caller_stream (NULL = the legacy default stream),
- * stage them behind it. */
+ * stage them behind it; bit 2: ids and counts are adjacent views of ONE allocation (one copy instead of two); bit 3: the
+ * inputs are pinned host memory -- staged by a small kernel reading them over PCIe, which keeps the host->device copy
+ * engine free for the parameter uploads of the graph launches. */
 int esr_pipeline_submit(EsrPipeline* p, const void* ids, const void* counts, esr_stream_t caller_stream, int32_t flags,
                         int64_t* step_out);
+/* Developer aid: timeline of the next n <= 64 steps; trace_read synchronises the device and returns, per traced step, the
+ * boundaries {copy begin, copy end, plan begin, plan end, step begin, step end} in microseconds since the arming call. */
+int esr_pipeline_trace(EsrPipeline* p, int32_t n);
+int esr_pipeline_trace_read(EsrPipeline* p, float* out_us, int32_t* n_out);
 int esr_pipeline_sync(const EsrPipeline* p);
 int esr_pipeline_destroy(EsrPipeline* p);
 
@@ -379,6 +394,17 @@ int esr_pipeline_destroy(EsrPipeline* p);
 int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks,
                         const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t D, float* out,
                         float* out_bias, esr_stream_t stream);
+/* Owner-routed step: the same lookup for the REMOTE rows only -- a row this rank owns is read where it lives.
+ * order / counts: the route plan of the unique rows (esr_route_plan_i32: bucket order, per-owner counts).  Row u lands in
+ * out[u,:] / out_bias[u] (the fetch region behind the shard; see esr_plan_compact_owner_i32). */
+int esr_peer_gather_remote_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks, int32_t me,
+                               const int32_t* uniq, const int32_t* order, const int32_t* counts, int64_t cap, int32_t D,
+                               float* out, float* out_bias, esr_stream_t stream);
+/* The plan re-expressed in ADDRESSES of the unified table [shard rows ; fetch region]: key of unique row u =
+ * uniq[u] / n_ranks when this rank owns it, base + u otherwise (base = rows of the shard allocation); partner likewise.
+ * scratch: n_slots ints. */
+int esr_plan_compact_owner_i32(const EsrPlan* plan, int32_t n_ranks, int32_t me, int32_t base, int32_t* sorted_keys,
+                               int32_t* partner, int32_t* scratch, esr_stream_t stream);
 /* Owner `me`: from every source rank's published esr_route_plan_i32 outputs (send_counts[n],
  * send_local[]) copy the owner-local ids destined to me into recv_ids (source-major), write
  * src_meta[s] = {offset in recv_ids, count, displacement in source s's bucket order}, src_meta[3n] = total
@@ -399,7 +425,7 @@ int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* pee
  * optax.adagrad to the shard in place.  All loads are local. */
 int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db,
                                int32_t n_ranks, const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
-                               int64_t map_stride, int32_t* desc /* scratch [recv_cap * (n_ranks + 1)] */, int64_t recv_cap,
+                               int64_t map_stride, int32_t* desc /* scratch [recv_cap * (n_ranks + 2)], 8-byte aligned, recv_cap * n_ranks even */, int64_t recv_cap,
                                float lr, float eps, esr_stream_t stream);
 
 /* All-reduce (sum) of count <= 6 floats across the ranks -- count == 0: a device barrier -- over symmetric peer memory,
@@ -449,7 +475,9 @@ int esr_peer_collect_pairs_i32(const int32_t* in_ids, const float* in_cnt, const
                                int32_t* err, esr_stream_t stream);
 
 /* The two halves of esr_peer_merge_adagrad_f32: resolve depends on the ids only (side stream, overlaps the row
- * pass); apply needs the gradients (after the device barrier). */
+ * pass); apply needs the gradients (after the device barrier).  desc: [recv_cap * (n_ranks + 2)] ints, 8-byte aligned --
+ * per received entry the inbox row of every source naming its row, then one 8-byte record per OWNED row
+ * {entry | several-sources flag << 31, owner-local row} that the merge streams. */
 int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_meta, const int32_t* slot_map,
                          int64_t map_stride, int32_t* desc, int64_t recv_cap, esr_stream_t stream);
 int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,

@@ -202,7 +202,7 @@ def test_find_knn_matches_oracle_with_ties():
 
 
 @pytest.mark.parametrize("V,D,T,k", [(50001, 128, 8, 10), (300, 64, 3, 10), (20000, 32, 1, 1024), (7000, 256, 64, 5),
-                                     (2262, 128, 2, 500)])
+                                     (2262, 128, 2, 500), (9000, 16, 5, 7), (4000, 512, 3, 20)])
 def test_fused_topk_scan_matches_oracle_both_tie_orders(V, D, T, k):
     """esr_topk_scan_f32 (one table pass, running top-k in shared memory) against the full-sort restatements:
     oracle.glove.top_k = tail of the stable ascending argsort (dump_knn: ties HIGHER index first) and
@@ -235,13 +235,14 @@ def test_fused_topk_scan_matches_oracle_both_tie_orders(V, D, T, k):
             kth = np.sort(dev_sc)[-k]
             must = np.flatnonzero(dev_sc > kth + 1e-5)
             assert set(must.tolist()) <= set(idx[t].tolist())
-    # the planted exact ties at the very top of query 0 (token 3): order is the reference's, bit for bit
-    top, _ = og.top_k(E, tokens[:1], 3)                                      # tail of the stable argsort
-    assert top[0].tolist() == [V - 1, V // 2, 3]
-    _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=True)
-    assert _np(idx)[0][:3].tolist() == [V - 1, V // 2, 3]
-    _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=False)       # jax.lax.top_k order
-    assert _np(idx)[0][:3].tolist() == [3, V // 2, V - 1]
+    if D >= 64:   # (at small D a foreign row can out-score the self dot product; the ordering asserts above still hold)
+        # the planted exact ties at the very top of query 0 (token 3): order is the reference's, bit for bit
+        # (tail of the stable ascending argsort of EXACTLY tied scores: [V-1, V//2, 3]; the fp32 BLAS scores of the NumPy
+        # restatement are not bit-identical for identical rows, the kernel's are: same code path for every row)
+        _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=True)
+        assert _np(idx)[0][:3].tolist() == [V - 1, V // 2, 3]
+        _, idx = engine.table_topk(table, q[:1], min(k, 8), ties_high_index_first=False)       # jax.lax.top_k order
+        assert _np(idx)[0][:3].tolist() == [3, V // 2, V - 1]
 
 
 def test_spotify_eval_step_matches_oracle():

@@ -63,8 +63,12 @@ def test_peer_integer_kernels_bit_exact(n):
         assert np.array_equal(k.desc[:total * n].cpu().numpy().reshape(total, n), desc)
         n_own = int(got_meta[3 * n + 1])
         assert n_own == int(own.sum())
-        own_list = k.desc[vp.inbox_cap * n: vp.inbox_cap * n + n_own].cpu().numpy()
-        assert np.array_equal(np.sort(own_list), np.flatnonzero(own))
+        recs = k.desc[vp.inbox_cap * n: vp.inbox_cap * n + 2 * n_own].cpu().numpy().reshape(n_own, 2)   # {k | multi << 31, x}
+        own_k = recs[:, 0] & 0x7fffffff
+        order_k = np.argsort(own_k)
+        assert np.array_equal(own_k[order_k], np.flatnonzero(own))
+        assert np.array_equal(recs[order_k, 1], recv[own])                          # owner-local row of every record
+        assert np.array_equal(recs[order_k, 0] < 0, (desc[own] >= 0).sum(axis=1) > 1)   # several-sources flag
         em = oidx.peer_emit_map(counts, me, uniqs[me], invs[me], n)
         assert np.array_equal(k.emit_map[:len(em)].cpu().numpy(), em)
         assert int(k.err.item()) == 0

@@ -46,8 +46,10 @@ class VirtualPeerGlove:
         for r in range(n):
             k = _Rank()
             V_loc = shard_rows(V, r, n)
-            k.rows = torch.zeros(V_max, D, device=self.dev)
-            k.bias = torch.zeros(V_max, device=self.dev)
+            # owner-routed: [shard ; fetch region] in one allocation (local rows are addressed in place, never copied)
+            extra = n_slots if B_cap is not None else 0
+            k.rows = torch.zeros(V_max + extra, D, device=self.dev)
+            k.bias = torch.zeros(V_max + extra, device=self.dev)
             k.shard = EmbeddingTable.wrap(k.rows[:V_loc], bias=k.bias[:V_loc], acc=torch.full((V_loc, D), 0.1, device=self.dev),
                                           bias_acc=torch.full((V_loc,), 0.1, device=self.dev))
             k.counts = torch.zeros(16, **i32)
@@ -60,8 +62,9 @@ class VirtualPeerGlove:
             k.err = torch.zeros(1, **i32)
             k.n_valid = torch.zeros(1, **i32) if B_cap is not None else None
             k.plan = IndexPlan(n_slots, V + (1 if B_cap is not None else 0), self.dev, n_valid=k.n_valid)   # pad key = V
-            k.compact = EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False)
-            k.cplan = IndexPlan(n_slots, n_slots, self.dev, n_valid=k.n_valid)
+            k.compact = (EmbeddingTable.wrap(k.rows, bias=k.bias) if B_cap is not None
+                         else EmbeddingTable(n_slots, D, self.dev, sparse=False, adagrad=False))
+            k.cplan = IndexPlan(n_slots, V_max + n_slots, self.dev, n_valid=k.n_valid)
             cs, ps = k.cplan.s, k.plan.s
             cs.n_slots = n_slots
             cs.perm, cs.useg, cs.seg_off, cs.n_uniq = ps.perm, ps.useg, ps.seg_off, ps.n_uniq
@@ -69,7 +72,7 @@ class VirtualPeerGlove:
             k.recv_ids = torch.zeros(self.inbox_cap, **i32)
             k.src_meta = torch.zeros(3 * 8 + 4, **i32)
             k.slot_map = torch.full((n, V_max), -1, **i32)
-            k.desc = torch.zeros(self.inbox_cap * (n + 1), **i32)
+            k.desc = torch.zeros(self.inbox_cap * (n + 2), **i32)   # per entry: n source rows; then 8-byte owner records
             self.ranks.append(k)
         self.map_stride = V_max
         self.p_rows = _ptr_array([k.rows for k in self.ranks])
@@ -209,8 +212,20 @@ class VirtualOwnerRoutedGlove(VirtualPeerGlove):
             k.plan.build(k.keys)
             self.ops.route_plan(k.plan.uniq, k.plan.n_uniq, self.n, out=(k.order, k.send_local, k.counts, k.inv_order))
             k.cplan.s.n_slots = k.plan.n_slots
-            L.check(lib.esr_plan_compact_i32(C.byref(k.plan.s), L.ptr(k.cplan.sorted_keys), L.ptr(k.cplan.partner),
-                                             L.ptr(k.cplan.uniq), L.ptr(k.scratch), L.stream_ptr()), "esr_plan_compact_i32")
+        for r, k in enumerate(self.ranks):
+            L.check(lib.esr_plan_compact_owner_i32(C.byref(k.plan.s), self.n, r, self.map_stride, L.ptr(k.cplan.sorted_keys),
+                                                   L.ptr(k.cplan.partner), L.ptr(k.scratch), L.stream_ptr()),
+                    "esr_plan_compact_owner_i32")
+
+    def fetch_phase(self, counts):
+        lib, n, sp = L.lib(), self.n, L.stream_ptr()
+        V_max = self.map_stride
+        for r, k in enumerate(self.ranks):
+            L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, r, L.ptr(k.plan.uniq), L.ptr(k.order),
+                                                   L.ptr(k.counts), k.plan.capacity, self.D, L.ptr(k.rows[V_max:]),
+                                                   L.ptr(k.bias[V_max:]), sp), "esr_peer_gather_remote_f32")
+            k.step_fn.prep(k.cplan, counts[r])
+        self._all_reduce(0, 3)
 
     def step(self, ids, counts):
         self.route_phase(ids, counts)
