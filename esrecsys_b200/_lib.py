@@ -124,11 +124,13 @@ _SIGNATURES = {
     "esr_pipeline_destroy": (C.c_int, [_P]),
     "esr_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "esr_topk_scan_f32": (C.c_int, [C.POINTER(EsrTopkCfg), _P, _P, _P, C.c_size_t, _P]),
-    "esr_peer_gather_remote_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "esr_peer_gather_remote_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P]),
+    "esr_peer_apply_parts_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
+                                           C.c_float, C.c_float, C.c_int32, _P]),
     "esr_plan_compact_owner_i32": (C.c_int, [C.POINTER(EsrPlan), C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "esr_peer_route_pairs_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "esr_peer_route_pairs_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "esr_peer_collect_pairs_i32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    "esr_peer_route_pairs_i32": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "esr_peer_collect_pairs_i32": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "esr_peer_apply_adagrad_f32": (C.c_int, [C.POINTER(EsrTable), _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                              C.c_float, C.c_float, _P]),
     "esr_route_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -84,7 +84,7 @@ template <int TPR, int ROWS>
 __global__ void __launch_bounds__(kThreads) k_peer_gather_remote(const __grid_constant__ PeerPtrs rows, const __grid_constant__ PeerPtrs bias,
                                                                  const int32_t* __restrict__ uniq, const int32_t* __restrict__ order,
                                                                  const int32_t* __restrict__ counts, int me, Cyclic cyc, int D4,
-                                                                 float4* __restrict__ out, float* __restrict__ out_bias) {
+                                                                 float4* __restrict__ out, float* __restrict__ out_bias, int parts) {
   const int lane = threadIdx.x % TPR;
   int before = 0, mine = 0, total = 0;
   for (int o = 0; o < cyc.n; ++o) {
@@ -111,19 +111,21 @@ __global__ void __launch_bounds__(kThreads) k_peer_gather_remote(const __grid_co
         const int owner = cyc.owner(row);
         const int64_t local = cyc.local(row);
         src[r] = reinterpret_cast<const float4*>(rows.p[owner]) + local * D4;
-        if (lane == 0) bv[r] = reinterpret_cast<const float*>(bias.p[owner])[local];
+        if (lane == 0 && (parts & 2)) bv[r] = reinterpret_cast<const float*>(bias.p[owner])[local];
       }
     }
-    for (int c = lane; c < D4; c += TPR) {
-      float4 v[ROWS];
+    if (parts & 1) {
+      for (int c = lane; c < D4; c += TPR) {
+        float4 v[ROWS];
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r)
-        if (src[r]) v[r] = src[r][c];
+        for (int r = 0; r < ROWS; ++r)
+          if (src[r]) v[r] = src[r][c];
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r)
-        if (src[r]) out[(int64_t)u[r] * D4 + c] = v[r];  // default caching: the row pass re-reads these from L2
+        for (int r = 0; r < ROWS; ++r)
+          if (src[r]) out[(int64_t)u[r] * D4 + c] = v[r];  // default caching: the row pass re-reads these from L2
+      }
     }
-    if (lane == 0) {
+    if (lane == 0 && (parts & 2)) {
 #pragma unroll
       for (int r = 0; r < ROWS; ++r)
         if (src[r]) out_bias[u[r]] = bv[r];
@@ -395,17 +397,19 @@ extern "C" int esr_peer_gather_f32(const void* const* peer_rows, const void* con
 
 extern "C" int esr_peer_gather_remote_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks, int32_t me,
                                           const int32_t* uniq, const int32_t* order, const int32_t* counts, int64_t cap,
-                                          int32_t D, float* out, float* out_bias, esr_stream_t stream_) {
+                                          int32_t D, float* out, float* out_bias, int32_t parts, esr_stream_t stream_) {
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && cap >= 0 && D > 0 && (D % 4) == 0);
+  ESR_REQUIRE((parts & 3) != 0);
   if (cap == 0 || n_ranks == 1) return ESR_OK;  // one rank: nothing is remote
   PeerPtrs pr, pb;
   ESR_REQUIRE(load_ptrs(&pr, peer_rows, n_ranks) && load_ptrs(&pb, peer_bias, n_ranks));
   ESR_REQUIRE(uniq && order && counts && out && out_bias && (reinterpret_cast<uintptr_t>(out) % 16) == 0);
   const int D4 = D / 4;
-  const int tpr = tpr_for(D4);
+  // biases only: one lane per row does the work, so use the narrowest group
+  const int tpr = (parts & 1) ? tpr_for(D4) : 1;
   constexpr int ROWS = 4;
   const int64_t want = ceil_div(ceil_div(cap, ROWS) * tpr, kThreads);
-  const int64_t persistent = (int64_t)sm_count() * 8;
+  const int64_t persistent = (int64_t)sm_count() * ((parts & 1) ? 8 : 2);
   const unsigned grid = (unsigned)(want < persistent ? want : persistent);
   Cyclic cyc;
   cyc.n = n_ranks;
@@ -413,7 +417,7 @@ extern "C" int esr_peer_gather_remote_f32(const void* const* peer_rows, const vo
   for (int b = 0; b < 4; ++b)
     if ((1 << b) == n_ranks) cyc.shift = b;
   ESR_DISPATCH_TPR(tpr, (k_peer_gather_remote<TPR, ROWS><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-                            pr, pb, uniq, order, counts, me, cyc, D4, reinterpret_cast<float4*>(out), out_bias)));
+                            pr, pb, uniq, order, counts, me, cyc, D4, reinterpret_cast<float4*>(out), out_bias, parts)));
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }
@@ -448,29 +452,43 @@ extern "C" int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, in
 
 // Owner side, step 2 (after every rank's gradients have landed): merge in source order + optax.adagrad, then restore
 // slot_map to -1.
+// parts: 1 = embedding rows, 2 = biases + restore slot_map.  The two halves touch disjoint state, so a caller may run them on
+// different streams: the rows as soon as every rank's gradient ROWS have landed, the biases after the bias gradients have.
+extern "C" int esr_peer_apply_parts_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+                                        const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
+                                        int64_t map_stride, const int32_t* desc, int64_t recv_cap, float lr, float eps,
+                                        int32_t parts, esr_stream_t stream_) {
+  ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
+  ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
+  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && recv_cap > 0);
+  ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0 && (parts & 3) != 0);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int D4 = shard->D / 4;
+  const int2* own_rec = reinterpret_cast<const int2*>(desc + recv_cap * n_ranks);  // 8-byte aligned (resolve checks it)
+  if (parts & 1) {
+    const int tpr = tpr_for(D4);
+    const int grid = 8 * sm_count();
+    ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 4><<<grid, kThreads, 0, stream>>>(
+                              reinterpret_cast<const float4*>(inbox_dE), n_ranks, src_meta, desc, own_rec, D4, shard->rows[0],
+                              shard->acc, lr, eps)));
+    ESR_LAUNCH_CHECK();
+  }
+  if (parts & 2) {
+    k_peer_merge_bias<<<2 * sm_count(), kThreads, 0, stream>>>(inbox_db, n_ranks, src_meta, desc, own_rec, shard->bias,
+                                                               shard->bias_acc, lr, eps);
+    ESR_LAUNCH_CHECK();
+    k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
+    ESR_LAUNCH_CHECK();
+  }
+  return ESR_OK;
+}
+
 extern "C" int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
                                           const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
                                           int64_t map_stride, const int32_t* desc, int64_t recv_cap, float lr, float eps,
                                           esr_stream_t stream_) {
-  ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
-  ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
-  ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && recv_cap > 0);
-  ESR_REQUIRE(inbox_dE && inbox_db && (reinterpret_cast<uintptr_t>(inbox_dE) % 16) == 0);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int D4 = shard->D / 4;
-  const int2* own_rec = reinterpret_cast<const int2*>(desc + recv_cap * n_ranks);  // 8-byte aligned: recv_cap * n is even or padded by the caller
-  const int tpr = tpr_for(D4);
-  const int grid = 8 * sm_count();
-  ESR_DISPATCH_TPR(tpr, (k_peer_merge_adagrad<TPR, 4><<<grid, kThreads, 0, stream>>>(
-                            reinterpret_cast<const float4*>(inbox_dE), n_ranks, src_meta, desc, own_rec, D4, shard->rows[0],
-                            shard->acc, lr, eps)));
-  ESR_LAUNCH_CHECK();
-  k_peer_merge_bias<<<2 * sm_count(), kThreads, 0, stream>>>(inbox_db, n_ranks, src_meta, desc, own_rec, shard->bias,
-                                                             shard->bias_acc, lr, eps);
-  ESR_LAUNCH_CHECK();
-  k_peer_clear_map<<<2 * sm_count(), kThreads, 0, stream>>>(recv_ids, src_meta, n_ranks, slot_map, map_stride);
-  ESR_LAUNCH_CHECK();
-  return ESR_OK;
+  return esr_peer_apply_parts_f32(shard, inbox_dE, inbox_db, n_ranks, recv_ids, src_meta, slot_map, map_stride, desc, recv_cap,
+                                  lr, eps, 3, stream_);
 }
 
 extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
@@ -636,8 +654,8 @@ extern "C" int esr_peer_emit_plan_i32(const void* const* peer_counts, int32_t n_
 // The triples themselves are 12 bytes per pair: routing them costs 2 % of what it saves.
 //
 //  esr_peer_route_pairs_i32   source side (ids only: side stream): STABLE partition of my B pairs by owner(i) written
-//                             straight into the owners' pair inboxes (region of source `me`), plus my per-owner
-//                             counts.  Stable => the received batch is a deterministic function of the global batch.
+//                             straight into the owners' pair inboxes (region of source `me`, one 16-byte record
+//                             {i, j, count, 0} = one NVLink store per pair), plus my per-owner counts.  Stable => the received batch is a deterministic function of the global batch.
 //  esr_peer_collect_pairs_i32 owner side, after a barrier: concatenates the regions in source order into the flat
 //                             [i ; j] slot array of the plan (capacity B_cap per half, padding key = pad_key sorts to
 //                             the end), the counts, and *n_valid = 2 m.  err |= 2 if m > B_cap (pairs dropped).
@@ -719,8 +737,7 @@ __global__ void __launch_bounds__(ESR_MAX_PEERS * 32) k_pair_scan(const int32_t*
 // stable scatter of the tile's pairs into the owners' inbox regions of source `me`
 __global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __restrict__ ids, const float* __restrict__ counts,
                                                            int64_t B, Cyclic cyc, int me, const int32_t* __restrict__ blk_base,
-                                                           const __grid_constant__ PeerPtrs peer_ids,
-                                                           const __grid_constant__ PeerPtrs peer_cnt) {
+                                                           const __grid_constant__ PeerPtrs peer_ids) {
   __shared__ unsigned long long wlo[kThreads / 32], whi[kThreads / 32];
   const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
   int32_t vi[kRouteItems], vj[kRouteItems];
@@ -763,17 +780,15 @@ __global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __rest
 #pragma unroll
       for (int o = 0; o < ESR_MAX_PEERS; ++o)
         if (o == own[k]) pos = run[o]++;
-      // region of source `me` in owner's inbox: ids [me][2][B], counts [me][B]
-      int32_t* dst = reinterpret_cast<int32_t*>(const_cast<void*>(peer_ids.p[own[k]])) + (int64_t)me * 2 * B;
-      dst[pos] = vi[k];
-      dst[B + pos] = vj[k];
-      reinterpret_cast<float*>(const_cast<void*>(peer_cnt.p[own[k]]))[(int64_t)me * B + pos] = vx[k];
+      // region of source `me` in owner's inbox: B records of 16 bytes {i, j, count bits, 0} -- ONE remote store per pair
+      int4* dst = reinterpret_cast<int4*>(const_cast<void*>(peer_ids.p[own[k]])) + (int64_t)me * B;
+      dst[pos] = make_int4(vi[k], vj[k], __float_as_int(vx[k]), 0);
     }
   }
 }
 
 // owner side: regions -> flat [i ; j] keys of capacity 2 * B_cap, counts, n_valid; padding keys sort to the end
-__global__ void __launch_bounds__(kThreads) k_pair_collect(const int32_t* __restrict__ in_ids, const float* __restrict__ in_cnt,
+__global__ void __launch_bounds__(kThreads) k_pair_collect(const int4* __restrict__ in_rec,
                                                            const int32_t* __restrict__ in_counts, int n_ranks, int64_t B,
                                                            int64_t B_cap, int32_t pad_key, int32_t* __restrict__ keys,
                                                            float* __restrict__ counts, int32_t* __restrict__ n_valid,
@@ -799,9 +814,10 @@ __global__ void __launch_bounds__(kThreads) k_pair_collect(const int32_t* __rest
       int s = 0;
       while (s + 1 < n_ranks && p >= off[s + 1]) ++s;
       const int64_t q = p - off[s];
-      keys[p] = in_ids[(int64_t)s * 2 * B + q];
-      keys[B_cap + p] = in_ids[(int64_t)s * 2 * B + B + q];
-      counts[p] = in_cnt[(int64_t)s * B + q];
+      const int4 r = in_rec[(int64_t)s * B + q];
+      keys[p] = r.x;
+      keys[B_cap + p] = r.y;
+      counts[p] = __int_as_float(r.z);
     } else {
       keys[p] = pad_key;
       keys[B_cap + p] = pad_key;
@@ -822,6 +838,137 @@ Cyclic make_cyclic(int n_ranks) {
 }  // namespace
 }  // namespace esr
 
+// ---------------------------------------------------------------------------------------------
+// Route plan for up to ESR_MAX_PEERS ranks without a sort: the unique rows arrive sorted, so bucketing them by owner is a
+// stable partition -- tile counts, a scan over the tiles, a stable scatter (the same three small kernels as the pair
+// routing above) instead of a cub radix sort + two kernels (35 -> ~12 us at 137k rows).  Same outputs, bit for bit
+// (oracle/index.py route_plan): order (bucket position -> unique index), owner-local ids in bucket order, per-owner counts,
+// inverse order.
+// ---------------------------------------------------------------------------------------------
+namespace esr {
+namespace {
+
+__global__ void __launch_bounds__(kThreads) k_route_count(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq,
+                                                          int64_t cap, Cyclic cyc, int32_t* __restrict__ blk_cnt) {
+  __shared__ int cnt[ESR_MAX_PEERS];
+  if (threadIdx.x < ESR_MAX_PEERS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t n = min((int64_t)*n_uniq, cap);
+  const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
+  OwnerCounts c{0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k)
+    if (base + k < n) c.add(cyc.owner(uniq[base + k]));
+  for (int o = 0; o < cyc.n; ++o) {
+    int v = c.get(o);
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[o], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < ESR_MAX_PEERS) blk_cnt[blockIdx.x * ESR_MAX_PEERS + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// one block, warp o scans owner o over the tiles; then the bucket displacements (prefix over the owners)
+__global__ void __launch_bounds__(ESR_MAX_PEERS * 32) k_route_scan(const int32_t* __restrict__ blk_cnt, int n_blocks, int n_ranks,
+                                                                   int32_t* __restrict__ blk_base, int32_t* __restrict__ send_counts) {
+  __shared__ int tot[ESR_MAX_PEERS];
+  const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int carry = 0;
+  if (o < n_ranks) {
+    for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+      const int b = b0 + lane;
+      const int v = b < n_blocks ? blk_cnt[b * ESR_MAX_PEERS + o] : 0;
+      int x = v;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const int y = __shfl_up_sync(FULL, x, s);
+        if (lane >= s) x += y;
+      }
+      if (b < n_blocks) blk_base[b * ESR_MAX_PEERS + o] = carry + x - v;
+      carry += __shfl_sync(FULL, x, 31);
+    }
+  }
+  if (lane == 0) tot[o] = o < n_ranks ? carry : 0;
+  __syncthreads();
+  if (threadIdx.x < n_ranks) send_counts[threadIdx.x] = tot[threadIdx.x];
+  // fold the bucket displacement into every tile base
+  int dsp = 0;
+  for (int q = 0; q < o; ++q) dsp += tot[q];
+  if (o < n_ranks)
+    for (int b = lane; b < n_blocks; b += 32) blk_base[b * ESR_MAX_PEERS + o] += dsp;
+}
+
+__global__ void __launch_bounds__(kThreads) k_route_scatter(const int32_t* __restrict__ uniq, const int32_t* __restrict__ n_uniq,
+                                                            int64_t cap, Cyclic cyc, const int32_t* __restrict__ blk_base,
+                                                            int32_t* __restrict__ order, int32_t* __restrict__ send_local,
+                                                            int32_t* __restrict__ inv_order) {
+  __shared__ unsigned long long wlo[kThreads / 32], whi[kThreads / 32];
+  const int64_t n = min((int64_t)*n_uniq, cap);
+  const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
+  int32_t row[kRouteItems];
+  int own[kRouteItems];
+  OwnerCounts c{0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k) {
+    own[k] = -1;
+    if (base + k < n) {
+      row[k] = uniq[base + k];
+      own[k] = cyc.owner(row[k]);
+      c.add(own[k]);
+    }
+  }
+  unsigned long long tlo, thi;
+  OwnerCounts ex;
+  ex.lo = warp_excl_scan_u64(c.lo, &tlo);
+  ex.hi = warp_excl_scan_u64(c.hi, &thi);
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 31) {
+    wlo[wid] = tlo;
+    whi[wid] = thi;
+  }
+  __syncthreads();
+  for (int w = 0; w < wid; ++w) {
+    ex.lo += wlo[w];
+    ex.hi += whi[w];
+  }
+  int run[ESR_MAX_PEERS];
+#pragma unroll
+  for (int o = 0; o < ESR_MAX_PEERS; ++o) run[o] = o < cyc.n ? blk_base[blockIdx.x * ESR_MAX_PEERS + o] + ex.get(o) : 0;
+#pragma unroll
+  for (int k = 0; k < kRouteItems; ++k) {
+    if (own[k] >= 0) {
+      int pos = 0;
+#pragma unroll
+      for (int o = 0; o < ESR_MAX_PEERS; ++o)
+        if (o == own[k]) pos = run[o]++;
+      order[pos] = (int32_t)(base + k);
+      send_local[pos] = (int32_t)cyc.local(row[k]);
+      if (inv_order) inv_order[base + k] = pos;
+    }
+  }
+}
+
+}  // namespace
+
+// called by esr_route_plan_i32 (shard_ops.cu) when n_ranks <= ESR_MAX_PEERS; ws: 2 * ceil(cap / 2048) * 8 ints
+int route_plan_small(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks, int32_t* order,
+                     int32_t* send_local, int32_t* send_counts, int32_t* inv_order, void* ws, cudaStream_t stream) {
+  const int blocks = (int)ceil_div(cap, (int64_t)kRouteTile);
+  Carver c(ws);
+  int32_t* blk_cnt = c.take<int32_t>((size_t)blocks * ESR_MAX_PEERS);
+  int32_t* blk_base = c.take<int32_t>((size_t)blocks * ESR_MAX_PEERS);
+  const Cyclic cyc = make_cyclic(n_ranks);
+  k_route_count<<<blocks, kThreads, 0, stream>>>(uniq, n_uniq, cap, cyc, blk_cnt);
+  ESR_LAUNCH_CHECK();
+  k_route_scan<<<1, ESR_MAX_PEERS * 32, 0, stream>>>(blk_cnt, blocks, n_ranks, blk_base, send_counts);
+  ESR_LAUNCH_CHECK();
+  k_route_scatter<<<blocks, kThreads, 0, stream>>>(uniq, n_uniq, cap, cyc, blk_base, order, send_local, inv_order);
+  ESR_LAUNCH_CHECK();
+  return ESR_OK;
+}
+
+}  // namespace esr
+
 extern "C" size_t esr_peer_route_pairs_workspace_bytes(int64_t B) {
   if (B < 0) return 0;
   const int64_t blocks = ceil_div(B > 0 ? B : 1, (int64_t)kRouteTile);
@@ -829,15 +976,14 @@ extern "C" size_t esr_peer_route_pairs_workspace_bytes(int64_t B) {
 }
 
 extern "C" int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts, int64_t B, int32_t n_ranks, int32_t me,
-                                        void* const* peer_pair_ids, void* const* peer_pair_cnt,
-                                        void* const* peer_pair_counts, int32_t* my_counts, void* ws, size_t ws_bytes,
-                                        esr_stream_t stream_) {
+                                        void* const* peer_pair_rec, void* const* peer_pair_counts, int32_t* my_counts,
+                                        void* ws, size_t ws_bytes, esr_stream_t stream_) {
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && B >= 0 && B < ((int64_t)1 << 30));
   ESR_REQUIRE(my_counts != nullptr);
-  PeerPtrs pi, pc, pn;
-  ESR_REQUIRE(load_ptrs(&pi, reinterpret_cast<const void* const*>(peer_pair_ids), n_ranks) &&
-              load_ptrs(&pc, reinterpret_cast<const void* const*>(peer_pair_cnt), n_ranks) &&
+  PeerPtrs pi, pn;
+  ESR_REQUIRE(load_ptrs(&pi, reinterpret_cast<const void* const*>(peer_pair_rec), n_ranks) &&
               load_ptrs(&pn, reinterpret_cast<const void* const*>(peer_pair_counts), n_ranks));
+  for (int r = 0; r < n_ranks; ++r) ESR_REQUIRE((reinterpret_cast<uintptr_t>(pi.p[r]) % 16) == 0);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = (int)ceil_div(B > 0 ? B : 1, (int64_t)kRouteTile);
   ESR_REQUIRE(ws != nullptr && (B == 0 || (ids && counts)));
@@ -851,21 +997,21 @@ extern "C" int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts,
   k_pair_scan<<<1, ESR_MAX_PEERS * 32, 0, stream>>>(blk_cnt, blocks, n_ranks, me, blk_base, pn, my_counts);
   ESR_LAUNCH_CHECK();
   if (B > 0) {
-    k_pair_scatter<<<blocks, kThreads, 0, stream>>>(ids, counts, B, cyc, me, blk_base, pi, pc);
+    k_pair_scatter<<<blocks, kThreads, 0, stream>>>(ids, counts, B, cyc, me, blk_base, pi);
     ESR_LAUNCH_CHECK();
   }
   return ESR_OK;
 }
 
-extern "C" int esr_peer_collect_pairs_i32(const int32_t* in_ids, const float* in_cnt, const int32_t* in_counts, int32_t n_ranks,
+extern "C" int esr_peer_collect_pairs_i32(const void* in_rec, const int32_t* in_counts, int32_t n_ranks,
                                           int64_t B, int64_t B_cap, int32_t pad_key, int32_t* keys, float* counts,
                                           int32_t* n_valid, int32_t* err, esr_stream_t stream_) {
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && B >= 0 && B_cap > 0 && B_cap < ((int64_t)1 << 30));
-  ESR_REQUIRE(in_ids && in_cnt && in_counts && keys && counts && n_valid && err);
+  ESR_REQUIRE(in_rec && in_counts && keys && counts && n_valid && err && (reinterpret_cast<uintptr_t>(in_rec) % 16) == 0);
   const int64_t want = ceil_div(B_cap, (int64_t)kThreads);
   const int64_t cap = (int64_t)sm_count() * 8;
   k_pair_collect<<<(unsigned)(want < cap ? want : cap), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      in_ids, in_cnt, in_counts, n_ranks, B, B_cap, pad_key, keys, counts, n_valid, err);
+      static_cast<const int4*>(in_rec), in_counts, n_ranks, B, B_cap, pad_key, keys, counts, n_valid, err);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

@@ -17,10 +17,11 @@
 #include "esr_common.cuh"
 
 namespace {
-// Host batches are staged by a few CTAs reading the pinned block over PCIe (UVA maps pinned host memory into the device
-// address space), not by the copy engine: a CUDA-graph launch uploads its node parameters through the same host->device
-// engine, so a 60 us DMA of the next batch in flight delayed the start of the plan / step graphs by 20-35 us per step
-// (timeline probe, profiles/r2_pipeline_timeline.txt).
+// Host batches are staged by a FEW CTAs reading the pinned block over PCIe (UVA maps pinned host memory into the device
+// address space), not by the copy engine.  Measured (esr_pipeline_trace, profiles/r2_pipeline_timeline.txt): while a 3 MB
+// upload runs at full PCIe rate -- DMA or 24 CTAs alike, ~60 us -- the plan / step graphs of the steps in flight start
+// 20-35 us late (their launches also have to come over PCIe), 184 us per step against 149 us from device-resident batches;
+// throttled to 2-4 CTAs the upload takes ~110 us, still hidden behind the 149 us step, and a step costs 158-165 us.
 __global__ void __launch_bounds__(256) k_stage_copy(const int4* __restrict__ src, int4* __restrict__ dst, int64_t n16) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -36,7 +37,9 @@ __global__ void __launch_bounds__(256) k_stage_copy(const int4* __restrict__ src
 
 int stage(void* dst, const void* src, size_t bytes, bool by_kernel, cudaStream_t stream) {
   if (by_kernel && (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
-    k_stage_copy<<<24, 256, 0, stream>>>(static_cast<const int4*>(src), static_cast<int4*>(dst), (int64_t)(bytes / 16));
+    static const int ctas = getenv("ESR_PIPE_STAGE_CTAS") ? atoi(getenv("ESR_PIPE_STAGE_CTAS")) : 3;  // throttled on purpose: see the comment on k_stage_copy
+    static const int thr = getenv("ESR_PIPE_STAGE_THREADS") ? atoi(getenv("ESR_PIPE_STAGE_THREADS")) : 256;
+    k_stage_copy<<<ctas, thr, 0, stream>>>(static_cast<const int4*>(src), static_cast<int4*>(dst), (int64_t)(bytes / 16));
     ESR_LAUNCH_CHECK();
     return ESR_OK;
   }
@@ -85,7 +88,8 @@ extern "C" int esr_pipeline_create(int32_t depth, int32_t main_high_priority, Es
   int lo = 0, hi = 0;
   ESR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   ESR_CUDA(cudaStreamCreateWithPriority(&p->copy, cudaStreamNonBlocking, lo));
-  ESR_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, lo));
+  static const bool side_hi = getenv("ESR_PIPE_SIDE_HI") != nullptr;  // A/B probe: plan stream above the step stream
+  ESR_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, side_hi ? hi : lo));
   ESR_CUDA(cudaStreamCreateWithPriority(&p->main, cudaStreamNonBlocking, main_high_priority ? hi : lo));
   ESR_CUDA(cudaStreamCreateWithPriority(&p->d2h, cudaStreamNonBlocking, lo));
   ESR_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
@@ -148,6 +152,8 @@ extern "C" int esr_pipeline_capture_end(EsrPipeline* p, int32_t which, int32_t k
   const cudaError_t e = cudaGraphInstantiate(slot, g, 0);
   cudaGraphDestroy(g);
   ESR_CUDA(e);
+  // make the executable graph resident on the device now: a launch then has nothing left to fetch but its trigger
+  ESR_CUDA(cudaGraphUpload(*slot, which == 0 ? p->side : p->main));
   return ESR_OK;
 }
 

@@ -169,6 +169,11 @@ size_t route_sort_bound(int64_t n) { return align_up((size_t)n * 8, 256) + (1 <<
 }  // namespace
 }  // namespace esr
 
+namespace esr {
+int route_plan_small(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks, int32_t* order,
+                     int32_t* send_local, int32_t* send_counts, int32_t* inv_order, void* ws, cudaStream_t stream);  // peer_ops.cu
+}
+
 using namespace esr;
 
 extern "C" size_t esr_route_workspace_bytes(int64_t cap) {
@@ -186,6 +191,8 @@ extern "C" int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, in
   if (cap == 0) return ESR_OK;
   ESR_REQUIRE(ws != nullptr && cap < ((int64_t)1 << 31));
   if (ws_bytes < esr_route_workspace_bytes(cap)) return ESR_EWORKSPACE;
+  if (n_ranks <= ESR_MAX_PEERS)  // stable partition of the (sorted) unique rows: no sort needed
+    return route_plan_small(uniq, n_uniq, cap, n_ranks, order, send_local, send_counts, inv_order, ws, stream);
   Carver c(ws);
   int32_t* owner = c.take<int32_t>(cap);
   int32_t* iota = c.take<int32_t>(cap);

@@ -119,11 +119,12 @@ __device__ __forceinline__ float transpose_sum(float (&v)[G], int gl) {
 
 // R rows per group and iteration (2 * NV independent 16-byte loads in flight per lane), G queries per pass: the query
 // vectors are read from shared memory once per pass for all R rows.
-template <int G, int NV>
+// FULL: D4 == G * NV (every lane column exists: no per-column bounds checks -- they were half of the instructions).
+template <int G, int NV, bool FULL>
 __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int R = 2;
-  const int D4 = a.DA4 + a.DB4;
+  const int D4 = FULL ? G * NV : a.DA4 + a.DB4;
   const int L = a.maxq ? 1 : a.T;
   const int Tp = (a.T + G - 1) / G * G;                                               // queries padded to whole passes
   float4* qs = reinterpret_cast<float4*>(smem_raw);                                   // [Tp][D4]
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const int c = k * G + gl;
-            x[r][k] = c < a.DA4 ? ld_stream(pa + c) : (c < D4 ? ld_stream(pb + (c - a.DA4)) : f4_zero());
+            if (FULL && Bt == nullptr) x[r][k] = ld_stream(pa + c);
+            else x[r][k] = c < a.DA4 ? ld_stream(pa + c) : ((FULL || c < D4) ? ld_stream(pb + (c - a.DA4)) : f4_zero());
           }
         } else {
 #pragma unroll
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) k_topk_scan(const TopkArgs a) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const int c = k * G + gl;
-            qv[k] = c < D4 ? qs[(q0 + j) * D4 + c] : f4_zero();
+            qv[k] = (FULL || c < D4) ? qs[(q0 + j) * D4 + c] : f4_zero();
           }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -310,7 +312,7 @@ bool topk_geom(int64_t N, int D4, int T, int maxq, int k, TopkGeom* g) {
   if (k + tile > cap) return false;
   g->tile_rows = tile;
   const int64_t want = ceil_div(N, (int64_t)tile * 4);  // at least 4 tiles per CTA
-  const int64_t cap_grid = 2 * (int64_t)sm_count();
+  const int64_t cap_grid = 3 * (int64_t)sm_count();
   g->grid = (int)(want < 1 ? 1 : (want < cap_grid ? want : cap_grid));
   g->slab = ceil_div(ceil_div(N, (int64_t)g->grid), (int64_t)rows_per_iter) * rows_per_iter;
   g->grid = (int)ceil_div(N, g->slab);
@@ -322,9 +324,12 @@ bool topk_geom(int64_t N, int D4, int T, int maxq, int k, TopkGeom* g) {
 template <int G>
 int launch_scan(const TopkArgs& a, const TopkGeom& g, cudaStream_t stream) {
   static SmemOptIn configured;
-  if (g.smem_scan > 48 * 1024 && configured.raise(g.smem_scan))
-    ESR_CUDA(cudaFuncSetAttribute(k_topk_scan<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_scan));
-  k_topk_scan<G, 4><<<g.grid, kThreads, g.smem_scan, stream>>>(a);
+  if (g.smem_scan > 48 * 1024 && configured.raise(g.smem_scan)) {
+    ESR_CUDA(cudaFuncSetAttribute(k_topk_scan<G, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_scan));
+    ESR_CUDA(cudaFuncSetAttribute(k_topk_scan<G, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_scan));
+  }
+  if (a.DA4 + a.DB4 == G * 4) k_topk_scan<G, 4, true><<<g.grid, kThreads, g.smem_scan, stream>>>(a);
+  else k_topk_scan<G, 4, false><<<g.grid, kThreads, g.smem_scan, stream>>>(a);
   ESR_LAUNCH_CHECK();
   return ESR_OK;
 }

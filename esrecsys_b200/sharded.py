@@ -523,10 +523,11 @@ class OwnerRoutedGloveTrainer:
     source order + Adagrad; no NCCL inside the step (libesr all-reduce / barrier kernels), both halves CUDA-graphed.
 
       side stream : stage the batch -> route pairs to their owners (peer stores, stable) -> barrier (side sequence)
-                    -> collect my pairs -> index plan (device-side slot count) -> route plan (published) -> compact plan
-      main stream : barrier -> [ids stream: owners pull the id lists, resolve, emit plan] || gather unique rows (own shard
-                    + NVLink loads) -> prep -> all-reduce(3) -> row pass (gradients -> inboxes) -> all-reduce(2) -> finish
-                    -> barrier -> owner merge + Adagrad
+                    -> collect my pairs -> index plan (device-side slot count)
+      main stream : route plan (published) -> barrier -> { gather stream: remote rows over NVLink | ids stream: owners
+                    pull the id lists, resolve, emit plan | main: remote biases -> plan in table addresses -> prep ->
+                    all-reduce(3) } -> row pass (gradients -> inboxes) -> all-reduce(2) -> { main: owner merge of the rows
+                    + Adagrad | ids stream: finish -> barrier -> owner bias merge }
 
     One global step equals the single-table step on the concatenated batch (tests: N virtual ranks on one GPU against
     oracle.glove.step_adagrad; bench.py --gpus N runs the same check before its timed region)."""
@@ -579,21 +580,21 @@ class OwnerRoutedGloveTrainer:
             send_local, p_send_local = symm((n_slots,), torch.int32)
             self.pub.append(dict(counts=counts, p_counts=p_counts, send_local=send_local, p_send_local=p_send_local,
                                  order=torch.empty(n_slots, **i32), inv_order=torch.empty(n_slots, **i32)))
-            ids, p_ids = symm((n, 2, B), torch.int32)
-            cnt, p_cnt = symm((n, B), torch.float32)
+            rec, p_rec = symm((n, B, 4), torch.int32)           # pair inbox: 16-byte records {i, j, count bits, 0} per source
             cc, p_cc = symm((16,), torch.int32)
             cc.zero_()
-            self.pin.append(dict(ids=ids, p_ids=p_ids, cnt=cnt, p_cnt=p_cnt, counts=cc, p_counts=p_cc))
+            self.pin.append(dict(rec=rec, p_rec=p_rec, counts=cc, p_counts=p_cc))
         self.inbox_cap = n_slots * n
         self.inbox_dE, self.p_inbox_dE = symm((self.inbox_cap, D), torch.float32)
         self.inbox_db, self.p_inbox_db = symm((self.inbox_cap,), torch.float32)
         words = int(L.lib().esr_peer_sync_bytes()) // 4
-        self.sync, self.p_sync = symm((words,), torch.int32)           # main-stream sequence (barriers + all-reduces)
-        self.sync2, self.p_sync2 = symm((words,), torch.int32)         # side-stream sequence (pairs-routed barrier)
-        self.sync.zero_()
-        self.sync2.zero_()
-        self.sync_seq = torch.zeros(1, **i32)
-        self.sync_seq2 = torch.zeros(1, **i32)
+        # three independent synchronisation sequences (one per stream that synchronises across ranks): 0 main stream
+        # (barriers + all-reduces), 1 side stream (pairs routed), 2 ids stream (bias gradients landed)
+        self.syncs = []
+        for _ in range(3):
+            blk, p_blk = symm((words,), torch.int32)
+            blk.zero_()
+            self.syncs.append((blk, p_blk, torch.zeros(1, **i32)))
         self.emit_map = torch.zeros(n_slots, **i32)
         self.err = torch.zeros(1, **i32)
         self.ops = LibesrOps(self.dev)
@@ -632,7 +633,9 @@ class OwnerRoutedGloveTrainer:
         self.s_ids = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.s_gather = torch.cuda.Stream(self.dev)
         self.ev_top, self.ev_ids = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_gather, self.ev_rows, self.ev_bias = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._keep = [None] * self.DEPTH
         self.st_ids = [torch.ones(2 * B, **i32) for _ in range(self.DEPTH)]
         self.st_counts = [torch.ones(B, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
@@ -646,8 +649,8 @@ class OwnerRoutedGloveTrainer:
         self._hdls[0].barrier()
 
     # -- synchronisation: libesr kernels over symmetric memory (one NVLink round trip, CUDA-graph capturable) ---------
-    def _sync(self, view=None, side=False):
-        p, seq = (self.p_sync2, self.sync_seq2) if side else (self.p_sync, self.sync_seq)
+    def _sync(self, view=None, side=0):
+        _, p, seq = self.syncs[int(side)]
         buf = L.ptr(view) if view is not None else None
         L.check(L.lib().esr_peer_allreduce_f32(p, self.n, self.rank, buf, buf, view.numel() if view is not None else 0,
                                                L.ptr(seq), L.stream_ptr()), "esr_peer_allreduce_f32")
@@ -663,17 +666,14 @@ class OwnerRoutedGloveTrainer:
         pin, pub, plan, cplan = self.pin[k], self.pub[k], self.plans[k], self.cplans[k]
         sp = L.stream_ptr()
         L.check(lib.esr_peer_route_pairs_i32(L.ptr(self.st_ids[k]), L.ptr(self.st_counts[k]), self.B, n, self.rank,
-                                             pin["p_ids"], pin["p_cnt"], pin["p_counts"], L.ptr(self.my_counts),
+                                             pin["p_rec"], pin["p_counts"], L.ptr(self.my_counts),
                                              L.ptr(self.route_ws), self.route_ws.numel(), sp), "esr_peer_route_pairs_i32")
         self._sync(side=True)                                   # every source's pairs for me have landed
-        L.check(lib.esr_peer_collect_pairs_i32(L.ptr(pin["ids"]), L.ptr(pin["cnt"]), L.ptr(pin["counts"]), n, self.B,
+        L.check(lib.esr_peer_collect_pairs_i32(L.ptr(pin["rec"]), L.ptr(pin["counts"]), n, self.B,
                                                self.B_cap, self.V, L.ptr(self.keys[k]), L.ptr(self.cnt_l[k]),
                                                L.ptr(self.n_valid[k]), L.ptr(self.err), sp), "esr_peer_collect_pairs_i32")
         plan.build(self.keys[k])
-        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
         cplan.s.n_slots = plan.n_slots
-        L.check(lib.esr_plan_compact_owner_i32(C.byref(plan.s), n, self.rank, self.V_max, L.ptr(cplan.sorted_keys),
-                                               L.ptr(cplan.partner), L.ptr(self.scratch), sp), "esr_plan_compact_owner_i32")
 
     def _ids_body(self, k, sp):
         lib, n = L.lib(), self.n
@@ -688,31 +688,58 @@ class OwnerRoutedGloveTrainer:
                                            L.ptr(self.err), sp), "esr_peer_emit_plan_i32")
 
     def _step_body(self, k):
+        """Main-stream half of a step.  After the top barrier three things run side by side -- the NVLink fetch of the remote
+        rows (gather stream), the owner-side id bookkeeping (ids stream), and bias fetch -> prep -> all-reduce (main) -- and
+        after the row pass the owner merge of the embedding rows starts behind the S1/S2 all-reduce (which is also the
+        "every rank's gradient rows have landed" barrier) while finish -> barrier -> bias merge run on the ids stream."""
         lib, n = L.lib(), self.n
-        plan, cplan, st = self.plans[k], self.cplans[k], self.step_fn
+        plan, cplan, st, pub = self.plans[k], self.cplans[k], self.step_fn, self.pub[k]
         main = torch.cuda.current_stream(self.dev)
         sp = L.stream_ptr()
+
+        def gather(parts, stream_ptr):
+            L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, self.rank, L.ptr(plan.uniq), L.ptr(pub["order"]),
+                                                   L.ptr(pub["counts"]), plan.capacity, self.D, L.ptr(self.fetch_rows),
+                                                   L.ptr(self.fetch_bias), parts, stream_ptr), "esr_peer_gather_remote_f32")
+
+        def apply(parts, stream_ptr):
+            L.check(lib.esr_peer_apply_parts_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
+                                                 L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
+                                                 self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, parts,
+                                                 stream_ptr), "esr_peer_apply_parts_f32")
+
+        # The step is bound by the SIDE stream (its ~150 us of routing + sorting crawl while the persistent row pass holds
+        # the SMs), so the owner routing of the unique rows and the address form of the plan -- they need the plan, not the
+        # table -- run here, in front of the barrier, instead of at the end of the side chain (measured: profiles/r2_summary.md).
+        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
         self.barrier()                      # every route plan of this step is published; every owner applied step t-1
         self.ev_top.record(main)
         self.s_ids.wait_event(self.ev_top)
+        self.s_gather.wait_event(self.ev_top)
         with torch.cuda.stream(self.s_ids):
             self._ids_body(k, L.stream_ptr())
             self.ev_ids.record(self.s_ids)
-        pub = self.pub[k]
-        L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, self.rank, L.ptr(plan.uniq), L.ptr(pub["order"]),
-                                               L.ptr(pub["counts"]), plan.capacity, self.D, L.ptr(self.fetch_rows),
-                                               L.ptr(self.fetch_bias), sp), "esr_peer_gather_remote_f32")
+        with torch.cuda.stream(self.s_gather):
+            gather(1, L.stream_ptr())       # remote embedding rows -> fetch region (NVLink loads)
+            self.ev_gather.record(self.s_gather)
+        gather(2, sp)                       # remote biases (4 bytes per row): all that prep needs
+        L.check(lib.esr_plan_compact_owner_i32(C.byref(plan.s), n, self.rank, self.V_max, L.ptr(cplan.sorted_keys),
+                                               L.ptr(cplan.partner), L.ptr(self.scratch), sp), "esr_plan_compact_owner_i32")
         st.prep(cplan, self.cnt_l[k])
-        self._sync(st.scalars[0:3])         # global sum(bs), sum(bs^2), S0; also: all fetches done
+        self._sync(st.scalars[0:3])         # global sum(bs), sum(bs^2), S0
         main.wait_event(self.ev_ids)
+        main.wait_event(self.ev_gather)
         st.rows(cplan)                      # gradient rows go straight to the owners' inboxes
-        self._sync(st.scalars[3:5])         # global S1, S2
-        st.finish(cplan)
-        self.barrier()                      # every rank's gradients have landed in the inboxes
-        L.check(lib.esr_peer_apply_adagrad_f32(C.byref(self.shard.struct()), L.ptr(self.inbox_dE), L.ptr(self.inbox_db), n,
-                                               L.ptr(self.recv_ids), L.ptr(self.src_meta), L.ptr(self.slot_map),
-                                               self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, sp),
-                "esr_peer_apply_adagrad_f32")
+        self._sync(st.scalars[3:5])         # global S1, S2 -- and: every rank's row pass is done, its gradient rows landed
+        self.ev_rows.record(main)
+        self.s_ids.wait_event(self.ev_rows)
+        with torch.cuda.stream(self.s_ids):
+            st.finish(cplan, stream=self.s_ids)                 # bias gradients -> the owners' inboxes
+            self._sync(side=2)                                  # every rank's bias gradients have landed
+            apply(2, L.stream_ptr())                            # owner bias merge + Adagrad, slot_map restored
+            self.ev_bias.record(self.s_ids)
+        apply(1, sp)                        # owner merge of the embedding rows in source order + Adagrad
+        main.wait_event(self.ev_bias)
 
     def _capture(self):
         """Both halves per parity into CUDA graphs.  Collective: every rank captures the same sequence."""

@@ -399,7 +399,7 @@ int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bi
  * out[u,:] / out_bias[u] (the fetch region behind the shard; see esr_plan_compact_owner_i32). */
 int esr_peer_gather_remote_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks, int32_t me,
                                const int32_t* uniq, const int32_t* order, const int32_t* counts, int64_t cap, int32_t D,
-                               float* out, float* out_bias, esr_stream_t stream);
+                               float* out, float* out_bias, int32_t parts /* 1 rows | 2 biases */, esr_stream_t stream);
 /* The plan re-expressed in ADDRESSES of the unified table [shard rows ; fetch region]: key of unique row u =
  * uniq[u] / n_ranks when this rank owns it, base + u otherwise (base = rows of the shard allocation); partner likewise.
  * scratch: n_slots ints. */
@@ -459,20 +459,20 @@ int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes, int32_t n
 /* OWNER-COMPUTES pair routing (csrc/peer_ops.cu): a pair (i, j, x) is processed by the rank owning row i, so only the
  * unique partner rows j cross NVLink (4.3x fewer bytes on the bench stream at 8 ranks than keeping the pairs where they
  * arrived).  esr_peer_route_pairs_i32 (source side; depends on the ids only) partitions the (2,B) batch STABLY by
- * owner(i) = i % n straight into the owners' pair inboxes: peer_pair_ids[o] -> int32 [n][2][B] (region of source `me`:
- * its i then its j), peer_pair_cnt[o] -> f32 [n][B], peer_pair_counts[o] -> int32 [n] (entry `me` = pairs I send to o);
- * my_counts[o] = the same numbers locally.  After a device barrier, esr_peer_collect_pairs_i32 (owner side) concatenates
- * the regions in source order into keys[2 * B_cap] ([i ; j] halves of capacity B_cap, padding = pad_key, which must
- * exceed every row id so that it sorts to the end), counts[B_cap] and *n_valid = 2 m for EsrPlan.n_valid;
- * err |= 2 if m > B_cap (the excess pairs are dropped: the caller must treat it as fatal).
- * Bit-exact contract: oracle/index.py route_pairs / collect_pairs. */
+ * owner(i) = i % n straight into the owners' pair inboxes: peer_pair_rec[o] -> int4 [n][B] (region of source `me`: one
+ * 16-byte record {i, j, count bits, 0} per pair -- a single NVLink store each), peer_pair_counts[o] -> int32 [n] (entry
+ * `me` = pairs I send to o); my_counts[o] = the same numbers locally.  After a device barrier,
+ * esr_peer_collect_pairs_i32 (owner side) concatenates the regions in source order into keys[2 * B_cap] ([i ; j] halves of
+ * capacity B_cap, padding = pad_key, which must exceed every row id so that it sorts to the end), counts[B_cap] and
+ * *n_valid = 2 m for EsrPlan.n_valid; err |= 2 if m > B_cap (the excess pairs are dropped: the caller must treat it as
+ * fatal).  Bit-exact contract: oracle/index.py route_pairs / collect_pairs. */
 size_t esr_peer_route_pairs_workspace_bytes(int64_t B);
 int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts, int64_t B, int32_t n_ranks, int32_t me,
-                             void* const* peer_pair_ids, void* const* peer_pair_cnt, void* const* peer_pair_counts,
-                             int32_t* my_counts, void* ws, size_t ws_bytes, esr_stream_t stream);
-int esr_peer_collect_pairs_i32(const int32_t* in_ids, const float* in_cnt, const int32_t* in_counts, int32_t n_ranks,
-                               int64_t B, int64_t B_cap, int32_t pad_key, int32_t* keys, float* counts, int32_t* n_valid,
-                               int32_t* err, esr_stream_t stream);
+                             void* const* peer_pair_rec, void* const* peer_pair_counts, int32_t* my_counts, void* ws,
+                             size_t ws_bytes, esr_stream_t stream);
+int esr_peer_collect_pairs_i32(const void* in_rec, const int32_t* in_counts, int32_t n_ranks, int64_t B, int64_t B_cap,
+                               int32_t pad_key, int32_t* keys, float* counts, int32_t* n_valid, int32_t* err,
+                               esr_stream_t stream);
 
 /* The two halves of esr_peer_merge_adagrad_f32: resolve depends on the ids only (side stream, overlaps the row
  * pass); apply needs the gradients (after the device barrier).  desc: [recv_cap * (n_ranks + 2)] ints, 8-byte aligned --
@@ -483,6 +483,12 @@ int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_
 int esr_peer_apply_adagrad_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
                                const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map, int64_t map_stride,
                                const int32_t* desc, int64_t recv_cap, float lr, float eps, esr_stream_t stream);
+/* The same in two independent halves (parts: 1 = embedding rows, 2 = biases + slot_map restore; 3 = both): they touch
+ * disjoint state, so the rows can start as soon as every rank's gradient ROWS have landed while the bias gradients are
+ * still being formed. */
+int esr_peer_apply_parts_f32(EsrTable* shard, const float* inbox_dE, const float* inbox_db, int32_t n_ranks,
+                             const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map, int64_t map_stride,
+                             const int32_t* desc, int64_t recv_cap, float lr, float eps, int32_t parts, esr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -167,6 +167,30 @@ def test_shared_table_steps_match_oracle(kind):
     np.testing.assert_allclose(gacc, acc, rtol=2e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("kind", ["hinge", "softmax"])
+def test_shared_table_graphed_step_equals_eager(kind):
+    """SharedTableInBatch.graphed(): the CUDA-graph replay of the trainer step is the eager step, bit for bit, and the
+    warm-up / capture calls leave no trace in the table."""
+    from esrecsys_b200 import engine, synth
+    from esrecsys_b200.inbatch import SharedTableInBatch
+    V, D, B, lr = 5000, 128, 512, 0.05
+    rng = np.random.default_rng(11)
+    E = (rng.standard_normal((V, D)) / D ** 0.25).astype(np.float32)
+    q, k = synth.pair_batches(V, V, B, 3, 5)
+    outs = []
+    for graphed in (False, True):
+        table = engine.EmbeddingTable.from_dense(E, sparse=False, adagrad=True)
+        tr = SharedTableInBatch(table, B, lr=lr, loss=kind)
+        ids = [torch.from_numpy(np.stack([q[s], k[s]])).cuda() for s in range(3)]
+        step = tr.graphed(ids[0]) if graphed else tr.step
+        if graphed:
+            assert np.array_equal(table.rows0.cpu().numpy(), E)            # capture left the table untouched
+        losses = [float(step(ids[s]).item()) for s in range(3)]
+        outs.append((losses, table.rows0.cpu().numpy(), table.acc.cpu().numpy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+
 def test_two_tower_steps_match_oracle():
     """configs[3] shape (scaled down): id tables + MLP towers + softmax in-batch loss, 3 steps."""
     from esrecsys_b200 import engine, synth

@@ -159,11 +159,11 @@ def test_pair_routing_kernels_bit_exact(n):
     for o, k in enumerate(vp.ranks):
         regions = [routed[s][0][o] for s in range(n)]
         assert k.pin_counts[:n].cpu().tolist() == [int(routed[s][1][o]) for s in range(n)]
-        pin_ids, pin_cnt = k.pin_ids.cpu().numpy(), k.pin_cnt.cpu().numpy()
+        rec = k.pin_rec.cpu().numpy()                               # [n][B][4] = {i, j, count bits, 0}
         for s in range(n):
             c = regions[s][0].size
-            assert np.array_equal(pin_ids[s, 0, :c], regions[s][0]) and np.array_equal(pin_ids[s, 1, :c], regions[s][1])
-            assert np.array_equal(pin_cnt[s, :c].view(np.uint32), regions[s][2].view(np.uint32))
+            assert np.array_equal(rec[s, :c, 0], regions[s][0]) and np.array_equal(rec[s, :c, 1], regions[s][1])
+            assert np.array_equal(rec[s, :c, 2].view(np.uint32), regions[s][2].view(np.uint32))
         keys, cnt, nv, over = oidx.collect_pairs(regions, vp.B_cap, V)
         assert not over and int(k.n_valid.item()) == nv and int(k.err.item()) == 0
         assert np.array_equal(k.keys.cpu().numpy(), keys)

@@ -182,15 +182,13 @@ class VirtualOwnerRoutedGlove(VirtualPeerGlove):
         n, B = self.n, self.B
         i32 = dict(dtype=torch.int32, device=self.dev)
         for k in self.ranks:
-            k.pin_ids = torch.zeros(n, 2, B, **i32)
-            k.pin_cnt = torch.zeros(n, B, dtype=torch.float32, device=self.dev)
+            k.pin_rec = torch.zeros(n, B, 4, **i32)              # 16-byte records {i, j, count bits, 0} per source
             k.pin_counts = torch.zeros(16, **i32)
             k.my_counts = torch.zeros(16, **i32)
             k.keys = torch.full((2 * cap,), V, **i32)
             k.cnt_l = torch.zeros(cap, dtype=torch.float32, device=self.dev)
             k.route_ws = torch.empty(int(L.lib().esr_peer_route_pairs_workspace_bytes(B)), dtype=torch.uint8, device=self.dev)
-        self.p_pin_ids = _ptr_array([k.pin_ids for k in self.ranks])
-        self.p_pin_cnt = _ptr_array([k.pin_cnt for k in self.ranks])
+        self.p_pin_rec = _ptr_array([k.pin_rec for k in self.ranks])
         self.p_pin_counts = _ptr_array([k.pin_counts for k in self.ranks])
 
     def route_phase(self, ids, counts):
@@ -198,11 +196,11 @@ class VirtualOwnerRoutedGlove(VirtualPeerGlove):
         for r, k in enumerate(self.ranks):
             k.ids_dev = ids[r].to(self.dev).reshape(-1).contiguous()
             k.cnt_dev = counts[r].to(self.dev).contiguous()
-            L.check(lib.esr_peer_route_pairs_i32(L.ptr(k.ids_dev), L.ptr(k.cnt_dev), self.B, n, r, self.p_pin_ids,
-                                                 self.p_pin_cnt, self.p_pin_counts, L.ptr(k.my_counts), L.ptr(k.route_ws),
+            L.check(lib.esr_peer_route_pairs_i32(L.ptr(k.ids_dev), L.ptr(k.cnt_dev), self.B, n, r, self.p_pin_rec,
+                                                 self.p_pin_counts, L.ptr(k.my_counts), L.ptr(k.route_ws),
                                                  k.route_ws.numel(), sp), "esr_peer_route_pairs_i32")
         for k in self.ranks:                                      # (side-stream barrier here in the product)
-            L.check(lib.esr_peer_collect_pairs_i32(L.ptr(k.pin_ids), L.ptr(k.pin_cnt), L.ptr(k.pin_counts), n, self.B,
+            L.check(lib.esr_peer_collect_pairs_i32(L.ptr(k.pin_rec), L.ptr(k.pin_counts), n, self.B,
                                                    self.B_cap, self.V, L.ptr(k.keys), L.ptr(k.cnt_l), L.ptr(k.n_valid),
                                                    L.ptr(k.err), sp), "esr_peer_collect_pairs_i32")
 
@@ -221,11 +219,21 @@ class VirtualOwnerRoutedGlove(VirtualPeerGlove):
         lib, n, sp = L.lib(), self.n, L.stream_ptr()
         V_max = self.map_stride
         for r, k in enumerate(self.ranks):
-            L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, r, L.ptr(k.plan.uniq), L.ptr(k.order),
-                                                   L.ptr(k.counts), k.plan.capacity, self.D, L.ptr(k.rows[V_max:]),
-                                                   L.ptr(k.bias[V_max:]), sp), "esr_peer_gather_remote_f32")
+            for parts in (2, 1):                                 # biases, then rows: the product runs them on two streams
+                L.check(lib.esr_peer_gather_remote_f32(self.p_rows, self.p_bias, n, r, L.ptr(k.plan.uniq), L.ptr(k.order),
+                                                       L.ptr(k.counts), k.plan.capacity, self.D, L.ptr(k.rows[V_max:]),
+                                                       L.ptr(k.bias[V_max:]), parts, sp), "esr_peer_gather_remote_f32")
             k.step_fn.prep(k.cplan, counts[r])
         self._all_reduce(0, 3)
+
+    def apply_phase(self):
+        lib, n, sp = L.lib(), self.n, L.stream_ptr()
+        for parts in (1, 2):                                     # embedding rows, then biases (two streams in the product)
+            for k in self.ranks:
+                L.check(lib.esr_peer_apply_parts_f32(C.byref(k.shard.struct()), L.ptr(k.inbox_dE), L.ptr(k.inbox_db), n,
+                                                     L.ptr(k.recv_ids), L.ptr(k.src_meta), L.ptr(k.slot_map), self.map_stride,
+                                                     L.ptr(k.desc), self.inbox_cap, self.lr, 1e-7, parts, sp),
+                        "esr_peer_apply_parts_f32")
 
     def step(self, ids, counts):
         self.route_phase(ids, counts)

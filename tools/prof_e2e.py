@@ -29,15 +29,14 @@ def run(batches, read_loss):
     e1.record(tr.s_main); tr.synchronize(); torch.cuda.synchronize()
     return round(e0.elapsed_time(e1) / steps * 1e3, 1), round(host, 1)
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("ESR_PIPE")}, "steps": steps}
-for name, b, rl in (("device", dev, False), ("pinned_adjacent", pin_adj, False), ("pinned_adjacent_readloss", pin_adj, True),
-                    ("pinned_separate", pin_sep, False), ("pinned_separate_readloss", pin_sep, True), ("device_again", dev, False)):
+for name, b, rl in (("device", dev, False), ("pinned_adjacent", pin_adj, False), ("pinned_separate", pin_sep, False)):
     out[name] = dict(zip(("gpu_us_per_step", "host_us_per_submit"), run(b, rl)))
 print(json.dumps(out))
 
 # timeline of 12 steady-state steps, device vs pinned
 import ctypes as C
 from esrecsys_b200 import _lib as L
-for name, b in (("device", dev), ("pinned_separate", pin_sep), ("pinned_adjacent", pin_adj)):
+for name, b in ((("pinned_adjacent", pin_adj),) if os.environ.get("TIMELINE") else ()):
     for k in range(8):
         tr.submit(*b[k % 8])
     L.check(L.lib().esr_pipeline_trace(tr.pipe, 12), "trace")

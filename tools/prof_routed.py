@@ -62,8 +62,9 @@ def main():
     L.lib = lambda: proxy                      # every module resolves L.lib() at call time
     cur = torch.cuda.current_stream()
     tr.s_side = cur                            # one stream: phases run back to back
-    if hasattr(tr, "s_ids"):
-        tr.s_ids = cur
+    for name in ("s_ids", "s_gather"):
+        if hasattr(tr, name):
+            setattr(tr, name, cur)
     steps = 10
     tot = 0.0
     for it in range(steps + 3):
