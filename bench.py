@@ -568,9 +568,10 @@ def rows_kernel_time(table, a, ids_dev, cnt_dev, steps):
 
 
 def ncu_traffic(stream, a):
-    """DRAM bytes per row-pass launch from the committed ncu capture of the same kernel / batch (None otherwise)."""
+    """DRAM bytes per row-pass launch from the committed ncu capture of the same kernel / batch (profiles/r2_traffic.json,
+    captured with tools/r2_evidence.sh on the round-2 kernel; None for any other shape)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[stream]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[stream]
         if t["batch"] == a.batch and a.vocab == 1_000_000 and a.dim == 128:
             return t["bytes"]
     except Exception:

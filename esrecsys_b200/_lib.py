@@ -120,6 +120,7 @@ _SIGNATURES = {
     "esr_pipeline_submit": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int64)]),
     "esr_pipeline_trace": (C.c_int, [_P, C.c_int32]),
     "esr_pipeline_trace_read": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "esr_pipeline_wait_staged": (C.c_int, [_P, C.c_int64]),
     "esr_pipeline_sync": (C.c_int, [_P]),
     "esr_pipeline_destroy": (C.c_int, [_P]),
     "esr_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -255,6 +255,14 @@ extern "C" int esr_pipeline_trace_read(EsrPipeline* p, float* out_us /* [n][6] *
   return ESR_OK;
 }
 
+// Host-side wait until the staging copy of step `step` (already submitted) has completed: its host batch may be rewritten.
+// Conservative: waits for the latest staging copy of that buffer parity.
+extern "C" int esr_pipeline_wait_staged(const EsrPipeline* p, int64_t step) {
+  ESR_REQUIRE(ok(p) && step >= 0 && step < p->t);
+  ESR_CUDA(cudaEventSynchronize(p->ev_copy[step % p->depth]));
+  return ESR_OK;
+}
+
 extern "C" int esr_pipeline_sync(const EsrPipeline* p) {
   ESR_REQUIRE(ok(p));
   ESR_CUDA(cudaStreamSynchronize(p->copy));

@@ -228,6 +228,17 @@ class GloveTrainer:
         buf = torch.empty(3 * self.B, dtype=torch.int32).pin_memory()
         return buf[: 2 * self.B].view(2, self.B), buf[2 * self.B:].view(torch.float32)
 
+    def wait_staged(self, step):
+        """Host-side wait (any thread) until the batch of step ``step`` has been staged on the device, i.e. its host
+        memory may be rewritten: the hand-shake of ``wikipedia.input_pipeline.PinnedBatchLoader``."""
+        import time
+        while self.t <= step:                 # not submitted yet
+            time.sleep(20e-6)
+        if self.pipe is not None:
+            L.check(L.lib().esr_pipeline_wait_staged(self.pipe, int(step)), "esr_pipeline_wait_staged")
+        else:
+            self.ev_copy[step % self.depth].synchronize()
+
     def read_loss(self, step):
         """Device->host read of one step's loss (asynchronous copy into pinned memory on the main stream); prefer
         ``submit(..., read_loss=True)``, which folds it into the step's call."""

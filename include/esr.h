@@ -381,6 +381,9 @@ int esr_pipeline_submit(EsrPipeline* p, const void* ids, const void* counts, esr
  * boundaries {copy begin, copy end, plan begin, plan end, step begin, step end} in microseconds since the arming call. */
 int esr_pipeline_trace(EsrPipeline* p, int32_t n);
 int esr_pipeline_trace_read(EsrPipeline* p, float* out_us, int32_t* n_out);
+/* Blocks the calling host thread until the staging copy of (already submitted) step `step` has completed, i.e. its host
+ * batch may be overwritten -- the hand-shake of a loader thread that refills a ring of pinned batches. */
+int esr_pipeline_wait_staged(const EsrPipeline* p, int64_t step);
 int esr_pipeline_sync(const EsrPipeline* p);
 int esr_pipeline_destroy(EsrPipeline* p);
 
