@@ -242,21 +242,32 @@ def timed_region(tr, batches, steps, warmup, read_loss, world):
 
 
 def timed_region_sharded(tr, batches, steps, warmup, pinned_loss, world):
-    """N > 1: ShardedGloveTrainer.step on the current stream (NCCL all-to-alls inside)."""
+    """N > 1: one sharded trainer step per batch.  The routed trainer runs on its own streams: the timing events on the
+    current stream bracket them explicitly."""
     import torch
     import torch.distributed as dist
     n = len(batches)
+    own = [getattr(tr, s) for s in ("s_main", "s_side") if hasattr(tr, s)] if hasattr(tr, "s_main") else []
     for k in range(warmup):
         tr.step(*batches[k % n])
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    cur = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    for s in own:
+        s.wait_event(e0)
     for k in range(steps):
         loss = tr.step(*batches[(warmup + k) % n])
         if pinned_loss is not None:
-            pinned_loss[k % pinned_loss.numel(): k % pinned_loss.numel() + 1].copy_(loss.reshape(1), non_blocking=True)
+            slot = pinned_loss[k % pinned_loss.numel(): k % pinned_loss.numel() + 1]
+            if hasattr(tr, "read_loss_to"):
+                tr.read_loss_to(slot)
+            else:
+                slot.copy_(loss.reshape(1), non_blocking=True)
+    for s in own:
+        cur.wait_stream(s)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -301,7 +312,8 @@ def sharded_parity_check(a, rank, world):
         loss = tr.step(torch.from_numpy(np.ascontiguousarray(ids[k][:, lo:hi])).cuda(), torch.from_numpy(counts[k][lo:hi]).cuda())
         plan.build(torch.from_numpy(ids[k].reshape(-1)).cuda())
         ref = single.run(plan, torch.from_numpy(counts[k]).cuda())[engine.L.SC_LOSS]
-        dl = max(dl, abs(float(loss.item()) - float(ref.item())) / max(1e-12, abs(float(ref.item()))))
+        got = tr.loss_value() if hasattr(tr, "loss_value") else float(loss.item())
+        dl = max(dl, abs(got - float(ref.item())) / max(1e-12, abs(float(ref.item()))))
     Eg, bg = tr.gather_dense()
     Es, bs = table.dense(), table.bias
     dE = float((Eg - Es).abs().max().item())

@@ -734,11 +734,15 @@ __global__ void __launch_bounds__(ESR_MAX_PEERS * 32) k_pair_scan(const int32_t*
   }
 }
 
-// stable scatter of the tile's pairs into the owners' inbox regions of source `me`
+// stable scatter of the tile's pairs into the owners' inbox regions of source `me`.  The tile is first ordered by owner in
+// shared memory (stable), then every owner's run is copied to its region with consecutive lanes writing consecutive
+// 16-byte records: 512-byte NVLink stores per warp instruction instead of 32 scattered ones (63 -> ~30 us at 8 ranks).
 __global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __restrict__ ids, const float* __restrict__ counts,
                                                            int64_t B, Cyclic cyc, int me, const int32_t* __restrict__ blk_base,
                                                            const __grid_constant__ PeerPtrs peer_ids) {
   __shared__ unsigned long long wlo[kThreads / 32], whi[kThreads / 32];
+  __shared__ int4 tile[kRouteTile];
+  __shared__ int tile_off[ESR_MAX_PEERS + 1];
   const int64_t base = (int64_t)blockIdx.x * kRouteTile + (int64_t)threadIdx.x * kRouteItems;
   int32_t vi[kRouteItems], vj[kRouteItems];
   float vx[kRouteItems];
@@ -766,13 +770,27 @@ __global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __rest
     whi[wid] = thi;
   }
   __syncthreads();
-  for (int w = 0; w < wid; ++w) {
-    ex.lo += wlo[w];
-    ex.hi += whi[w];
+  OwnerCounts tot{0ull, 0ull};
+  for (int w = 0; w < kThreads / 32; ++w) {
+    if (w < wid) {
+      ex.lo += wlo[w];
+      ex.hi += whi[w];
+    }
+    tot.lo += wlo[w];
+    tot.hi += whi[w];
   }
+  if (threadIdx.x == 0) {
+    int o_off = 0;
+    for (int o = 0; o < ESR_MAX_PEERS; ++o) {
+      tile_off[o] = o_off;
+      o_off += o < cyc.n ? tot.get(o) : 0;
+    }
+    tile_off[ESR_MAX_PEERS] = o_off;
+  }
+  __syncthreads();
   int run[ESR_MAX_PEERS];
 #pragma unroll
-  for (int o = 0; o < ESR_MAX_PEERS; ++o) run[o] = o < cyc.n ? blk_base[blockIdx.x * ESR_MAX_PEERS + o] + ex.get(o) : 0;
+  for (int o = 0; o < ESR_MAX_PEERS; ++o) run[o] = o < cyc.n ? tile_off[o] + ex.get(o) : 0;
 #pragma unroll
   for (int k = 0; k < kRouteItems; ++k) {
     if (own[k] >= 0) {
@@ -780,10 +798,19 @@ __global__ void __launch_bounds__(kThreads) k_pair_scatter(const int32_t* __rest
 #pragma unroll
       for (int o = 0; o < ESR_MAX_PEERS; ++o)
         if (o == own[k]) pos = run[o]++;
-      // region of source `me` in owner's inbox: B records of 16 bytes {i, j, count bits, 0} -- ONE remote store per pair
-      int4* dst = reinterpret_cast<int4*>(const_cast<void*>(peer_ids.p[own[k]])) + (int64_t)me * B;
-      dst[pos] = make_int4(vi[k], vj[k], __float_as_int(vx[k]), 0);
+      tile[pos] = make_int4(vi[k], vj[k], __float_as_int(vx[k]), 0);
     }
+  }
+  __syncthreads();
+  // region of source `me` in owner's inbox: B records of 16 bytes {i, j, count bits, 0}
+  const int n_tile = tile_off[ESR_MAX_PEERS];
+  for (int t = threadIdx.x; t < n_tile; t += kThreads) {
+    int o = 0;
+#pragma unroll
+    for (int q = 1; q < ESR_MAX_PEERS; ++q)
+      if (t >= tile_off[q]) o = q;   // tile_off is non-decreasing; empty owners share an offset and the last match wins
+    int4* dst = reinterpret_cast<int4*>(const_cast<void*>(peer_ids.p[o])) + (int64_t)me * B;
+    dst[blk_base[blockIdx.x * ESR_MAX_PEERS + o] + (t - tile_off[o])] = tile[t];
   }
 }
 

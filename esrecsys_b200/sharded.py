@@ -523,10 +523,10 @@ class OwnerRoutedGloveTrainer:
     source order + Adagrad; no NCCL inside the step (libesr all-reduce / barrier kernels), both halves CUDA-graphed.
 
       side stream : stage the batch -> route pairs to their owners (peer stores, stable) -> barrier (side sequence)
-                    -> collect my pairs -> index plan (device-side slot count)
-      main stream : route plan (published) -> barrier -> { gather stream: remote rows over NVLink | ids stream: owners
-                    pull the id lists, resolve, emit plan | main: remote biases -> plan in table addresses -> prep ->
-                    all-reduce(3) } -> row pass (gradients -> inboxes) -> all-reduce(2) -> { main: owner merge of the rows
+                    -> collect my pairs -> index plan (device-side slot count) -> route plan (published) -> plan in
+                    unified-table addresses
+      main stream : barrier -> { gather stream: remote rows over NVLink | ids stream: owners pull the id lists, resolve,
+                    emit plan | main: remote biases -> prep -> all-reduce(3) } -> row pass (gradients -> inboxes) -> all-reduce(2) -> { main: owner merge of the rows
                     + Adagrad | ids stream: finish -> barrier -> owner bias merge }
 
     One global step equals the single-table step on the concatenated batch (tests: N virtual ranks on one GPU against
@@ -629,6 +629,7 @@ class OwnerRoutedGloveTrainer:
         self.map_stride = V_max
         self.slot_map = torch.full((n, V_max), -1, **i32)
         self.desc = torch.empty(self.recv_cap * (n + 2), **i32)   # per entry: n source rows; then 8-byte owner records
+        self.s_main = torch.cuda.Stream(self.dev)
         self.s_side = torch.cuda.Stream(self.dev)
         self.s_ids = torch.cuda.Stream(self.dev)
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
@@ -674,6 +675,12 @@ class OwnerRoutedGloveTrainer:
                                                L.ptr(self.n_valid[k]), L.ptr(self.err), sp), "esr_peer_collect_pairs_i32")
         plan.build(self.keys[k])
         cplan.s.n_slots = plan.n_slots
+        # owner routing of the unique rows (published for the peers) and the plan in unified-table addresses: they need the
+        # plan, not the table.  (With both halves of the step truly overlapped the main chain is the longer one, so they
+        # sit here; while the halves were serialised by mistake their placement made no difference.)
+        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
+        L.check(lib.esr_plan_compact_owner_i32(C.byref(plan.s), n, self.rank, self.V_max, L.ptr(cplan.sorted_keys),
+                                               L.ptr(cplan.partner), L.ptr(self.scratch), sp), "esr_plan_compact_owner_i32")
 
     def _ids_body(self, k, sp):
         lib, n = L.lib(), self.n
@@ -708,10 +715,6 @@ class OwnerRoutedGloveTrainer:
                                                  self.map_stride, L.ptr(self.desc), self.recv_cap, self.lr, 1e-7, parts,
                                                  stream_ptr), "esr_peer_apply_parts_f32")
 
-        # The step is bound by the SIDE stream (its ~150 us of routing + sorting crawl while the persistent row pass holds
-        # the SMs), so the owner routing of the unique rows and the address form of the plan -- they need the plan, not the
-        # table -- run here, in front of the barrier, instead of at the end of the side chain (measured: profiles/r2_summary.md).
-        self.ops.route_plan(plan.uniq, plan.n_uniq, n, out=(pub["order"], pub["send_local"], pub["counts"], pub["inv_order"]))
         self.barrier()                      # every route plan of this step is published; every owner applied step t-1
         self.ev_top.record(main)
         self.s_ids.wait_event(self.ev_top)
@@ -723,8 +726,6 @@ class OwnerRoutedGloveTrainer:
             gather(1, L.stream_ptr())       # remote embedding rows -> fetch region (NVLink loads)
             self.ev_gather.record(self.s_gather)
         gather(2, sp)                       # remote biases (4 bytes per row): all that prep needs
-        L.check(lib.esr_plan_compact_owner_i32(C.byref(plan.s), n, self.rank, self.V_max, L.ptr(cplan.sorted_keys),
-                                               L.ptr(cplan.partner), L.ptr(self.scratch), sp), "esr_plan_compact_owner_i32")
         st.prep(cplan, self.cnt_l[k])
         self._sync(st.scalars[0:3])         # global sum(bs), sum(bs^2), S0
         main.wait_event(self.ev_ids)
@@ -771,14 +772,19 @@ class OwnerRoutedGloveTrainer:
 
     def step(self, ids, counts):
         """ids: int32 (2, B_local) global rows (host pinned or device) -- this rank's share of the global batch, in the
-        layout of wikipedia/cooccurrence_matrix.py:103-114; counts: f32 (B_local,).  Enqueues one step; returns the
-        GLOBAL loss as a device scalar."""
+        layout of wikipedia/cooccurrence_matrix.py:103-114; counts: f32 (B_local,).  Enqueues one step on the trainer's
+        own streams; returns the GLOBAL loss as a device scalar that is valid once the trainer's main stream has reached
+        it (``loss_value()``, ``read_loss_to()``, ``synchronize()``)."""
         k = self.t % self.DEPTH
-        main = torch.cuda.current_stream(self.dev)
-        side = self.s_side
+        cur = torch.cuda.current_stream(self.dev)
+        main, side = self.s_main, self.s_side
         if self.use_graphs and self.g_step[0] is None and self.t == 2 * self.DEPTH:
             self._capture()                    # after two eager steps per parity (lazy module / allocator state is warm)
-        side.wait_stream(main)
+        # The trainer runs on its OWN streams.  (Round 1 and the first round-2 version ran the main half on the caller's
+        # stream and made the side stream wait for that stream "for the inputs" -- which also made the routing + plan of
+        # batch t+1 wait for the whole step t: the two halves never overlapped, step = main + side.)
+        if torch.is_tensor(ids) and ids.is_cuda:
+            side.wait_stream(cur)              # device inputs produced on the caller's stream
         side.wait_event(self.ev_done[k])       # step t-2 is done with parity k's buffers on this rank
         with torch.cuda.stream(side):
             self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
@@ -790,16 +796,28 @@ class OwnerRoutedGloveTrainer:
                 self._plan_body(k)
             self.ev_plan[k].record(side)
         main.wait_event(self.ev_plan[k])
-        if self.g_step[k] is not None:
-            self.g_step[k].replay()
-        else:
-            self._step_body(k)
-        self.ev_done[k].record(main)
-        slot = self.t % self.loss_log.numel()
-        self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
+        with torch.cuda.stream(main):
+            if self.g_step[k] is not None:
+                self.g_step[k].replay()
+            else:
+                self._step_body(k)
+            self.ev_done[k].record(main)
+            slot = self.t % self.loss_log.numel()
+            self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
         self.loss = self.loss_log[slot]
         self.t += 1
         return self.loss
+
+    def loss_value(self):
+        """The last step's global loss as a Python float (waits for the trainer's main stream)."""
+        self.s_main.synchronize()
+        return float(self.loss.item())
+
+    def read_loss_to(self, pinned_slot):
+        """Asynchronous device->host copy of the last step's loss into a pinned 1-element tensor, ordered on the trainer's
+        main stream."""
+        with torch.cuda.stream(self.s_main):
+            pinned_slot.copy_(self.loss.reshape(1), non_blocking=True)
 
     def check(self):
         """Synchronise and raise if a step overflowed the pair capacity (bit 1) or a gradient inbox (bit 0)."""

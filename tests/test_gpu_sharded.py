@@ -44,7 +44,8 @@ def _worker(rank, world, port, V, D, B_loc, steps, bias_mode, q, peer=False):
         for k in range(steps):
             loss = tr.step(torch.from_numpy(np.ascontiguousarray(ids[k][:, lo:hi])), torch.from_numpy(counts[k][lo:hi]))
             oloss = og.step_adagrad(Eo, bo, aE, ab, ids[k, 0], ids[k, 1], counts[k], 0.05, bias_mode)
-            np.testing.assert_allclose(float(loss.item()), oloss, rtol=2e-5, atol=1e-5)
+            got = tr.loss_value() if hasattr(tr, "loss_value") else float(loss.item())     # routed trainer: own streams
+            np.testing.assert_allclose(got, oloss, rtol=2e-5, atol=1e-5)
         Eg, bg = tr.gather_dense()
         np.testing.assert_allclose(Eg.cpu().numpy(), Eo, rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(bg.cpu().numpy(), bo, rtol=1e-5, atol=1e-5)

@@ -62,7 +62,7 @@ def main():
     L.lib = lambda: proxy                      # every module resolves L.lib() at call time
     cur = torch.cuda.current_stream()
     tr.s_side = cur                            # one stream: phases run back to back
-    for name in ("s_ids", "s_gather"):
+    for name in ("s_main", "s_ids", "s_gather"):
         if hasattr(tr, name):
             setattr(tr, name, cur)
     steps = 10
