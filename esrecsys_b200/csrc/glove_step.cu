@@ -863,6 +863,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
   issue_partner(1);
   cp_async_commit();
 
+  // EMIT: destination of the gradient row of the segment in flight, loaded one segment ahead (it sat as a dependent
+  // global load in front of every gradient store)
+  const bool emit_mapped = a.emit && a.emit_map != nullptr;
+  uint32_t e_cur = (emit_mapped && cnt > 0) ? (uint32_t)a.emit_map[u] : 0u, e_nx = 0u;
   for (int s = 0; s < a.chunk; ++s) {
     const bool active = s < cnt;
     cp_async_wait1();  // partner(s), self(s), acc(s) have landed; partner(s+1) may still be in flight
@@ -882,8 +886,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
         row_zero(grad);
         bacc = 0.f;
         started_here = is_head;
-        if (is_head && s > 0) ++u;
+        if (is_head && s > 0) {
+          ++u;
+          e_cur = e_nx;
+        }
       }
+      if (emit_mapped && is_end && s + 1 < cnt) e_nx = (uint32_t)a.emit_map[u + 1];  // the next segment starts at s + 1
       if (!a.emit && is_end && started_here)
         grow_from_smem_f<G, NV, FULLD>(A, reinterpret_cast<const float4*>(bufs + 4 * (size_t)RB), gl, a.D4);
     }
@@ -910,7 +918,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_glove_rows_grp_async(const R
       bacc += a.per_pair ? g : rec.bs;
       if (is_end && started_here) {
         if (a.emit) {
-          uint64_t e = a.emit_map ? (uint64_t)a.emit_map[u] : (uint64_t)u;
+          uint64_t e = a.emit_map ? (uint64_t)e_cur : (uint64_t)u;
           float* base = a.dE;
           if (a.peers.on) {
             base = a.peers.dE[e >> kEmitShift];
