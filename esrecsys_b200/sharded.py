@@ -230,6 +230,9 @@ class PeerShardedGloveTrainer:
                     -> owners merge their inbox locally, Adagrad -> barrier
     ``overlap_ids=True`` (EXPERIMENTAL, off): pull / resolve / emit plan move to a second side stream behind a barrier at
     the top of the step, which also replaces the barrier at its end.
+    NOTE (round 2): this trainer runs its main half on the CALLER's stream and makes the side stream wait for it, so the
+    two halves do not overlap (the owner-routed trainer below fixed that for itself: 385 -> 303 us per step at 2 GPUs);
+    kept as the round-1 reference point.
     ``graphs=True`` captures both halves into CUDA graphs per parity after two eager steps (the eager step is ~25 host
     calls and partly host-bound).  EXPERIMENTAL and off by default: in round 1 the replay of the captured
     NCCL all-reduce + symmetric-memory barrier sequence dead-locked in the 2-GPU bench (killed by its timeout).
@@ -533,8 +536,9 @@ class OwnerRoutedGloveTrainer:
     oracle.glove.step_adagrad; bench.py --gpus N runs the same check before its timed region)."""
 
     DEPTH = 2
-    # libesr kernels per step (cub sort passes included): route pairs 3, collect 1, plan 8, route plan 5, compact 2, gather,
-    # prep, pull, resolve, emit plan, rows, combine, finish, merge, clear map, 2 all-reduces + 3 barriers
+    # libesr kernels per step (cub sort passes included): route pairs 3, collect 1, plan 8, route plan 3, address plan 2,
+    # gather 2 (rows, biases), prep, pull, resolve, emit plan, rows, combine, finish, merge rows, merge bias, clear map,
+    # 2 all-reduces + 3 barriers
     LAUNCHES_PER_STEP = 34
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
