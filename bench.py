@@ -135,19 +135,54 @@ def cpu_same_algorithm(a, steps, warmup):
                        "segment sums, Adagrad on the touched rows only), torch CPU ops, %d threads" % (steps, B, V, D, cores))
 
 
+def config_single(a, table_gb=None):
+    """``config`` of the N = 1 workload (shared by both arms so that the driver's same-config check holds)."""
+    V, D, B = a.vocab, a.dim, a.batch
+    return {"workload": workload_name(a), "vocab": V, "dim": D, "batch": B, "optimizer": "sparse adagrad (north star)",
+            "bias_mode": "reference_broadcast", "kernel": a.kernel, "stream": "zipf(1)",
+            **({"stream_priority": True} if a.stream_priority else {}),
+            "l2": "no flush: table + state = %.2f GB per GPU >> 126 MB L2, fresh random rows every step"
+                  % (table_gb if table_gb is not None else (3 * V * D * 4 + V * 9) / 1e9),
+            "parallelism": "single"}
+
+
+PARALLELISM = {
+    "routed": "row-sharded table (cyclic), dp%d over pairs, OWNER-COMPUTES: every pair is routed to the rank owning row i "
+              "(16 B per pair), only the unique partner rows and their gradients cross NVLink (libesr peer-memory "
+              "kernels, no NCCL inside the step, CUDA graphs)",
+    "peer": "row-sharded table (cyclic), dp%d over pairs; rows fetched and gradients merged by libesr kernels over "
+            "NVLink peer memory",
+    "nccl": "row-sharded table (cyclic), dp%d over pairs; NCCL all-to-all of ids / rows / gradients"}
+
+
+def config_sharded(a, world):
+    V, D, B = a.vocab, a.dim, a.batch
+    return {"workload": workload_name(a) + "; table row-sharded (cyclic) over %d GPUs, B per GPU" % world, "vocab": V,
+            "dim": D, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "sparse adagrad (north star)",
+            "bias_mode": "reference_broadcast", "stream": "zipf(1)", "exchange": a.exchange,
+            "l2": "no flush: per-step working set (fetched rows + shard rows + state) >> 126 MB L2",
+            "parallelism": PARALLELISM[a.exchange] % world}
+
+
 def run_reference(a):
+    """Reference arm: the reference's own step (dense gradient + dense optax.adam over every row,
+    wikipedia/train_cooccurence.py:71-101) on the host cores -- the oracle port, since jax / flax cannot be installed here --
+    on OUR arm's config, EXACTLY the requested steps (bounded at 60: ~0.3 s per step) after the requested warm-up (bounded
+    at 5).  N > 1: rank 0 alone runs, one B-pair batch per step (the per-GPU share of the global batch)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 5))
-    warm = max(0, min(a.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    steps = max(1, min(a.steps, 60))
+    warm = max(0, min(a.warmup, 5))
     cb, ms = cpu_reference(a, steps, warm)
+    cfg = config_single(a) if world <= 1 else config_sharded(a, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "batch": a.batch,
-                                                         "note": "reference is CPU-only (jax/flax absent): oracle port, "
-                                                                 "steps clamped to <=5 so the run stays bounded"},
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "note": "CPU-only reference (jax / flax absent): oracle/glove_torch.step_adam_dense on all host threads; "
+                "steps bounded at 60, warm-up at 5",
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -388,11 +423,7 @@ def run_sharded(a, rank, world, local):
         "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a) + "; table row-sharded (cyclic) over %d GPUs, B per GPU" % world, "vocab": V,
-                   "dim": D, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "sparse adagrad (north star)",
-                   "bias_mode": "reference_broadcast", "stream": "zipf(1)", "exchange": a.exchange,
-                   "l2": "no flush: per-step working set (fetched rows + shard rows + state) >> 126 MB L2",
-                   "parallelism": par},
+        "config": config_sharded(a, world),
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * B,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": a.steps * tr.LAUNCHES_PER_STEP, "final_loss": float(tr.loss.item()),
@@ -784,11 +815,7 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "vocab": V, "dim": D, "batch": B, "optimizer": "sparse adagrad (north star)",
-                   "bias_mode": "reference_broadcast", "kernel": a.kernel, "stream": "zipf(1)",
-                   **({"stream_priority": True} if a.stream_priority else {}),
-                   "l2": "no flush: table + state = %.2f GB per GPU >> 126 MB L2, fresh random rows every step" % (table.nbytes() / 1e9),
-                   "parallelism": "replicas" if world > 1 else "single"},
+        "config": config_single(a, table.nbytes() / 1e9),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": a.steps * tr.launches_per_step,
