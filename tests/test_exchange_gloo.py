@@ -188,3 +188,135 @@ def test_sharded_inbatch_decomposition_gloo(kind):
     for p in procs:
         p.join(30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _routed_worker(rank, world, port, bias_mode, q):
+    """The owner-computes decomposition of the GloVe step (esrecsys_b200/sharded.py OwnerRoutedGloveTrainer; kernels
+    esr_peer_route_pairs_i32 / esr_peer_collect_pairs_i32 / esr_peer_gather_remote_f32 / esr_peer_apply_parts_f32) with gloo
+    collectives in place of the NVLink peer stores: pairs go to the owner of row i, the owner fetches the partner rows it
+    does not own, the batch sums are all-reduced (B = global batch), gradients of foreign rows return to their owners and
+    are merged there.  Every shard must then equal the oracle's single global step on the concatenated batch."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from esrecsys_b200.sharded import pair_capacity
+        from oracle import glove as og
+        from oracle import index as oidx
+        from oracle import optim as oopt
+        V, D, B, lr = 211, 8, 96, 0.05
+        rng = np.random.default_rng(5)                                   # same table and batches on every rank
+        E = (0.1 * rng.standard_normal((V, D))).astype(np.float32)
+        b = (0.1 * rng.standard_normal(V)).astype(np.float32)
+        ids = [np.minimum(rng.zipf(1.3, size=(2, B)) - 1, V - 1).astype(np.int32) for _ in range(world)]
+        cnt = [rng.uniform(1, 200, size=B).astype(np.float32) for _ in range(world)]
+        mine = np.arange(rank, V, world)
+        Es, bs_ = E[mine].copy(), b[mine].copy()
+        accE, accb = np.full_like(Es, 0.1), np.full_like(bs_, 0.1)
+
+        # 1. route: stable partition by owner(i); "peer store" = exchange of the per-owner regions
+        per_owner, send_counts = oidx.route_pairs(ids[rank], cnt[rank], world)
+        inbox = [None] * world
+        dist.all_gather_object(inbox, per_owner)
+        regions = [inbox[s][rank] for s in range(world)]                  # source-major
+        cap = pair_capacity(B, world)
+        keys, x, n_valid, over = oidx.collect_pairs(regions, cap, V)
+        assert not over
+        m = n_valid // 2
+        i, j, x = keys[:m], keys[cap:cap + m], x[:m]
+        assert np.all(i % world == rank)
+        exp = oidx.routed_batches(ids, cnt, world)[rank]
+        assert np.array_equal(i, exp[0]) and np.array_equal(j, exp[1]) and np.array_equal(x, exp[2])
+
+        # 2. fetch the partner rows this rank does not own
+        need = np.unique(j[j % world != rank])
+        asks = [None] * world
+        dist.all_gather_object(asks, [need[need % world == o] for o in range(world)])
+        reply = [(Es[asks[s][rank] // world], bs_[asks[s][rank] // world]) for s in range(world)]
+        got = [None] * world
+        dist.all_gather_object(got, reply)
+        Eloc = np.zeros((V, D), np.float32)
+        bloc = np.zeros(V, np.float32)
+        Eloc[mine], bloc[mine] = Es, bs_
+        for o in range(world):
+            if o != rank:
+                want = need[need % world == o]
+                Eloc[want], bloc[want] = got[o][rank]
+
+        # 3. batch sums over ALL ranks (the three-float all-reduce of the step), then the closed-form gradients
+        dot = np.einsum("cd,cd->c", Eloc[i], Eloc[j])
+        bsum = bloc[i] + bloc[j]
+        w, t = og.weight_fn(x), og.log_target_fn(x)
+        res = t - dot
+        part = torch.tensor([w.sum(), (w * res).sum(), (w * res * res).sum(), bsum.sum(), (bsum * bsum).sum(),
+                             (w * (res - bsum) ** 2).sum()], dtype=torch.float64)
+        dist.all_reduce(part)
+        S0, S1, S2, sb, sb2, pp = part.tolist()
+        Bg = float(B * world)
+        if bias_mode == "reference_broadcast":
+            loss = (S2 - 2 * (sb / Bg) * S1 + (sb2 / Bg) * S0) / Bg
+            g = -(2 / Bg) * w * (res - sb / Bg)
+            h = -(2 / (Bg * Bg)) * (S1 - bsum * S0)
+        else:
+            loss = pp / Bg
+            g = -(2 / Bg) * w * (res - bsum)
+            h = g
+        dE = np.zeros((V, D), np.float64)
+        db = np.zeros(V, np.float64)
+        np.add.at(dE, i, g[:, None] * Eloc[j])
+        np.add.at(dE, j, g[:, None] * Eloc[i])
+        np.add.at(db, i, h)
+        np.add.at(db, j, h)
+
+        # 4. gradients of foreign rows return to the owner; the owner merges all sources and applies Adagrad
+        touched = np.unique(np.concatenate([i, j]))
+        outs = [None] * world
+        dist.all_gather_object(outs, [(touched[touched % world == o], dE[touched[touched % world == o]],
+                                       db[touched[touched % world == o]]) for o in range(world)])
+        gE = np.zeros((V, D), np.float64)
+        gb = np.zeros(V, np.float64)
+        for s in range(world):
+            rows, a, c = outs[s][rank]
+            gE[rows] += a
+            gb[rows] += c
+            assert np.all(rows % world == rank)
+        upd = np.unique(np.concatenate([outs[s][rank][0] for s in range(world)]))
+        loc = upd // world
+        Es[loc], accE[loc] = oopt.adagrad_update(Es[loc], gE[upd].astype(np.float32), accE[loc], lr)
+        bs_[loc], accb[loc] = oopt.adagrad_update(bs_[loc], gb[upd].astype(np.float32), accb[loc], lr)
+
+        # oracle: ONE global step on the concatenated batch
+        Eg, bg = E.copy(), b.copy()
+        aE, ab = np.full_like(Eg, 0.1), np.full_like(bg, 0.1)
+        gi = np.concatenate([a[0] for a in ids])
+        gj = np.concatenate([a[1] for a in ids])
+        gx = np.concatenate(cnt)
+        gl = og.step_adagrad(Eg, bg, aE, ab, gi, gj, gx, lr, bias_mode)
+        assert abs(loss - gl) < 2e-5 * max(1.0, abs(gl)), (loss, gl)
+        np.testing.assert_allclose(Es, Eg[mine], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(bs_, bg[mine], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(accE, aE[mine], rtol=2e-5, atol=2e-7)
+        untouched = np.setdiff1d(mine, np.unique(np.concatenate([gi, gj])))
+        assert np.array_equal(Es[untouched // world], E[untouched])       # rows nobody touched are bit-unchanged
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world,bias_mode", [(2, "reference_broadcast"), (2, "per_pair"), (3, "reference_broadcast")])
+def test_owner_routed_glove_decomposition_gloo(world, bias_mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 100) + world + (7 if bias_mode == "per_pair" else 0)
+    procs = [ctx.Process(target=_routed_worker, args=(r, world, port, bias_mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
