@@ -37,7 +37,11 @@ class EsrPlan(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("key_bits", C.c_int32), ("n_slots", C.c_int64),
                 ("keys", C.c_void_p), ("sorted_keys", C.c_void_p), ("perm", C.c_void_p),
                 ("partner", C.c_void_p), ("useg", C.c_void_p), ("uniq", C.c_void_p),
-                ("seg_off", C.c_void_p), ("n_uniq", C.c_void_p), ("n_valid", C.c_void_p)]
+                ("seg_off", C.c_void_p), ("n_uniq", C.c_void_p), ("n_valid", C.c_void_p),
+                ("sort_impl", C.c_int32), ("reserved", C.c_int32)]
+
+
+ESR_SORT_AUTO, ESR_SORT_WIDE, ESR_SORT_LIBRARY = 0, 1, 2
 
 
 class EsrTopkCfg(C.Structure):

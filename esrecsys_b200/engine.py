@@ -107,9 +107,13 @@ class EmbeddingTable:
 class IndexPlan:
     """Device buffers + descriptor of one batch's index plan (EsrPlan)."""
 
-    def __init__(self, n_slots, V, device=None, with_partner=True, n_valid=None):
+    SORTS = {"auto": L.ESR_SORT_AUTO, "wide": L.ESR_SORT_WIDE, "library": L.ESR_SORT_LIBRARY}
+
+    def __init__(self, n_slots, V, device=None, with_partner=True, n_valid=None, sort="auto"):
         """``n_valid``: optional device int32 scalar -- only the first ``n_valid`` SORTED slots are real (the row-sharded
-        path pads its fixed-capacity slot array with a key larger than every row id; EsrPlan.n_valid)."""
+        path pads its fixed-capacity slot array with a key larger than every row id; EsrPlan.n_valid).
+        ``sort``: "wide" = libesr's own radix sort (fastest when SMs are idle while the plan is built), "library" = cub's
+        fat-block sort (cheaper next to the persistent row pass), "auto" = library (EsrPlan.sort_impl)."""
         self.device = _dev(device)
         n = int(n_slots)
         self.n_slots = n
@@ -138,6 +142,7 @@ class IndexPlan:
                                                L.ptr(self.n_uniq))
         self.n_valid = n_valid
         s.n_valid = L.ptr(n_valid) if n_valid is not None else None
+        s.sort_impl = self.SORTS[sort]
         self.s = s
         self._keys = None
 

@@ -608,7 +608,8 @@ class OwnerRoutedGloveTrainer:
         self.keys = [torch.full((n_slots,), V, **i32) for _ in range(self.DEPTH)]
         self.cnt_l = [torch.zeros(B_cap, dtype=torch.float32, device=self.dev) for _ in range(self.DEPTH)]
         self.n_valid = [torch.zeros(1, **i32) for _ in range(self.DEPTH)]
-        self.plans = [IndexPlan(n_slots, V + 1, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]   # pad key = V
+        # pad key = V; libesr's wide sort: SMs idle in the exchange phases while the plan is built (2 GPUs: 265 vs 270 us/step)
+        self.plans = [IndexPlan(n_slots, V + 1, self.dev, n_valid=self.n_valid[k], sort="wide") for k in range(self.DEPTH)]
         self.cplans = [IndexPlan(n_slots, V_max + n_slots, self.dev, n_valid=self.n_valid[k]) for k in range(self.DEPTH)]
         for cp, pl in zip(self.cplans, self.plans):
             cp.s.n_slots = n_slots

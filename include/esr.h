@@ -165,7 +165,17 @@ typedef struct EsrPlan {
                            * fixed-capacity slot array whose padding carries a key larger than every row id, so it sorts
                            * to the end; every consumer (plan, compact plan, prep, row pass, combine) then covers only the
                            * first *n_valid sorted slots.  NULL: all n_slots are real. */
+  int32_t sort_impl;      /* ESR_SORT_*: which slot sort builds the plan (results are identical).  AUTO = LIBRARY. */
+  int32_t reserved;
 } EsrPlan;
+
+/* Slot sort of the plan.  WIDE is libesr's own LSD radix sort (csrc/index_plan.cu: 2048-slot tiles over the whole GPU,
+ * two-level look-back): 56 us for 2^19 slots on an idle B200 against 74 us for LIBRARY (cub::DeviceRadixSort, 60 fat
+ * blocks per pass) -- the faster plan wherever SMs are idle while it runs (the row-sharded step).  Next to the
+ * persistent row pass of the single-GPU pipeline, which leaves it one block slot on 33 SMs, the fat-block sort costs the
+ * step less (profiles/r2_plan_sort.md), hence AUTO.  ESR_PLAN_SORT=own|cub in the environment overrides the field
+ * (measurement control). */
+enum { ESR_SORT_AUTO = 0, ESR_SORT_WIDE = 1, ESR_SORT_LIBRARY = 2 };
 
 size_t esr_plan_workspace_bytes(int64_t n_slots);
 int esr_plan_build_i32(const EsrPlan* plan, void* ws, size_t ws_bytes, esr_stream_t stream);

@@ -33,9 +33,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from esrecsys_b200 import _lib
-    # EsrTable: u32, i32, i64, 2 ptr, 4 ptr ; EsrPlan: u32, i32, i64, 9 ptr (n_valid last) ; EsrGloveCfg: 4x4, 2x8, 4 floats, 2 ints
+    # EsrTable: u32, i32, i64, 2 ptr, 4 ptr ; EsrPlan: u32, i32, i64, 9 ptr, sort_impl + reserved ; EsrGloveCfg: 4x4, 2x8, 4 floats, 2 ints
     assert C.sizeof(_lib.EsrTable) == 16 + 6 * 8
-    assert C.sizeof(_lib.EsrPlan) == 16 + 9 * 8 and _lib.EsrPlan.n_valid.offset == 16 + 8 * 8
+    assert C.sizeof(_lib.EsrPlan) == 16 + 9 * 8 + 8 and _lib.EsrPlan.n_valid.offset == 16 + 8 * 8
+    assert _lib.EsrPlan.sort_impl.offset == 16 + 9 * 8
     assert C.sizeof(_lib.EsrGloveCfg) == 16 + 16 + 16 + 8 + 8 + 24 + 24 + 8      # + loss_log, loss_step, loss_log_len, reserved2, loss_host
     assert _lib.EsrGloveCfg.B.offset == 16 and _lib.EsrGloveCfg.lr.offset == 32
 

@@ -63,6 +63,69 @@ def test_plan_bit_exact(V, B):
     assert np.array_equal(ouniq[remap], oidx.slot_keys(i, j))
 
 
+def _check_plan(plan, keys_np, n_real=None):
+    """Every output of esr_plan_build_i32 against oracle/index.py (stable argsort): bit for bit."""
+    n = keys_np.size
+    n_real = n if n_real is None else n_real
+    osk, operm = oidx.sort_slots(keys_np)
+    sk, perm = plan.sorted_keys[:n].cpu().numpy(), plan.perm[:n].cpu().numpy()
+    assert np.array_equal(sk, osk)
+    assert np.array_equal(perm, operm)
+    ouniq, ooff = oidx.segments(osk[:n_real])
+    U = int(plan.n_uniq.item())
+    assert U == len(ouniq)
+    assert np.array_equal(plan.uniq[:U].cpu().numpy(), ouniq)
+    assert np.array_equal(plan.seg_off[:U + 1].cpu().numpy(), ooff)
+    assert np.array_equal(plan.useg[:n_real].cpu().numpy(), oidx.slot_segment_index(osk[:n_real]))
+    if plan.partner is not None and n % 2 == 0:
+        half = n // 2
+        other = np.where(operm < half, operm + half, operm - half)
+        assert np.array_equal(plan.partner[:n_real].cpu().numpy(), keys_np[other][:n_real])
+
+
+@pytest.mark.parametrize("sort", ["own", "cub"])
+@pytest.mark.parametrize("V,n,dist", [
+    (10, 2, "uniform"), (10, 62, "zipf"), (300, 2046, "uniform"), (300, 2048, "zipf"), (300, 2050, "uniform"),
+    (2 ** 16, 4098, "zipf"), (2 ** 16 + 1, 6144, "uniform"), (10 ** 6, 100000, "zipf"), (10 ** 6, 2 * 262144, "zipf"),
+    (10 ** 6, 2 * 262144, "uniform"), (10 ** 8, 2 * 262144, "zipf"), (10 ** 8, 300002, "uniform"),
+    (2 ** 31 - 1, 70000, "uniform"), (5, 2 * 262144, "uniform"), (10 ** 6, 2 * 262144, "same")])
+def test_plan_sort_every_shape(V, n, dist, sort, monkeypatch):
+    """The two plan builders (libesr's wide sort + fused head pass, cub + the head count / scan / write kernels -- chosen
+    by EsrPlan.sort_impl, here forced through ESR_PLAN_SORT): tile tails, one to four digit passes, skewed / uniform /
+    constant keys, keys up to 2^31 - 2."""
+    eng = _engine()
+    monkeypatch.setenv("ESR_PLAN_SORT", sort)
+    rng = np.random.default_rng(V % 1000 + n)
+    if dist == "uniform":
+        keys = rng.integers(0, V, size=n, dtype=np.int64)
+    elif dist == "zipf":
+        keys = np.minimum(rng.zipf(1.1, size=n) - 1, V - 1)
+    else:
+        keys = np.full(n, V - 1)
+    keys = keys.astype(np.int32)
+    plan = eng.IndexPlan(n, V).build(torch.from_numpy(keys).cuda())
+    _check_plan(plan, keys)
+    # the same plan object again with other keys (workspace counters are re-zeroed by every build)
+    keys2 = np.ascontiguousarray(keys[::-1])
+    plan.build(torch.from_numpy(keys2).cuda())
+    _check_plan(plan, keys2)
+
+
+@pytest.mark.parametrize("n_real", [0, 1, 2047, 2048, 2049, 40000, 65536])
+@pytest.mark.parametrize("sort", ["wide", "library"])
+def test_plan_sort_padded(n_real, sort):
+    """EsrPlan.n_valid: capacity 65536 slots, the tail padded with the key V (sorts last, no segment of its own)."""
+    eng = _engine()
+    V, cap = 5000, 65536
+    rng = np.random.default_rng(n_real)
+    keys = np.full(cap, V, np.int32)
+    keys[:n_real] = np.minimum(rng.zipf(1.2, size=n_real) - 1, V - 1)
+    rng.shuffle(keys)                                   # padding anywhere in the slot array
+    nv = torch.tensor([n_real], dtype=torch.int32, device="cuda")
+    plan = eng.IndexPlan(cap, V + 1, with_partner=False, n_valid=nv, sort=sort).build(torch.from_numpy(keys).cuda())
+    _check_plan(plan, keys, n_real)
+
+
 def test_plan_empty_and_all_same():
     eng = _engine()
     plan = eng.IndexPlan(0, 10).build(torch.zeros(0, dtype=torch.int32, device="cuda"))
