@@ -536,10 +536,10 @@ class OwnerRoutedGloveTrainer:
     oracle.glove.step_adagrad; bench.py --gpus N runs the same check before its timed region)."""
 
     DEPTH = 2
-    # libesr kernels per step (cub sort passes included): route pairs 3, collect 1, plan 8, route plan 3, address plan 2,
-    # gather 2 (rows, biases), prep, pull, resolve, emit plan, rows, combine, finish, merge rows, merge bias, clear map,
-    # 2 all-reduces + 3 barriers
-    LAUNCHES_PER_STEP = 34
+    # libesr kernels per step: route pairs 3, collect 1, plan 5 (digit histogram, 3 sort passes at V <= 2^24, head pass),
+    # route plan 3, address plan 2, gather 2 (rows, biases), prep, pull, resolve, emit plan, rows, combine, finish,
+    # merge rows, merge bias, clear map, 2 all-reduces + 3 barriers
+    LAUNCHES_PER_STEP = 31
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
                  graphs=True, pair_cap=None, impl="auto", row_blocks=None):
