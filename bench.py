@@ -701,14 +701,18 @@ def inbatch_trainer_steps():
     qs, ks = synth.pair_batches(V, V, B, 4, 6)
     sid = [torch.from_numpy(qs[k]).cuda() for k in range(4)]
     pid = [torch.from_numpy(ks[k]).cuda() for k in range(4)]
-    tr = TwoTowerInBatch(ts, tp, B, loss="softmax")
-    ms_eager = timeit(lambda k: tr.step(sid[k % 4], pid[k % 4]))
-    g = tr.graphed(sid[0], pid[0])
-    ms = timeit(lambda k: g(sid[k % 4], pid[k % 4]))
-    out["two_tower_softmax_TRAINER_step_V1M_D256_B4096"] = {
-        "ms_per_step": ms, "ms_per_step_eager_launches": ms_eager, "pairs_per_s": B / (ms * 1e-3), "cuda_graph": True,
-        "includes": "2 id gathers, 2 x (Linear-ReLU-Linear) towers fwd + bwd + Adam (cuBLAS GEMMs through torch), scores + "
-                    "loss + dQ/dK (tcgen05), sparse Adagrad on both tables"}
+    for mm in ("fp32", "tf32"):
+        tr = TwoTowerInBatch(ts, tp, B, loss="softmax", tower_matmul=mm)
+        ms_eager = timeit(lambda k: tr.step(sid[k % 4], pid[k % 4]))
+        g = tr.graphed(sid[0], pid[0])
+        ms = timeit(lambda k: g(sid[k % 4], pid[k % 4]))
+        out["two_tower_softmax_TRAINER_step_V1M_D256_B4096" + ("" if mm == "fp32" else "_tf32_towers")] = {
+            "ms_per_step": ms, "ms_per_step_eager_launches": ms_eager, "pairs_per_s": B / (ms * 1e-3), "cuda_graph": True,
+            "tower_matmul": mm,
+            "includes": "2 id gathers, 2 x (Linear-ReLU-Linear) towers fwd + bwd + Adam (cuBLAS GEMMs through torch: 48 % of "
+                        "the step's kernel time at fp32, profiles/r2_twotower_launches.txt), scores + loss + dQ/dK "
+                        "(tcgen05), sparse Adagrad on both tables"}
+        del tr, g
     return out
 
 

@@ -124,6 +124,40 @@ __global__ void __launch_bounds__(kThreads) k_permute_rows(const float4* __restr
   for (int c = lane; c < D4; c += TPR) d[c] = ld_stream(s + c);
 }
 
+// Sum of the rows g_in[perm[p]], p in [a, b), column c of this lane, in slot order; kSegBatch rows in flight (the adds
+// stay in slot order: batching changes the latency, not the result).
+constexpr int kSegBatch = 8;
+__device__ __forceinline__ float4 sum_slots(const int32_t* __restrict__ perm, const float4* __restrict__ g_in, int D4, int c,
+                                            int a, int b) {
+  float4 acc = f4_zero();
+  for (int p = a; p < b; p += kSegBatch) {
+    int64_t r[kSegBatch];
+#pragma unroll
+    for (int q = 0; q < kSegBatch; ++q) r[q] = p + q < b ? perm[p + q] : -1;
+    float4 v[kSegBatch];
+#pragma unroll
+    for (int q = 0; q < kSegBatch; ++q) v[q] = r[q] >= 0 ? ld_stream(g_in + r[q] * D4 + c) : f4_zero();
+#pragma unroll
+    for (int q = 0; q < kSegBatch; ++q)
+      if (r[q] >= 0) f4_add(acc, v[q]);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float sum_slots_scalar(const int32_t* __restrict__ perm, const float* __restrict__ gb_in, int a,
+                                                  int b) {
+  float acc = 0.f;
+  for (int p = a; p < b; p += kSegBatch) {
+    float v[kSegBatch];
+#pragma unroll
+    for (int q = 0; q < kSegBatch; ++q) v[q] = p + q < b ? gb_in[perm[p + q]] : 0.f;
+#pragma unroll
+    for (int q = 0; q < kSegBatch; ++q)
+      if (p + q < b) acc += v[q];
+  }
+  return acc;
+}
+
 // One group of TPR lanes per unique row: sums the rows g_in[perm[p]] over the row's sorted slots,
 // in slot order (fixed => deterministic).
 template <int TPR>
@@ -136,15 +170,62 @@ __global__ void __launch_bounds__(kThreads) k_segment_sum(const int32_t* __restr
   const int64_t u = (blockIdx.x * (int64_t)kThreads + threadIdx.x) / TPR;
   if (u >= cap || u >= *n_uniq) return;
   const int s0 = seg_off[u], s1 = seg_off[u + 1];
-  for (int c = lane; c < D4; c += TPR) {
-    float4 acc = f4_zero();
-    for (int p = s0; p < s1; ++p) f4_add(acc, ld_stream(g_in + (int64_t)perm[p] * D4 + c));
-    g_out[u * D4 + c] = acc;
+  for (int c = lane; c < D4; c += TPR) g_out[u * D4 + c] = sum_slots(perm, g_in, D4, c, s0, s1);
+  if (lane == 0 && gb_in != nullptr) gb_out[u] = sum_slots_scalar(perm, gb_in, s0, s1);
+}
+
+// Rows of D >= 128: a warp per unique row, and the block's 8 warps TOGETHER on every row of theirs with more than
+// kLongSeg slots (an in-batch id stream is Zipf: the hottest id owns 7 % of the slots, and one warp walking that segment
+// alone was 230 us of a 0.76 ms two-tower step).  A long row is cut into 8 equal pieces, one per warp, summed in slot
+// order and added up in piece order: a fixed tree, so the result does not depend on scheduling.
+constexpr int kLongSeg = 64;
+__global__ void __launch_bounds__(kThreads) k_segment_sum_coop(const int32_t* __restrict__ perm,
+                                                               const int32_t* __restrict__ seg_off,
+                                                               const int32_t* __restrict__ n_uniq, int64_t cap, int D4,
+                                                               const float4* __restrict__ g_in,
+                                                               const float* __restrict__ gb_in, float4* __restrict__ g_out,
+                                                               float* __restrict__ gb_out) {
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ float4 part[];  // [kWarps][D4]
+  __shared__ float part_b[kWarps];
+  __shared__ int long_u[kWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t nu = min((int64_t)*n_uniq, cap);
+  const int64_t u = (int64_t)blockIdx.x * kWarps + w;
+  int s0 = 0, s1 = 0;
+  if (u < nu) {
+    s0 = seg_off[u];
+    s1 = seg_off[u + 1];
   }
-  if (lane == 0 && gb_in != nullptr) {
-    float b = 0.f;
-    for (int p = s0; p < s1; ++p) b += gb_in[perm[p]];
-    gb_out[u] = b;
+  const bool is_long = s1 - s0 > kLongSeg;
+  if (lane == 0) long_u[w] = is_long ? 1 : 0;
+  if (u < nu && !is_long) {
+    for (int c = lane; c < D4; c += 32) g_out[u * D4 + c] = sum_slots(perm, g_in, D4, c, s0, s1);
+    if (lane == 0 && gb_in != nullptr) gb_out[u] = sum_slots_scalar(perm, gb_in, s0, s1);
+  }
+  __syncthreads();
+  for (int x = 0; x < kWarps; ++x) {
+    if (!long_u[x]) continue;  // block-uniform
+    const int64_t ux = (int64_t)blockIdx.x * kWarps + x;
+    const int a = seg_off[ux], b = seg_off[ux + 1];
+    const int piece = (b - a + kWarps - 1) / kWarps;
+    const int pa = min(b, a + w * piece), pb = min(b, pa + piece);
+    for (int c = lane; c < D4; c += 32) part[w * D4 + c] = sum_slots(perm, g_in, D4, c, pa, pb);
+    if (lane == 0 && gb_in != nullptr) part_b[w] = sum_slots_scalar(perm, gb_in, pa, pb);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D4; c += kThreads) {
+      float4 acc = part[c];
+#pragma unroll
+      for (int y = 1; y < kWarps; ++y) f4_add(acc, part[y * D4 + c]);
+      g_out[ux * D4 + c] = acc;
+    }
+    if (threadIdx.x == 0 && gb_in != nullptr) {
+      float acc = part_b[0];
+#pragma unroll
+      for (int y = 1; y < kWarps; ++y) acc += part_b[y];
+      gb_out[ux] = acc;
+    }
+    __syncthreads();
   }
 }
 
@@ -281,6 +362,14 @@ extern "C" int esr_segment_sum_rows_f32(const EsrPlan* plan, int32_t D, const fl
   const int D4 = D / 4;
   const int tpr = tpr_for(D4);
   const unsigned grid = (unsigned)ceil_div(n * tpr, kThreads);
+  const size_t coop_smem = (size_t)(kThreads / 32) * D4 * sizeof(float4);
+  if (tpr == 32 && coop_smem <= 40 * 1024) {
+    k_segment_sum_coop<<<grid, kThreads, coop_smem, static_cast<cudaStream_t>(stream_)>>>(
+        plan->perm, plan->seg_off, plan->n_uniq, n, D4, reinterpret_cast<const float4*>(g_in), gb_in,
+        reinterpret_cast<float4*>(g_out), gb_out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+  }
   ESR_DISPATCH_TPR(tpr, (k_segment_sum<TPR><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
                             plan->perm, plan->seg_off, plan->n_uniq, n, D4, reinterpret_cast<const float4*>(g_in), gb_in,
                             reinterpret_cast<float4*>(g_out), gb_out)));

@@ -100,11 +100,29 @@ class SharedTableInBatch:
         return g
 
 
+class _MatmulPrecision:
+    """fp32 (IEEE, cuBLAS SIMT kernels: exact parity with the NumPy oracle) or tf32 (tensor cores, 10-bit mantissa inputs --
+    what XLA's DEFAULT precision does with a float32 Dense on an NVIDIA GPU) for the GEMMs issued inside the block."""
+
+    def __init__(self, mode):
+        assert mode in ("fp32", "tf32"), mode
+        self.tf32 = mode == "tf32"
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 class MLPTower:
     """``Linear(D, H) -> ReLU -> Linear(H, O)`` with explicit backward; weights updated by ``optax.adam``
-    semantics through ``esr_dense_adam_f32``."""
+    semantics through ``esr_dense_adam_f32``.  The six GEMMs of a step are library calls (cuBLAS through torch): measured
+    share of the configs[3] step in profiles/r2_summary.md section 4."""
 
-    def __init__(self, D, H, O, gen, device, lr=1e-3):
+    def __init__(self, D, H, O, gen, device, lr=1e-3, matmul="fp32"):
+        self.precision = _MatmulPrecision(matmul)
         mk = lambda i, o: (torch.randn(i, o, generator=gen) / np.sqrt(i)).to(device)
         self.p = {"W1": mk(D, H), "b1": torch.zeros(H, device=device), "W2": mk(H, O), "b2": torch.zeros(O, device=device)}
         self.g = {k: torch.zeros_like(v) for k, v in self.p.items()}
@@ -114,18 +132,20 @@ class MLPTower:
 
     def forward(self, x):
         self.x = x
-        self.h = torch.relu(torch.addmm(self.p["b1"], x, self.p["W1"]))
-        return torch.addmm(self.p["b2"], self.h, self.p["W2"])
+        with self.precision:
+            self.h = torch.relu(torch.addmm(self.p["b1"], x, self.p["W1"]))
+            return torch.addmm(self.p["b2"], self.h, self.p["W2"])
 
     def backward(self, dy):
         g = self.g
-        torch.mm(self.h.t(), dy, out=g["W2"])
-        torch.sum(dy, 0, out=g["b2"])
-        dh = torch.mm(dy, self.p["W2"].t())
-        dh.mul_(self.h > 0)
-        torch.mm(self.x.t(), dh, out=g["W1"])
-        torch.sum(dh, 0, out=g["b1"])
-        return torch.mm(dh, self.p["W1"].t())
+        with self.precision:
+            torch.mm(self.h.t(), dy, out=g["W2"])
+            torch.sum(dy, 0, out=g["b2"])
+            dh = torch.mm(dy, self.p["W2"].t())
+            dh.mul_(self.h > 0)
+            torch.mm(self.x.t(), dh, out=g["W1"])
+            torch.sum(dh, 0, out=g["b1"])
+            return torch.mm(dh, self.p["W1"].t())
 
     def update(self):
         self.count += 1
@@ -137,7 +157,8 @@ class TwoTowerInBatch:
     """configs[3]: scene / product id tables + MLP towers, B x B in-batch negatives."""
 
     def __init__(self, scene_table, product_table, B, hidden=None, out=None, lr=0.05, tower_lr=1e-3, loss="softmax",
-                 margin=1.0, scale=1.0, seed=0):
+                 margin=1.0, scale=1.0, seed=0, tower_matmul="fp32"):
+        """``tower_matmul``: "fp32" (default; parity with the oracle at 1e-5) or "tf32" (tensor-core GEMMs in the towers)."""
         for t in (scene_table, product_table):
             assert not t.sparse and t.acc is not None
         self.ts, self.tp, self.B = scene_table, product_table, int(B)
@@ -146,8 +167,8 @@ class TwoTowerInBatch:
         H = int(hidden or D)
         O = int(out or D)
         gen = torch.Generator(device="cpu").manual_seed(seed)
-        self.scene_tower = MLPTower(D, H, O, gen, dev, tower_lr)
-        self.product_tower = MLPTower(D, H, O, gen, dev, tower_lr)
+        self.scene_tower = MLPTower(D, H, O, gen, dev, tower_lr, tower_matmul)
+        self.product_tower = MLPTower(D, H, O, gen, dev, tower_lr, tower_matmul)
         self.scorer = engine.InBatchScorer(B, O, loss=loss, margin=margin, scale=scale, device=dev)
         self.xs = torch.empty(self.B, D, dtype=torch.float32, device=dev)
         self.xp = torch.empty(self.B, D, dtype=torch.float32, device=dev)

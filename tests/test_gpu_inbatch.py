@@ -217,3 +217,63 @@ def test_two_tower_steps_match_oracle():
     np.testing.assert_allclose(tp.rows0.cpu().numpy(), Epo, rtol=1e-3, atol=2e-4)
     for k in ps:
         np.testing.assert_allclose(tr.scene_tower.p[k].cpu().numpy(), ps[k], rtol=1e-3, atol=2e-4)
+
+
+def test_two_tower_tf32_towers_stay_close_and_restore_the_flag():
+    """tower_matmul="tf32": tensor-core GEMMs in the towers (10-bit mantissa inputs) -- loss within 2e-3 of the fp32 oracle
+    on the first step, and torch's global TF32 switch is left as it was found."""
+    from esrecsys_b200 import engine, synth
+    from esrecsys_b200.inbatch import TwoTowerInBatch
+    V, D, B = 3000, 64, 256
+    rng = np.random.default_rng(12)
+    Es = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+    Ep = (rng.standard_normal((V, D)) / D ** 0.5).astype(np.float32)
+    ts = engine.EmbeddingTable.from_dense(Es, sparse=False, adagrad=True)
+    tp = engine.EmbeddingTable.from_dense(Ep, sparse=False, adagrad=True)
+    tr = TwoTowerInBatch(ts, tp, B, lr=0.05, tower_lr=1e-3, loss="softmax", scale=4.0, seed=3, tower_matmul="tf32")
+    ps = {k: v.cpu().numpy().copy() for k, v in tr.scene_tower.p.items()}
+    pp = {k: v.cpu().numpy().copy() for k, v in tr.product_tower.p.items()}
+    mk = lambda p: dict(count=0, mu={k: np.zeros_like(v) for k, v in p.items()}, nu={k: np.zeros_like(v) for k, v in p.items()})
+    s_ids, p_ids = synth.pair_batches(V, V, B, 1, 9)
+    before = torch.backends.cuda.matmul.allow_tf32
+    got = float(tr.step(torch.from_numpy(s_ids[0]).cuda(), torch.from_numpy(p_ids[0]).cuda()).item())
+    assert torch.backends.cuda.matmul.allow_tf32 == before
+    want = oib.two_tower_step(Es.copy(), np.full_like(Es, 0.1), Ep.copy(), np.full_like(Ep, 0.1), ps, pp, mk(ps), mk(pp),
+                              s_ids[0], p_ids[0], 0.05, 1e-3, "softmax", 1.0, 4.0)
+    assert abs(got - want) <= 2e-3 * max(1.0, abs(want)), (got, want)
+
+
+@pytest.mark.parametrize("D", [32, 128, 256])
+def test_segment_sum_rows_long_and_short_segments(D):
+    """esr_segment_sum_rows_f32 (per-row gradient sums of the in-batch trainers, the owner-side merge of the NCCL
+    exchange): one id owning a third of the slots (the block-cooperative path at D >= 128), pairs, singletons; twice
+    the same launch gives the same bits (fixed summation tree)."""
+    import ctypes as C
+    from esrecsys_b200 import _lib as L
+    from esrecsys_b200 import engine
+    n, V = 6000, 4000
+    rng = np.random.default_rng(D)
+    keys = rng.integers(0, V, size=n).astype(np.int32)
+    keys[rng.permutation(n)[:2000]] = 77                      # a 2000-slot segment
+    keys[rng.permutation(n)[:70]] = 1234                      # one just above the long-segment threshold
+    g = rng.standard_normal((n, D)).astype(np.float32)
+    gb = rng.standard_normal(n).astype(np.float32)
+    plan = engine.IndexPlan(n, V, with_partner=False).build(torch.from_numpy(keys).cuda())
+    U = int(plan.n_uniq.item())
+    g_d, gb_d = torch.from_numpy(g).cuda(), torch.from_numpy(gb).cuda()
+    outs = []
+    for _ in range(2):
+        out = torch.full((n, D), np.nan, dtype=torch.float32, device="cuda")
+        outb = torch.full((n,), np.nan, dtype=torch.float32, device="cuda")
+        L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), D, L.ptr(g_d), L.ptr(gb_d), L.ptr(out), L.ptr(outb),
+                                                 L.stream_ptr()), "esr_segment_sum_rows_f32")
+        outs.append((out[:U].cpu().numpy(), outb[:U].cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    uniq, inv = np.unique(keys, return_inverse=True)
+    want = np.zeros((len(uniq), D), np.float64)
+    wantb = np.zeros(len(uniq), np.float64)
+    np.add.at(want, inv, g.astype(np.float64))
+    np.add.at(wantb, inv, gb.astype(np.float64))
+    assert U == len(uniq)
+    np.testing.assert_allclose(outs[0][0], want, rtol=1e-5, atol=2e-5 * np.sqrt(2000))
+    np.testing.assert_allclose(outs[0][1], wantb, rtol=1e-5, atol=2e-5 * np.sqrt(2000))
