@@ -26,7 +26,7 @@ def _inner(params):
 def _row_grads(table, ids, g):
     """Sum the per-example gradient rows ``g`` by table row (scatter-add over duplicates, fixed order)."""
     V, D = table.shape
-    plan = engine.IndexPlan(ids.numel(), V, table.device, with_partner=False).build(ids)
+    plan = engine.IndexPlan(ids.numel(), V, table.device, with_partner=False, sort="wide").build(ids)
     gsum = torch.empty(ids.numel(), D, device=table.device)
     L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), D, L.ptr(g), None, L.ptr(gsum), None, L.stream_ptr()),
             "esr_segment_sum_rows_f32")

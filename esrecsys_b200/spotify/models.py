@@ -113,7 +113,7 @@ class SpotifyModel:
         for name, rows, g, V in (("album_embed", r["album_rows"], r["dXa"], self.max_albums),
                                  ("artist_embed", r["artist_rows"], r["dXr"], self.num_artists)):
             T = rows.numel()
-            plan = engine.IndexPlan(T, V, dev, with_partner=False).build(rows)
+            plan = engine.IndexPlan(T, V, dev, with_partner=False, sort="wide").build(rows)
             gsum = torch.empty(T, self.feature_size, device=dev)
             import ctypes as C
             L.check(L.lib().esr_segment_sum_rows_f32(C.byref(plan.s), self.feature_size, L.ptr(g), None, L.ptr(gsum), None,
