@@ -173,8 +173,8 @@ typedef struct EsrPlan {
  * two-level look-back): 56 us for 2^19 slots on an idle B200 against 74 us for LIBRARY (cub::DeviceRadixSort, 60 fat
  * blocks per pass) -- the faster plan wherever SMs are idle while it runs (the row-sharded step).  Next to the
  * persistent row pass of the single-GPU pipeline, which leaves it one block slot on 33 SMs, the fat-block sort costs the
- * step less (profiles/r2_plan_sort.md), hence AUTO.  ESR_PLAN_SORT=own|cub in the environment overrides the field
- * (measurement control). */
+ * step less (profiles/r2_plan_sort.md), hence AUTO.  Plans of up to 6144 slots are always built by LIBRARY (one
+ * single-tile kernel).  ESR_PLAN_SORT=own|cub in the environment overrides field and threshold (measurement control). */
 enum { ESR_SORT_AUTO = 0, ESR_SORT_WIDE = 1, ESR_SORT_LIBRARY = 2 };
 
 size_t esr_plan_workspace_bytes(int64_t n_slots);

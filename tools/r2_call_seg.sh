@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_inbatch.py tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/seg_tests.log
+timeout 600 python -m pytest tests/test_gpu_inbatch.py tests/test_gpu_models.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/seg_tests.log
 python - <<'PY' 2>&1 | tee gpurun_out/seg_bench.txt
 import json, bench
 r = bench.inbatch_trainer_steps()
