@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -31,6 +32,16 @@ void set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
   } while (0)
 
 int sm_count();  // of the current device (cached per device)
+
+// NVTX range over a C-ABI entry point (header-only NVTX 3: a no-op unless a profiler injects itself), so that a
+// timeline shows the phases of a step -- plan / prep / rows / finish, route / gather / merge -- by name.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define ESR_RANGE(name) ::esr::NvtxRange esr_nvtx_range__(name)
 
 // Largest dynamic shared-memory opt-in already made for ONE kernel, per device (cudaFuncSetAttribute is a per-device
 // setting; a process normally drives one GPU, but nothing here relies on it):

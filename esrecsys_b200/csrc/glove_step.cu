@@ -1598,6 +1598,7 @@ extern "C" size_t esr_glove_workspace_bytes(int64_t B, int32_t D, int32_t chunk)
 
 extern "C" int esr_glove_prep_f32(const EsrTable* t, const EsrPlan* plan, const float* counts, const EsrGloveCfg* cfg,
                                   float* scalars, void* ws, size_t ws_bytes, esr_stream_t stream_) {
+  ESR_RANGE("esr_glove_prep_f32");
   ESR_REQUIRE(cfg_ok(cfg, plan) && glove_table_ok(t, cfg->rows_mode == ESR_ROWS_UPDATE) && scalars != nullptr);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ESR_CUDA(cudaMemsetAsync(scalars, 0, sizeof(float) * ESR_GLOVE_NSCAL, stream));
@@ -1721,19 +1722,23 @@ static int glove_rows_impl(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* 
 
 extern "C" int esr_glove_rows_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* dE,
                                   void* ws, size_t ws_bytes, esr_stream_t stream) {
+  ESR_RANGE("esr_glove_rows_f32");
   return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 3, stream);
 }
 extern "C" int esr_glove_rows_main_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
                                        float* dE, void* ws, size_t ws_bytes, esr_stream_t stream) {
+  ESR_RANGE("esr_glove_rows_main_f32");
   return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 1, stream);
 }
 extern "C" int esr_glove_rows_combine_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars,
                                           float* dE, void* ws, size_t ws_bytes, esr_stream_t stream) {
+  ESR_RANGE("esr_glove_rows_combine_f32");
   return glove_rows_impl(t, plan, cfg, scalars, dE, ws, ws_bytes, 2, stream);
 }
 
 extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrGloveCfg* cfg, float* scalars, float* db,
                                     void* ws, size_t ws_bytes, esr_stream_t stream_) {
+  ESR_RANGE("esr_glove_finish_f32");
   ESR_REQUIRE(cfg_ok(cfg, plan) && glove_table_ok(t, cfg->rows_mode == ESR_ROWS_UPDATE) && scalars != nullptr);
   const bool emit = cfg->rows_mode == ESR_ROWS_EMIT_GRADS;
   if (cfg->B == 0) return ESR_OK;
@@ -1770,6 +1775,7 @@ extern "C" int esr_glove_finish_f32(EsrTable* t, const EsrPlan* plan, const EsrG
 
 extern "C" int esr_glove_step_f32(EsrTable* t, const EsrPlan* plan, const float* counts, const EsrGloveCfg* cfg,
                                   float* scalars, float* dE, float* db, void* ws, size_t ws_bytes, esr_stream_t stream) {
+  ESR_RANGE("esr_glove_step_f32");
   int rc = esr_glove_prep_f32(t, plan, counts, cfg, scalars, ws, ws_bytes, stream);
   if (rc != ESR_OK) return rc;
   rc = esr_glove_rows_f32(t, plan, cfg, scalars, dE, ws, ws_bytes, stream);

@@ -958,6 +958,7 @@ extern "C" int esr_inbatch_ws_layout(const EsrInbatchCfg* cfg, int64_t* out /* [
 
 extern "C" int esr_inbatch_fwd_bwd_bf16(const float* Q, const float* K, const EsrInbatchCfg* cfg, float* dQ, float* dK,
                                         float* loss, void* ws, size_t ws_bytes, esr_stream_t stream_) {
+  ESR_RANGE("esr_inbatch_fwd_bwd_bf16");
   ESR_REQUIRE(ib_cfg_ok(cfg) && Q && K && dQ && dK && loss && ws);
   ESR_REQUIRE((reinterpret_cast<uintptr_t>(Q) % 16) == 0 && (reinterpret_cast<uintptr_t>(K) % 16) == 0 &&
               (reinterpret_cast<uintptr_t>(dQ) % 16) == 0 && (reinterpret_cast<uintptr_t>(dK) % 16) == 0 &&

@@ -373,6 +373,7 @@ using namespace esr;
 extern "C" int esr_peer_gather_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks,
                                    const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t D, float* out,
                                    float* out_bias, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_gather_f32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && cap >= 0 && D > 0 && (D % 4) == 0);
   if (cap == 0) return ESR_OK;
   PeerPtrs pr, pb;
@@ -398,6 +399,7 @@ extern "C" int esr_peer_gather_f32(const void* const* peer_rows, const void* con
 extern "C" int esr_peer_gather_remote_f32(const void* const* peer_rows, const void* const* peer_bias, int32_t n_ranks, int32_t me,
                                           const int32_t* uniq, const int32_t* order, const int32_t* counts, int64_t cap,
                                           int32_t D, float* out, float* out_bias, int32_t parts, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_gather_remote_f32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && cap >= 0 && D > 0 && (D % 4) == 0);
   ESR_REQUIRE((parts & 3) != 0);
   if (cap == 0 || n_ranks == 1) return ESR_OK;  // one rank: nothing is remote
@@ -425,6 +427,7 @@ extern "C" int esr_peer_gather_remote_f32(const void* const* peer_rows, const vo
 extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void* const* peer_send_local, int32_t n_ranks,
                                      int32_t me, int64_t recv_cap, int32_t* recv_ids, int32_t* src_meta, int32_t* slot_map,
                                      int64_t map_stride, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_pull_ids_i32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && recv_cap > 0 && recv_ids && src_meta);
   ESR_REQUIRE(slot_map != nullptr && map_stride > 0);
   PeerPtrs pc, ps;
@@ -442,6 +445,7 @@ extern "C" int esr_peer_pull_ids_i32(const void* const* peer_counts, const void*
 // (so desc holds recv_cap * (n_ranks + 2) ints; counter in src_meta[3n + 1]).
 extern "C" int esr_peer_resolve_i32(int32_t n_ranks, const int32_t* recv_ids, int32_t* src_meta, const int32_t* slot_map,
                                     int64_t map_stride, int32_t* desc, int64_t recv_cap, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_resolve_i32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && desc &&
               recv_cap > 0 && ((recv_cap * n_ranks) % 2) == 0 && (reinterpret_cast<uintptr_t>(desc) % 8) == 0);
   k_peer_resolve<<<4 * sm_count(), kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(n_ranks, recv_ids, src_meta, slot_map,
@@ -458,6 +462,7 @@ extern "C" int esr_peer_apply_parts_f32(EsrTable* shard, const float* inbox_dE, 
                                         const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
                                         int64_t map_stride, const int32_t* desc, int64_t recv_cap, float lr, float eps,
                                         int32_t parts, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_apply_parts_f32");
   ESR_REQUIRE(shard && shard->struct_size >= sizeof(EsrTable) && shard->D > 0 && (shard->D % 4) == 0 && desc);
   ESR_REQUIRE(shard->rows[0] && shard->acc && shard->bias && shard->bias_acc && shard->ver == nullptr);
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && recv_ids && src_meta && slot_map && map_stride > 0 && recv_cap > 0);
@@ -495,6 +500,7 @@ extern "C" int esr_peer_merge_adagrad_f32(EsrTable* shard, const float* inbox_dE
                                           const int32_t* recv_ids, const int32_t* src_meta, int32_t* slot_map,
                                           int64_t map_stride, int32_t* desc, int64_t recv_cap, float lr, float eps,
                                           esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_merge_adagrad_f32");
   const int rc = esr_peer_resolve_i32(n_ranks, recv_ids, const_cast<int32_t*>(src_meta), slot_map, map_stride, desc, recv_cap,
                                       stream_);
   if (rc != ESR_OK) return rc;
@@ -581,6 +587,7 @@ extern "C" size_t esr_peer_sync_bytes(void) { return (size_t)kSyncRing * ESR_MAX
 
 extern "C" int esr_peer_allreduce_f32(void* const* peer_sync, int32_t n_ranks, int32_t me, const float* in, float* out,
                                       int32_t count, uint32_t* seq_counter, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_allreduce_f32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && count >= 0 && count <= kSyncMaxCount);
   ESR_REQUIRE(seq_counter != nullptr && (count == 0 || (in != nullptr && out != nullptr)));
   PeerPtrs ps;
@@ -628,6 +635,7 @@ __global__ void __launch_bounds__(kThreads) k_peer_emit_plan(const __grid_consta
 extern "C" int esr_peer_emit_plan_i32(const void* const* peer_counts, int32_t n_ranks, int32_t me, const int32_t* uniq,
                                       const int32_t* n_uniq, int64_t cap, const int32_t* inv_order, int64_t inbox_cap,
                                       int32_t* emit_map, int32_t* err, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_emit_plan_i32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && cap >= 0 && inbox_cap > 0);
   if (cap == 0) return ESR_OK;
   ESR_REQUIRE(uniq && n_uniq && inv_order && emit_map && err);
@@ -1005,6 +1013,7 @@ extern "C" size_t esr_peer_route_pairs_workspace_bytes(int64_t B) {
 extern "C" int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts, int64_t B, int32_t n_ranks, int32_t me,
                                         void* const* peer_pair_rec, void* const* peer_pair_counts, int32_t* my_counts,
                                         void* ws, size_t ws_bytes, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_route_pairs_i32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && me >= 0 && me < n_ranks && B >= 0 && B < ((int64_t)1 << 30));
   ESR_REQUIRE(my_counts != nullptr);
   PeerPtrs pi, pn;
@@ -1033,6 +1042,7 @@ extern "C" int esr_peer_route_pairs_i32(const int32_t* ids, const float* counts,
 extern "C" int esr_peer_collect_pairs_i32(const void* in_rec, const int32_t* in_counts, int32_t n_ranks,
                                           int64_t B, int64_t B_cap, int32_t pad_key, int32_t* keys, float* counts,
                                           int32_t* n_valid, int32_t* err, esr_stream_t stream_) {
+  ESR_RANGE("esr_peer_collect_pairs_i32");
   ESR_REQUIRE(n_ranks >= 1 && n_ranks <= ESR_MAX_PEERS && B >= 0 && B_cap > 0 && B_cap < ((int64_t)1 << 30));
   ESR_REQUIRE(in_rec && in_counts && keys && counts && n_valid && err && (reinterpret_cast<uintptr_t>(in_rec) % 16) == 0);
   const int64_t want = ceil_div(B_cap, (int64_t)kThreads);

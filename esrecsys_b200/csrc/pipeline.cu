@@ -164,6 +164,7 @@ extern "C" int esr_pipeline_capture_end(EsrPipeline* p, int32_t which, int32_t k
 // Returns the step number in *step_out.
 extern "C" int esr_pipeline_submit(EsrPipeline* p, const void* ids, const void* counts, esr_stream_t caller_stream,
                                    int32_t flags, int64_t* step_out) {
+  ESR_RANGE("esr_pipeline_submit");
   const bool read_loss = (flags & 1) != 0;
   ESR_REQUIRE(ok(p) && ids && counts && p->capturing < 0);
   const int k = (int)(p->t % p->depth);

@@ -337,6 +337,7 @@ using namespace esr;
 extern "C" int esr_stl_triplet_f32(const float* scene, const float* pos, const float* neg, int64_t B, int32_t D,
                                    float regularization, float batch_size, float* d_scene, float* d_pos, float* d_neg,
                                    float* pos_score, float* neg_score, float* loss, float* row_ws, esr_stream_t stream_) {
+  ESR_RANGE("esr_stl_triplet_f32");
   ESR_REQUIRE(B >= 0 && D > 0 && batch_size > 0.f && loss != nullptr);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (B == 0) {
@@ -360,6 +361,7 @@ extern "C" int esr_spotify_fwd_bwd_f32(const float* album_table, int64_t VA, con
                                        const int32_t* neg_artist, float regularization, float* loss, float* dXa,
                                        float* dXr, int32_t* album_rows, int32_t* artist_rows, float* pos_aff, float* neg_aff, float* l2,
                                        esr_stream_t stream_) {
+  ESR_RANGE("esr_spotify_fwd_bwd_f32");
   ESR_REQUIRE(n_playlists >= 0 && F > 0 && 2 * F <= 32 * kMaxColsPerLane && nc >= 1 && o >= 1 && max_m >= 1 && VA > 0);
   if (n_playlists == 0) return ESR_OK;
   ESR_REQUIRE(album_table && artist_table && album_ctx && artist_ctx && next_album && next_artist && next_off &&

@@ -266,6 +266,7 @@ extern "C" size_t esr_route_workspace_bytes(int64_t cap) {
 extern "C" int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, int64_t cap, int32_t n_ranks,
                                   int32_t* order, int32_t* send_local, int32_t* send_counts, int32_t* inv_order, void* ws,
                                   size_t ws_bytes, esr_stream_t stream_) {
+  ESR_RANGE("esr_route_plan_i32");
   ESR_REQUIRE(uniq && n_uniq && order && send_local && send_counts && cap >= 0 && n_ranks >= 1 && n_ranks <= kMaxRanks);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ESR_CUDA(cudaMemsetAsync(send_counts, 0, sizeof(int32_t) * n_ranks, stream));
@@ -296,6 +297,7 @@ extern "C" int esr_route_plan_i32(const int32_t* uniq, const int32_t* n_uniq, in
 
 extern "C" int esr_plan_compact_i32(const EsrPlan* plan, int32_t* sorted_keys, int32_t* partner, int32_t* uniq,
                                     int32_t* scratch, esr_stream_t stream_) {
+  ESR_RANGE("esr_plan_compact_i32");
   ESR_REQUIRE(plan && plan->struct_size >= sizeof(EsrPlan) && sorted_keys && partner && uniq && scratch);
   const int64_t n = plan->n_slots;
   ESR_REQUIRE(n >= 0 && (n % 2) == 0);
@@ -313,6 +315,7 @@ extern "C" int esr_plan_compact_i32(const EsrPlan* plan, int32_t* sorted_keys, i
 
 extern "C" int esr_plan_compact_owner_i32(const EsrPlan* plan, int32_t n_ranks, int32_t me, int32_t base, int32_t* sorted_keys,
                                           int32_t* partner, int32_t* scratch, esr_stream_t stream_) {
+  ESR_RANGE("esr_plan_compact_owner_i32");
   ESR_REQUIRE(plan && plan->struct_size >= sizeof(EsrPlan) && sorted_keys && partner && scratch);
   ESR_REQUIRE(n_ranks >= 1 && me >= 0 && me < n_ranks && base >= 0);
   const int64_t n = plan->n_slots;
@@ -354,6 +357,7 @@ extern "C" int esr_permute_rows_f32(const float* src, const int32_t* idx, const 
 
 extern "C" int esr_segment_sum_rows_f32(const EsrPlan* plan, int32_t D, const float* g_in, const float* gb_in, float* g_out,
                                         float* gb_out, esr_stream_t stream_) {
+  ESR_RANGE("esr_segment_sum_rows_f32");
   ESR_REQUIRE(plan && plan->struct_size >= sizeof(EsrPlan) && D > 0 && (D % 4) == 0);
   const int64_t n = plan->n_slots;
   if (n == 0) return ESR_OK;

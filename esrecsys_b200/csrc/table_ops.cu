@@ -267,6 +267,7 @@ int gather_impl(const EsrTable* t, const int32_t* ids, int64_t n, float* out, cu
 using namespace esr;
 
 extern "C" int esr_table_gather_f32(const EsrTable* t, const int32_t* ids, int64_t n, float* out, esr_stream_t stream) {
+  ESR_RANGE("esr_table_gather_f32");
   ESR_REQUIRE(table_ok(t) && n >= 0 && (n == 0 || (ids != nullptr && out != nullptr)));
   ESR_REQUIRE((reinterpret_cast<uintptr_t>(out) % 16) == 0);
   return gather_impl(t, ids, n, out, static_cast<cudaStream_t>(stream));
@@ -279,6 +280,7 @@ extern "C" int esr_table_export_f32(const EsrTable* t, float* out, esr_stream_t 
 
 extern "C" int esr_sparse_adagrad_f32(EsrTable* t, const int32_t* uniq, const int32_t* n_uniq, int64_t cap,
                                       const float* g, const float* gb, float lr, float eps, esr_stream_t stream_) {
+  ESR_RANGE("esr_sparse_adagrad_f32");
   ESR_REQUIRE(table_ok(t) && cap >= 0 && uniq != nullptr && n_uniq != nullptr);
   ESR_REQUIRE(g == nullptr || (t->acc != nullptr && (reinterpret_cast<uintptr_t>(g) % 16) == 0));
   ESR_REQUIRE(gb == nullptr || (t->bias != nullptr && t->bias_acc != nullptr));
@@ -322,6 +324,7 @@ static unsigned dense_grid(int64_t n) {
 
 extern "C" int esr_dense_adam_f32(float* p, const float* g, float* mu, float* nu, int64_t n, double lr, double b1,
                                   double b2, double eps, int64_t count, esr_stream_t stream_) {
+  ESR_RANGE("esr_dense_adam_f32");
   ESR_REQUIRE(n >= 0 && count >= 1);
   if (n == 0) return ESR_OK;
   ESR_REQUIRE(p && g && mu && nu);
@@ -358,6 +361,7 @@ extern "C" int esr_rowwise_dot_f32(const float* x, const float* y, int64_t B, in
 }
 
 extern "C" int esr_score_all_f32(const EsrTable* t, const float* queries, int32_t T, float* scores, esr_stream_t stream_) {
+  ESR_RANGE("esr_score_all_f32");
   ESR_REQUIRE(table_ok(t) && T >= 1 && T <= kMaxQueries && queries && scores);
   ESR_REQUIRE((reinterpret_cast<uintptr_t>(queries) % 16) == 0);
   if (t->V == 0) return ESR_OK;

@@ -347,6 +347,7 @@ extern "C" size_t esr_topk_workspace_bytes(int64_t N, int32_t D, int32_t T, int3
 
 extern "C" int esr_topk_scan_f32(const EsrTopkCfg* cfg, int32_t* out_idx, float* out_val, void* ws, size_t ws_bytes,
                                  esr_stream_t stream_) {
+  ESR_RANGE("esr_topk_scan_f32");
   ESR_REQUIRE(cfg != nullptr && cfg->struct_size >= sizeof(EsrTopkCfg) && out_idx != nullptr && ws != nullptr);
   ESR_REQUIRE(cfg->rows_a != nullptr && cfg->queries != nullptr && cfg->Da > 0 && (cfg->Da % 4) == 0 && cfg->Db >= 0 &&
               (cfg->Db % 4) == 0);
