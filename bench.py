@@ -295,7 +295,9 @@ def timed_region_sharded(tr, batches, steps, warmup, pinned_loss, world):
         s.wait_event(e0)
     for k in range(steps):
         loss = tr.step(*batches[(warmup + k) % n])
-        if pinned_loss is not None:
+        if pinned_loss is not None and not hasattr(tr, "loss_host"):
+            # (the owner-routed trainer's finish kernel writes every step's loss into pinned host memory itself:
+            # tr.loss_host, 4 bytes per step over PCIe -- checked after the timed region)
             slot = pinned_loss[k % pinned_loss.numel(): k % pinned_loss.numel() + 1]
             if hasattr(tr, "read_loss_to"):
                 tr.read_loss_to(slot)
@@ -305,6 +307,10 @@ def timed_region_sharded(tr, batches, steps, warmup, pinned_loss, world):
         cur.wait_stream(s)
     e1.record()
     torch.cuda.synchronize()
+    if pinned_loss is not None and hasattr(tr, "loss_host"):
+        last = tr.host_loss(tr.t - 1)           # the host really holds the losses of the timed steps
+        if not (last == float(tr.loss.item()) and np.isfinite(last)):
+            raise RuntimeError("host loss mirror %r != device loss %r" % (last, float(tr.loss.item())))
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.barrier()

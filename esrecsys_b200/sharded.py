@@ -22,6 +22,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -628,6 +630,13 @@ class OwnerRoutedGloveTrainer:
         cfg.emit_peers_dE = C.cast(self.p_inbox_dE, C.c_void_p)
         cfg.emit_peers_db = C.cast(self.p_inbox_db, C.c_void_p)
         cfg.n_emit_peers = n
+        # the finish kernel logs every step's (global) loss itself: device log + pinned host mirror (a 4-byte posted PCIe
+        # write per step) -- no copy node between the step graphs (a D2H copy there cost 30 us per step at 2 GPUs)
+        self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        self.loss_step = torch.zeros(1, **i32)
+        self.loss_host = torch.zeros(4096, dtype=torch.float32).pin_memory()
+        cfg.loss_log, cfg.loss_step, cfg.loss_log_len = L.ptr(self.loss_log), L.ptr(self.loss_step), 4096
+        cfg.loss_host = self.loss_host.data_ptr()
         self.recv_cap = self.inbox_cap
         self.recv_ids = torch.empty(self.recv_cap, **i32)
         self.src_meta = torch.zeros(3 * 8 + 4, **i32)
@@ -637,6 +646,8 @@ class OwnerRoutedGloveTrainer:
         self.s_main = torch.cuda.Stream(self.dev)
         self.s_side = torch.cuda.Stream(self.dev)
         self.s_ids = torch.cuda.Stream(self.dev)
+        self.s_copy = torch.cuda.Stream(self.dev)         # host batches: uploaded beside the previous step's routing + plan
+        self.ev_up = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_plan = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.s_gather = torch.cuda.Stream(self.dev)
@@ -650,7 +661,6 @@ class OwnerRoutedGloveTrainer:
         self.g_step = [None] * self.DEPTH
         self.t = 0
         self.loss = None
-        self.loss_log = torch.zeros(4096, dtype=torch.float32, device=self.dev)
         torch.cuda.current_stream().synchronize()
         self._hdls[0].barrier()
 
@@ -788,12 +798,23 @@ class OwnerRoutedGloveTrainer:
         # The trainer runs on its OWN streams.  (Round 1 and the first round-2 version ran the main half on the caller's
         # stream and made the side stream wait for that stream "for the inputs" -- which also made the routing + plan of
         # batch t+1 wait for the whole step t: the two halves never overlapped, step = main + side.)
-        if torch.is_tensor(ids) and ids.is_cuda:
+        on_device = (torch.is_tensor(ids) and ids.is_cuda) or os.environ.get("ESR_ROUTED_COPY_STREAM", "1") == "0"
+        if on_device:
             side.wait_stream(cur)              # device inputs produced on the caller's stream
         side.wait_event(self.ev_done[k])       # step t-2 is done with parity k's buffers on this rank
+        if not on_device:
+            # host batch: its upload runs on a stream of its own, next to routing + plan of the previous step (on the side
+            # stream it sat in front of this step's routing: 3 MB over PCIe, 60 us of the side chain)
+            self.s_copy.wait_event(self.ev_done[k])
+            with torch.cuda.stream(self.s_copy):
+                self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
+                self.st_counts[k].copy_(counts, non_blocking=True)
+                self.ev_up[k].record(self.s_copy)
+            side.wait_event(self.ev_up[k])
         with torch.cuda.stream(side):
-            self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
-            self.st_counts[k].copy_(counts, non_blocking=True)
+            if on_device:
+                self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
+                self.st_counts[k].copy_(counts, non_blocking=True)
             self._keep[k] = (ids, counts)
             if self.g_plan[k] is not None:
                 self.g_plan[k].replay()
@@ -807,9 +828,7 @@ class OwnerRoutedGloveTrainer:
             else:
                 self._step_body(k)
             self.ev_done[k].record(main)
-            slot = self.t % self.loss_log.numel()
-            self.loss_log[slot: slot + 1].copy_(self.step_fn.scalars[L.SC_LOSS: L.SC_LOSS + 1], non_blocking=True)
-        self.loss = self.loss_log[slot]
+        self.loss = self.loss_log[self.t % self.loss_log.numel()]     # written by this step's finish kernel
         self.t += 1
         return self.loss
 
@@ -818,9 +837,14 @@ class OwnerRoutedGloveTrainer:
         self.s_main.synchronize()
         return float(self.loss.item())
 
+    def host_loss(self, step):
+        """Loss of step ``step`` (0-based) from the pinned host mirror the finish kernel writes -- valid once that step
+        has run (``synchronize()``, or simply later: the mirror keeps the last 4096 steps)."""
+        return float(self.loss_host[step % self.loss_host.numel()])
+
     def read_loss_to(self, pinned_slot):
         """Asynchronous device->host copy of the last step's loss into a pinned 1-element tensor, ordered on the trainer's
-        main stream."""
+        main stream.  (Every step's loss also arrives in ``loss_host`` without any copy: ``host_loss``.)"""
         with torch.cuda.stream(self.s_main):
             pinned_slot.copy_(self.loss.reshape(1), non_blocking=True)
 

@@ -41,6 +41,17 @@ def test_struct_layouts_match_header():
     assert _lib.EsrGloveCfg.B.offset == 16 and _lib.EsrGloveCfg.lr.offset == 32
 
 
+def test_header_enums_match_the_binding():
+    """The ESR_SORT_* values of include/esr.h are the ones esrecsys_b200/_lib.py passes in EsrPlan.sort_impl."""
+    import re
+    from esrecsys_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "esr.h")).read()
+    m = re.search(r"enum \{ ESR_SORT_AUTO = (\d+), ESR_SORT_WIDE = (\d+), ESR_SORT_LIBRARY = (\d+) \}", hdr)
+    assert m, "ESR_SORT_* enum not found in include/esr.h"
+    assert tuple(int(x) for x in m.groups()) == (_lib.ESR_SORT_AUTO, _lib.ESR_SORT_WIDE, _lib.ESR_SORT_LIBRARY)
+
+
 def test_pure_queries_work_without_gpu():
     from esrecsys_b200 import _lib
     h = _lib.lib()
