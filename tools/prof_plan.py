@@ -42,7 +42,7 @@ def main():
         os.environ["ESR_PLAN_TRACE"] = "1"
         ids, _ = synth.glove_batches(10 ** 6, a.batch, 1, 7, False)
         keys = torch.from_numpy(ids[0].reshape(-1)).cuda()
-        plan = eng.IndexPlan(2 * a.batch, 10 ** 6)
+        plan = eng.IndexPlan(2 * a.batch, 10 ** 6, sort="wide")
         for _ in range(5):
             plan.build(keys)
         torch.cuda.synchronize()
@@ -79,7 +79,7 @@ def main():
     if a.eager:
         ids, _ = synth.glove_batches(10 ** 6, a.batch, 1, 7, False)
         keys = torch.from_numpy(ids[0].reshape(-1)).cuda()
-        plan = eng.IndexPlan(2 * a.batch, 10 ** 6)
+        plan = eng.IndexPlan(2 * a.batch, 10 ** 6, sort="wide")
         for _ in range(a.eager):
             plan.build(keys)
         torch.cuda.synchronize()
