@@ -170,7 +170,7 @@ typedef struct EsrPlan {
 } EsrPlan;
 
 /* Slot sort of the plan.  WIDE is libesr's own LSD radix sort (csrc/index_plan.cu: 2048-slot tiles over the whole GPU,
- * two-level look-back): 56 us for 2^19 slots on an idle B200 against 74 us for LIBRARY (cub::DeviceRadixSort, 60 fat
+ * two-level look-back): 47 us for 2^19 slots on an idle B200 against 75 us for LIBRARY (cub::DeviceRadixSort, 60 fat
  * blocks per pass) -- the faster plan wherever SMs are idle while it runs (the row-sharded step).  Next to the
  * persistent row pass of the single-GPU pipeline, which leaves it one block slot on 33 SMs, the fat-block sort costs the
  * step less (profiles/r2_plan_sort.md), hence AUTO.  Plans of up to 6144 slots are always built by LIBRARY (one
