@@ -112,8 +112,8 @@ class IndexPlan:
     def __init__(self, n_slots, V, device=None, with_partner=True, n_valid=None, sort="auto"):
         """``n_valid``: optional device int32 scalar -- only the first ``n_valid`` SORTED slots are real (the row-sharded
         path pads its fixed-capacity slot array with a key larger than every row id; EsrPlan.n_valid).
-        ``sort``: "wide" = libesr's own radix sort (fastest when SMs are idle while the plan is built), "library" = cub's
-        fat-block sort (cheaper next to the persistent row pass), "auto" = library (EsrPlan.sort_impl)."""
+        ``sort``: "auto" / "wide" = libesr's own radix sort (cub's single-tile kernel up to 6144 slots), "library" = cub
+        (the measurement control); EsrPlan.sort_impl."""
         self.device = _dev(device)
         n = int(n_slots)
         self.n_slots = n

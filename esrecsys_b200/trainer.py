@@ -106,9 +106,13 @@ class GloveTrainer:
         except Exception:  # pragma: no cover  (interpreter shutdown)
             pass
 
-    # kernels one step launches (libesr only; the radix sort is cub code compiled into libesr)
-    LAUNCHES_PLAN = 8    # iota, cub histogram + <=4 onesweep passes (key_bits<=32), head count, scan, head write
+    # kernels one step launches (libesr only)
     LAUNCHES_STEP = 4    # prep (+ fused reduction and work-list clear), rows, combine, finish
+
+    @property
+    def LAUNCHES_PLAN(self):
+        """digit histogram, one sort pass per 8 key bits (3 at V = 1M, 4 at V = 100M), head pass"""
+        return 2 + (self.plans[0].key_bits + 7) // 8
 
     def _plan_body(self, k, stream=None):
         self.plans[k].build(self.ids[k], stream=stream)

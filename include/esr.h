@@ -165,16 +165,17 @@ typedef struct EsrPlan {
                            * fixed-capacity slot array whose padding carries a key larger than every row id, so it sorts
                            * to the end; every consumer (plan, compact plan, prep, row pass, combine) then covers only the
                            * first *n_valid sorted slots.  NULL: all n_slots are real. */
-  int32_t sort_impl;      /* ESR_SORT_*: which slot sort builds the plan (results are identical).  AUTO = LIBRARY. */
+  int32_t sort_impl;      /* ESR_SORT_*: which slot sort builds the plan (results are identical).  AUTO = WIDE. */
   int32_t reserved;
 } EsrPlan;
 
-/* Slot sort of the plan.  WIDE is libesr's own LSD radix sort (csrc/index_plan.cu: 2048-slot tiles over the whole GPU,
- * two-level look-back): 47 us for 2^19 slots on an idle B200 against 75 us for LIBRARY (cub::DeviceRadixSort, 60 fat
- * blocks per pass) -- the faster plan wherever SMs are idle while it runs (the row-sharded step).  Next to the
- * persistent row pass of the single-GPU pipeline, which leaves it one block slot on 33 SMs, the fat-block sort costs the
- * step less (profiles/r2_plan_sort.md), hence AUTO.  Plans of up to 6144 slots are always built by LIBRARY (one
- * single-tile kernel).  ESR_PLAN_SORT=own|cub in the environment overrides field and threshold (measurement control). */
+/* Slot sort of the plan (results are identical).  WIDE is libesr's own LSD radix sort (csrc/index_plan.cu: 2048-slot
+ * tiles over the whole GPU, two-level look-back, fused head pass): 47 us for 2^19 slots on an idle B200 against 75 us for
+ * LIBRARY (cub::DeviceRadixSort + head count / scan / write kernels), and the faster one inside every trainer step
+ * measured (single-GPU pipeline 146.8 vs 149 us, owner-routed step at 2 GPUs 265 vs 270 us, in-batch step 0.166 vs 0.200
+ * ms; profiles/r2_plan_sort.md).  AUTO = WIDE.  Plans of up to 6144 slots (cub's single-tile kernel wins there) and of
+ * more than 2^20 slots are always built by LIBRARY.  ESR_PLAN_SORT=own|cub in the environment overrides field and
+ * thresholds (measurement control). */
 enum { ESR_SORT_AUTO = 0, ESR_SORT_WIDE = 1, ESR_SORT_LIBRARY = 2 };
 
 size_t esr_plan_workspace_bytes(int64_t n_slots);

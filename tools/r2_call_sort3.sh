@@ -1,9 +1,7 @@
 #!/bin/bash
-# plan builders: parity of all three, standalone time, and the step with cub + fused head pass vs cub + round-1 head kernels
+# step time of the single-GPU pipeline with the wide plan vs the library plan (same box, back to back)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_glove.py tests/test_gpu_virtual_peers.py -x -q -m gpu -k "plan or routed" 2>&1 | tail -5 | tee gpurun_out/sort_tests.log
-timeout 120 python tools/prof_plan.py 2>&1 | tail -3 | tee gpurun_out/sort_prof.json
-for s in cub cub_split cub cub_split own; do
+for s in own cub own cub; do
   ESR_PLAN_SORT=$s timeout 200 python bench.py --no-cpu --no-uniform --no-inbatch --no-table-100m > gpurun_out/sortbench_$s.json 2> gpurun_out/sortbench_$s.err
   python - <<PY
 import json
