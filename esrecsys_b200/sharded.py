@@ -509,6 +509,53 @@ class PeerShardedGloveTrainer:
         return E, b
 
 
+# ---- retrieval over a row-sharded table ("sharded: local top-k -> all-gather -> merge") ---------------
+def merge_topk(cand_val, cand_idx, k, ties_high_index_first=False):
+    """Top-k of per-query candidate lists.  ``cand_val`` f32 (T, M) (-inf = empty), ``cand_idx`` int64 (T, M) global rows
+    (-1 = empty).  Equal scores are ordered by GLOBAL row: lower row first (``jax.lax.top_k``, spotify/train_spotify.py:
+    121-124) or higher row first (the tail of the stable ascending ``argsort`` dump_knn reads, wikipedia/
+    train_cooccurence.py:91-97,121-125).  Returns ``(values (T,k), rows (T,k))``."""
+    order = torch.argsort(cand_idx, dim=1, descending=bool(ties_high_index_first), stable=True)
+    ci, cv = torch.gather(cand_idx, 1, order), torch.gather(cand_val, 1, order)
+    best = torch.argsort(cv, dim=1, descending=True, stable=True)[:, :k]
+    return torch.gather(cv, 1, best), torch.gather(ci, 1, best)
+
+
+def sharded_query_rows(shard_rows, rows, rank, n, group=None):
+    """Rows ``rows`` (global ids, identical on every rank) of a cyclically sharded table, on every rank: each owner
+    contributes the rows it holds, one all-reduce.  ``shard_rows``: this rank's (V_local, D) rows (row r lives at
+    r // n on rank r % n)."""
+    rows = torch.as_tensor(rows, device=shard_rows.device).long()
+    out = torch.zeros(rows.numel(), shard_rows.shape[1], dtype=shard_rows.dtype, device=shard_rows.device)
+    mine = (rows % n) == rank
+    out[mine] = shard_rows[rows[mine] // n]
+    dist.all_reduce(out, group=group)
+    return out
+
+
+def sharded_table_topk(shard_table, queries, k, rank, n, group=None, ties_high_index_first=False, local_topk=None):
+    """dump_knn / find_top_k over a row-sharded table (owner = row % n): every rank scans ITS rows once with the fused
+    score + top-k kernel (esr_topk_scan_f32 through engine.table_topk), the n local lists are all-gathered and merged in
+    the reference's tie order (a row of the global top-k is beaten by fewer than k rows, hence by fewer than k rows of
+    its own shard: it is in its shard's list).  ``queries`` (T, D) must be the same on every rank
+    (``sharded_query_rows``).  Returns ``(values (T,k), global rows (T,k))``, identical on every rank."""
+    from . import engine
+    k = int(k)
+    kl = min(k, int(shard_table.V))
+    val, idx = (local_topk or engine.table_topk)(shard_table, queries, kl, ties_high_index_first)
+    T = val.shape[0]
+    pv = torch.full((T, k), float("-inf"), dtype=torch.float32, device=val.device)
+    pi = torch.full((T, k), -1, dtype=torch.int64, device=val.device)
+    pv[:, :kl] = val
+    pi[:, :kl] = idx.long() * n + rank
+    all_v = torch.empty(n * T, k, dtype=torch.float32, device=val.device)     # rank-major concatenation along dim 0
+    all_i = torch.empty(n * T, k, dtype=torch.int64, device=val.device)
+    dist.all_gather_into_tensor(all_v, pv.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, pi.contiguous(), group=group)
+    return merge_topk(all_v.view(n, T, k).permute(1, 0, 2).reshape(T, n * k),
+                      all_i.view(n, T, k).permute(1, 0, 2).reshape(T, n * k), k, ties_high_index_first)
+
+
 def pair_capacity(B_local, n):
     """Pairs an owner must be able to take per step: its expected share is B_local (the global batch is n * B_local and
     ownership is cyclic over frequency-ranked ids), the margin covers the binomial spread (sigma ~ sqrt(B_local)) many

@@ -320,3 +320,75 @@ def test_owner_routed_glove_decomposition_gloo(world, bias_mode):
     for p in procs:
         p.join(30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _topk_worker(rank, world, port, q):
+    """Retrieval over a row-sharded table (esrecsys_b200/sharded.py sharded_table_topk): local top-k of every shard (here
+    NumPy on the shard, on the GPU the fused scan kernel) -> all-gather -> merge; equals the oracle's top-k over the
+    whole table in BOTH tie conventions, planted exact ties across shards included."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from esrecsys_b200.sharded import merge_topk, sharded_query_rows, sharded_table_topk
+        from oracle import glove as og
+        V, D, k = 103, 8, 10
+        rng = np.random.default_rng(4)
+        E = rng.integers(-3, 4, size=(V, D)).astype(np.float32)          # small integers: many exactly equal scores
+        E[50] = E[7]
+        E[51] = E[7]                                                      # rows 7, 50, 51 tie for every query
+        tokens = np.array([7, 13, 99], np.int32)
+
+        class Shard:
+            pass
+        Shard.V = len(range(rank, V, world))
+        Shard.rows = torch.from_numpy(E[rank::world].copy())
+
+        def local_topk(shard, queries, kl, high_first):
+            sc = shard.rows.numpy() @ queries.numpy().T                   # (V_loc, T)
+            idx = np.arange(shard.V)
+            out_i, out_v = [], []
+            for t in range(sc.shape[1]):
+                order = np.lexsort((-idx if high_first else idx, -sc[:, t]))[:kl]
+                out_i.append(order)
+                out_v.append(sc[order, t])
+            return torch.from_numpy(np.array(out_v, np.float32)), torch.from_numpy(np.array(out_i, np.int32))
+
+        queries = sharded_query_rows(Shard.rows, tokens, rank, world)
+        assert np.array_equal(queries.numpy(), E[tokens])
+        for high_first in (True, False):
+            val, rows = sharded_table_topk(Shard, queries, k, rank, world, ties_high_index_first=high_first,
+                                           local_topk=local_topk)
+            sc = E @ E[tokens].T
+            for t in range(len(tokens)):
+                want = np.lexsort((-np.arange(V) if high_first else np.arange(V), -sc[:, t]))[:k]
+                assert rows[t].tolist() == want.tolist(), (high_first, t, rows[t].tolist(), want.tolist())
+                assert np.array_equal(val[t].numpy(), sc[want, t])
+            if high_first:                                                # the convention dump_knn reads (oracle.glove.top_k)
+                top, _ = og.top_k(E, tokens, k)
+                assert np.array_equal(rows.numpy(), top)
+        # k larger than a shard: padding never wins
+        val, rows = sharded_table_topk(Shard, queries, 60, rank, world, local_topk=local_topk)
+        assert rows.min() >= 0 and torch.isfinite(val).all() and all(len(set(r.tolist())) == 60 for r in rows)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_table_topk_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 100) + world
+    procs = [ctx.Process(target=_topk_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
