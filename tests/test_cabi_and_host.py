@@ -225,3 +225,32 @@ def test_sass_of_the_hot_kernels():
     # TMA-store epilogue of the passes that write the bf16 dL/dS block (the softmax statistics pass, mode 1, writes none)
     assert all("UTMASTG" in v["mn"] for k, v in rows.items() if k.startswith("k_inbatch_scores<") and not k.endswith(", 1>"))
     assert any("UBLKCP" in v["mn"] for k, v in rows.items() if k.startswith("k_glove_rows_tma<"))
+
+
+def test_mlp_tower_parameters_are_views_of_flat_buffers():
+    """MLPTower (configs[3]): parameters, gradients and Adam moments are 16-byte aligned views of four flat buffers, so
+    one esr_dense_adam_f32 launch and one gradient all-reduce per tower cover every tensor (host layout only: no GPU)."""
+    import torch
+    from esrecsys_b200.inbatch import MLPTower
+    gen = torch.Generator().manual_seed(1)
+    t = MLPTower(10, 6, 5, gen, "cpu")                      # odd sizes: W1 60, b1 6 (-> 8), W2 30 (-> 32), b2 5 (-> 8)
+    assert t.flat["p"].numel() == 60 + 8 + 32 + 8
+    for name, buf in t.flat.items():
+        group = getattr(t, {"p": "p", "g": "g", "mu": "mu", "nu": "nu"}[name])
+        for k, v in group.items():
+            off = (v.data_ptr() - buf.data_ptr()) // 4
+            assert 0 <= off and off + v.numel() <= buf.numel() and off % 4 == 0, (name, k, off)
+            assert v.is_contiguous()
+    t.g["W2"].fill_(3.0)
+    t.g["b1"].fill_(-1.0)
+    assert float(t.flat["g"].sum()) == 3.0 * 30 - 6.0        # writes through the views land in the flat buffer
+    x = torch.randn(7, 10, generator=gen)
+    y = t.forward(x)
+    want = torch.relu(x @ t.p["W1"] + t.p["b1"]) @ t.p["W2"] + t.p["b2"]
+    assert torch.allclose(y, want, atol=1e-6)
+    dy = torch.randn(7, 5, generator=gen)
+    dx = t.backward(dy)
+    h = torch.relu(x @ t.p["W1"] + t.p["b1"])
+    assert torch.allclose(t.g["b2"], dy.sum(0), atol=1e-5) and torch.allclose(t.g["W2"], h.t() @ dy, atol=1e-5)
+    dh = (dy @ t.p["W2"].t()) * (h > 0)
+    assert torch.allclose(t.g["b1"], dh.sum(0), atol=1e-5) and torch.allclose(dx, dh @ t.p["W1"].t(), atol=1e-5)
