@@ -148,6 +148,7 @@ _SIGNATURES = {
                                            C.POINTER(C.c_size_t)]),
     "esr_decode_tfrecord_int64": (C.c_int64, [_P, C.c_size_t, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(_P),
                                               C.POINTER(C.c_int64), C.POINTER(_P), C.c_int64, C.POINTER(C.c_size_t)]),
+    "esr_host_shuffle_gather": (C.c_int, [_P, _P, _P, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, _P, _P, _P, C.c_int32]),
     "esr_inbatch_workspace_bytes": (C.c_size_t, [C.POINTER(EsrInbatchCfg)]),
     "esr_inbatch_fwd_bwd_bf16": (C.c_int, [_P, _P, C.POINTER(EsrInbatchCfg), _P, _P, _P, _P, C.c_size_t, _P]),
     "esr_inbatch_ws_layout": (C.c_int, [C.POINTER(EsrInbatchCfg), C.POINTER(C.c_int64)]),

@@ -158,6 +158,119 @@ def batch_stream(blocks, batch_size, shuffle_size=0, rng=None):
             pos += used
 
 
+class _Accumulator:
+    """Incoming (i, j, count) blocks -> contiguous windows of exactly W triples (one copy per window)."""
+
+    def __init__(self):
+        self.chunks, self.size = [], 0
+
+    def push(self, i, j, c):
+        if i.size:
+            self.chunks.append((i, j, c))
+            self.size += i.size
+
+    def take(self, W):
+        oi, oj, oc = np.empty(W, np.int32), np.empty(W, np.int32), np.empty(W, np.float32)
+        pos = 0
+        while pos < W:
+            i, j, c = self.chunks[0]
+            m = min(i.size, W - pos)
+            oi[pos:pos + m], oj[pos:pos + m], oc[pos:pos + m] = i[:m], j[:m], c[:m]
+            pos += m
+            if m == i.size:
+                self.chunks.pop(0)
+            else:
+                self.chunks[0] = (i[m:], j[m:], c[m:])
+        self.size -= W
+        return oi, oj, oc
+
+
+def _prefetch(gen, depth=1):
+    """Runs ``gen`` on a background thread, ``depth`` items ahead (window assembly is NumPy copies: the GIL is released)."""
+    q = queue.Queue(maxsize=depth)
+    end = object()
+
+    def work():
+        try:
+            for item in gen:
+                q.put(item)
+            q.put(end)
+        except Exception as e:  # pragma: no cover  (surfaced to the consumer)
+            q.put(e)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, Exception):
+            raise item
+        yield item
+
+
+def batch_fillers(blocks, batch_size, shuffle_size=0, rng=None, threads=None):
+    """The input stream of ``get_batch`` as ``fill(ids (2,B) int32, counts (B,) f32)`` callables that write a batch
+    straight into its destination (a pinned block of the ring) -- and, for ``shuffle_size`` > 0, shuffle natively: the
+    window's permutation is a keyed bijection evaluated on the fly by ``esr_host_shuffle_gather`` on ``threads`` host
+    threads (250 M pairs/s on 8 cores against 10 M pairs/s for a NumPy permutation + three fancy-index gathers).
+
+    Semantics are the reference's (``get_shuffled_items`` + ``get_batch``, wikipedia/cooccurrence_matrix.py:80-107):
+    consecutive windows of ``shuffle_size`` triples, each shuffled and consumed whole; a batch that starts in the tail of
+    one shuffled window ends in the head of the next; the triples after the last full window are dropped.  The
+    permutation inside a window comes from ``rng`` (one 63-bit seed per window), not the one ``np.random.shuffle`` would
+    draw.  The next window is assembled on a background thread while the current one is consumed."""
+    from .. import _lib as L
+    import ctypes as C
+    rng = rng if rng is not None else np.random.default_rng()
+    B = int(batch_size)
+    W = max(int(shuffle_size), B) if shuffle_size else B
+    threads = int(threads or min(8, len(os.sched_getaffinity(0))))
+    h = L.lib().esr_host_shuffle_gather if shuffle_size else None
+
+    def windows():
+        acc = _Accumulator()
+        for i, j, c in blocks:
+            acc.push(np.asarray(i, np.int32), np.asarray(j, np.int32), np.asarray(c, np.float32))
+            while acc.size >= W:
+                yield acc.take(W) + (int(rng.integers(0, 2 ** 63)) if shuffle_size else 0,)
+
+    def piece(win, k0, m, ids, cnt, d0):
+        """elements [k0, k0 + m) of the (shuffled) window -> positions [d0, d0 + m) of the batch"""
+        wi, wj, wc, seed = win
+        if not shuffle_size:
+            ids[0, d0:d0 + m], ids[1, d0:d0 + m], cnt[d0:d0 + m] = wi[k0:k0 + m], wj[k0:k0 + m], wc[k0:k0 + m]
+            return
+        base = ids.ctypes.data + 4 * d0
+        L.check(h(C.c_void_p(wi.ctypes.data), C.c_void_p(wj.ctypes.data), C.c_void_p(wc.ctypes.data), W, seed, k0, m,
+                  C.c_void_p(base), C.c_void_p(base + 4 * B), C.c_void_p(cnt.ctypes.data + 4 * d0), threads),
+                "esr_host_shuffle_gather")
+
+    def filler(parts):
+        def fill(ids, cnt):
+            assert ids.flags.c_contiguous and ids.shape == (2, B) and ids.dtype == np.int32 and cnt.dtype == np.float32
+            d0 = 0
+            for win, k0, m in parts:
+                piece(win, k0, m, ids, cnt, d0)
+                d0 += m
+        return fill
+
+    it = _prefetch(windows(), depth=1)
+    cur = next(it, None)
+    off = 0
+    while cur is not None:
+        if off + B <= W:
+            yield filler([(cur, off, B)])
+            off += B
+            if off == W:
+                cur, off = next(it, None), 0
+        else:
+            nxt = next(it, None)
+            if nxt is None:
+                return                                  # the tail that does not fill a batch is dropped
+            yield filler([(cur, off, W - off), (nxt, 0, B - (W - off))])
+            cur, off = nxt, B - (W - off)
+
+
 class PinnedBatchLoader:
     """Background thread: batches of ``blocks`` -> a ring of pinned ``(ids (2,B), counts (B,))`` blocks.
 
@@ -167,11 +280,16 @@ class PinnedBatchLoader:
     (the trainer's staging copy of that step has completed) -- ``None``: immediately.
     """
 
-    def __init__(self, blocks, batch_size, make_block, ring=4, shuffle_size=0, rng=None, reusable=None):
+    def __init__(self, blocks, batch_size, make_block, ring=4, shuffle_size=0, rng=None, reusable=None, native=True,
+                 threads=None):
+        """``native``: batches are written into the ring by ``batch_fillers`` (window shuffle in libesr, host threads);
+        ``False``: the NumPy path of ``batch_stream`` (same windows AND same permutations as ``get_batch`` for one rng)."""
         self.B = int(batch_size)
         self.ring = [make_block() for _ in range(int(ring))]
         self._np = [(np.asarray(a), np.asarray(b)) for a, b in self.ring]       # zero-copy NumPy views of the blocks
-        self._src = batch_stream(blocks, self.B, shuffle_size, rng)
+        self._native = bool(native)
+        self._src = (batch_fillers(blocks, self.B, shuffle_size, rng, threads) if self._native
+                     else batch_stream(blocks, self.B, shuffle_size, rng))
         self._ready = queue.Queue(maxsize=len(self.ring) - 1)
         self._reusable = reusable
         self._stop = threading.Event()
@@ -181,14 +299,15 @@ class PinnedBatchLoader:
     def _fill(self):
         k = 0
         try:
-            for bi, bj, bc in self._src:
+            for item in self._src:
                 slot = k % len(self.ring)
                 if k >= len(self.ring) and self._reusable is not None:
                     self._reusable(k - len(self.ring))          # the step that last used this block has been staged
                 ids, cnt = self._np[slot]
-                ids[0, :] = bi
-                ids[1, :] = bj
-                cnt[:] = bc
+                if self._native:
+                    item(ids, cnt)
+                else:
+                    ids[0, :], ids[1, :], cnt[:] = item
                 while not self._stop.is_set():
                     try:
                         self._ready.put(slot, timeout=0.1)

@@ -470,6 +470,14 @@ int64_t esr_decode_tfrecord_int64(const uint8_t* data, size_t n_bytes, int32_t n
                                   int64_t* const* vals, const int64_t* val_cap, int64_t* const* offs,
                                   int64_t max_records, size_t* consumed);
 
+/* Window shuffle of the host input pipeline (HOST pointers; get_shuffled_items, wikipedia/cooccurrence_matrix.py:80-87).
+ * pi = a pseudo-random permutation of [0, n) fixed by `seed` (keyed multiply / xor-shift bijection, cycle-walked; never
+ * stored);
+ * dst_*[a] = src_*[pi(k0 + a)] for a in [0, m): elements [k0, k0 + m) of the shuffled window, gathered by `threads` host
+ * threads straight into their destination (a pinned batch block).  k0 + m <= n. */
+int esr_host_shuffle_gather(const int32_t* i, const int32_t* j, const float* c, int64_t n, uint64_t seed, int64_t k0,
+                            int64_t m, int32_t* dst_i, int32_t* dst_j, float* dst_c, int32_t threads);
+
 /* OWNER-COMPUTES pair routing (csrc/peer_ops.cu): a pair (i, j, x) is processed by the rank owning row i, so only the
  * unique partner rows j cross NVLink (4.3x fewer bytes on the bench stream at 8 ranks than keeping the pairs where they
  * arrived).  esr_peer_route_pairs_i32 (source side; depends on the ids only) partitions the (2,B) batch STABLY by
