@@ -290,7 +290,11 @@ class PinnedBatchLoader:
         self._native = bool(native)
         self._src = (batch_fillers(blocks, self.B, shuffle_size, rng, threads) if self._native
                      else batch_stream(blocks, self.B, shuffle_size, rng))
-        self._ready = queue.Queue(maxsize=len(self.ring) - 1)
+        self._ready = queue.Queue()
+        self._free = queue.Queue()                      # blocks the consumer is done with (FIFO: batch k uses block k % ring)
+        for slot in range(len(self.ring)):
+            self._free.put(slot)
+        self._held = None                               # the block handed out last: released by the NEXT __next__ call
         self._reusable = reusable
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._fill, daemon=True)
@@ -300,7 +304,14 @@ class PinnedBatchLoader:
         k = 0
         try:
             for item in self._src:
-                slot = k % len(self.ring)
+                slot = None
+                while slot is None:
+                    if self._stop.is_set():
+                        return
+                    try:
+                        slot = self._free.get(timeout=0.1)
+                    except queue.Empty:
+                        continue
                 if k >= len(self.ring) and self._reusable is not None:
                     self._reusable(k - len(self.ring))          # the step that last used this block has been staged
                 ids, cnt = self._np[slot]
@@ -308,14 +319,7 @@ class PinnedBatchLoader:
                     item(ids, cnt)
                 else:
                     ids[0, :], ids[1, :], cnt[:] = item
-                while not self._stop.is_set():
-                    try:
-                        self._ready.put(slot, timeout=0.1)
-                        break
-                    except queue.Full:
-                        continue
-                if self._stop.is_set():
-                    return
+                self._ready.put(slot)
                 k += 1
             self._ready.put(None)
         except Exception as e:  # pragma: no cover
@@ -325,11 +329,17 @@ class PinnedBatchLoader:
         return self
 
     def __next__(self):
+        """The next batch block.  It stays untouched until the following ``__next__`` call (and, with ``reusable``, until
+        the trainer has staged it)."""
+        if self._held is not None:
+            self._free.put(self._held)
+            self._held = None
         slot = self._ready.get()
         if slot is None:
             raise StopIteration
         if isinstance(slot, Exception):
             raise slot
+        self._held = slot
         return self.ring[slot]
 
     def close(self):
