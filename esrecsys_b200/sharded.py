@@ -152,9 +152,9 @@ class RowExchange:
 
 
 class ShardedGloveTrainer:
-    # libesr kernels one step launches (cub sort passes included, NCCL excluded): plan 8, route 5, owner gathers 2,
-    # row permutes 3, compact 2, prep / rows / combine / finish 4, owner plan 8 + segment sum 1 + Adagrad 2
-    LAUNCHES_PER_STEP = 35
+    # libesr kernels one step launches (NCCL excluded): plan 5 (digit histogram, 3 sort passes, head pass), route 5, owner
+    # gathers 2, row permutes 3, compact 2, prep / rows / combine / finish 4, owner plan 5 + segment sum 1 + Adagrad 2
+    LAUNCHES_PER_STEP = 29
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0):
         L.require_cuda()
@@ -241,9 +241,10 @@ class PeerShardedGloveTrainer:
     """
 
     DEPTH = 2
-    # libesr kernels one step launches (NCCL all-reduces and symmetric-memory barriers excluded): plan 8, route 5,
-    # compact 2, gather, prep, pull, resolve, emit plan, rows, combine, finish, merge, clear map
-    LAUNCHES_PER_STEP = 25
+    # libesr kernels one step launches (NCCL all-reduces and symmetric-memory barriers excluded): plan 5 (digit histogram,
+    # 3 sort passes, head pass), route 5, compact 2, gather, prep, pull, resolve, emit plan, rows, combine, finish, merge,
+    # clear map
+    LAUNCHES_PER_STEP = 22
 
     def __init__(self, V, D, B_local, lr=0.05, bias_mode="reference_broadcast", group=None, device=None, chunk=0,
                  graphs=False, fast_sync=False, overlap_ids=False, impl="auto"):
