@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "ldg", "tma", "fifo", "endfirst"])
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=16, help="timed steps of the CPU baseline leg (10-30 s of host work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-uniform", action="store_true")
     ap.add_argument("--no-inbatch", action="store_true")
