@@ -846,13 +846,14 @@ class OwnerRoutedGloveTrainer:
         # The trainer runs on its OWN streams.  (Round 1 and the first round-2 version ran the main half on the caller's
         # stream and made the side stream wait for that stream "for the inputs" -- which also made the routing + plan of
         # batch t+1 wait for the whole step t: the two halves never overlapped, step = main + side.)
-        on_device = (torch.is_tensor(ids) and ids.is_cuda) or os.environ.get("ESR_ROUTED_COPY_STREAM", "1") == "0"
+        on_device = torch.is_tensor(ids) and ids.is_cuda
         if on_device:
             side.wait_stream(cur)              # device inputs produced on the caller's stream
         side.wait_event(self.ev_done[k])       # step t-2 is done with parity k's buffers on this rank
         if not on_device:
-            # host batch: its upload runs on a stream of its own, next to routing + plan of the previous step (on the side
-            # stream it sat in front of this step's routing: 3 MB over PCIe, 60 us of the side chain)
+            # host batch: its upload runs on a stream of its own, next to routing + plan of the previous step instead of in
+            # front of this step's routing (measured at 2 GPUs: no difference, 300 us per e2e step either way -- the side
+            # chain is not the critical path there; what cost 30 us per step was the loss copy between the step graphs)
             self.s_copy.wait_event(self.ev_done[k])
             with torch.cuda.stream(self.s_copy):
                 self.st_ids[k].copy_(ids.reshape(-1), non_blocking=True)
