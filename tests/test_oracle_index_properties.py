@@ -13,7 +13,7 @@ ids_arrays = st.integers(1, 4000).flatmap(
     lambda V: st.tuples(st.just(V), st.lists(st.integers(0, V - 1), min_size=0, max_size=300)))
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=80, deadline=None, derandomize=True)
 @given(ids_arrays)
 def test_sort_is_the_stable_permutation_and_segments_partition_the_slots(arg):
     V, keys = arg
@@ -32,7 +32,7 @@ def test_sort_is_the_stable_permutation_and_segments_partition_the_slots(arg):
         assert np.all(sk[off[u]:off[u + 1]] == uniq[u])
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(ids_arrays, st.integers(1, 8))
 def test_cyclic_sharding_is_a_bijection_and_the_route_plan_groups_by_owner(arg, n):
     V, keys = arg
@@ -56,7 +56,7 @@ pair_batches = st.integers(2, 500).flatmap(lambda V: st.tuples(
     st.lists(st.tuples(st.integers(0, V - 1), st.integers(0, V - 1), st.floats(1.0, 500.0, width=32)), min_size=1, max_size=60)))
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(pair_batches, st.integers(0, 3))
 def test_pair_routing_conserves_every_pair_and_keeps_source_order(arg, seed):
     V, n, pairs = arg
@@ -95,7 +95,7 @@ def test_pair_routing_conserves_every_pair_and_keeps_source_order(arg, seed):
             assert np.array_equal(keys[:m], routed[o][0][:m]) and np.array_equal(keys[cap:cap + m], routed[o][1][:m])
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(st.integers(0, 2 ** 40), st.integers(0, 1000), st.integers(1, 200), st.integers(1, 10 ** 8))
 def test_uniform_sampler_is_in_range_and_a_pure_function_of_seed_and_step(seed, step, n, hi):
     a = oidx.sample_uniform(seed, step, n, hi)
