@@ -22,8 +22,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import os
-
 import torch
 import torch.distributed as dist
 

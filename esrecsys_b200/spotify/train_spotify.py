@@ -12,7 +12,7 @@ import torch
 
 from .. import engine
 from ..train_state import TrainState
-from .models import SpotifyModel, _i32
+from .models import SpotifyModel
 
 
 def train_step(state: TrainState, model: SpotifyModel, examples, regularization=10.0):

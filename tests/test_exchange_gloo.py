@@ -331,7 +331,7 @@ def _topk_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from esrecsys_b200.sharded import merge_topk, sharded_query_rows, sharded_table_topk
+        from esrecsys_b200.sharded import sharded_query_rows, sharded_table_topk
         from oracle import glove as og
         V, D, k = 103, 8, 10
         rng = np.random.default_rng(4)
