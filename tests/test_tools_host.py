@@ -29,3 +29,28 @@ def test_lookup_accounting():
     assert ts.remote_unique(uniq, 1, 4) == 9 - 3
     assert ts.remote_unique(uniq, 0, 1) == 0
     assert ts.lookup_bytes(10, 128) == 10 * (4 + 512)
+
+
+def test_bench_reference_arm_line_matches_the_contract():
+    """`bench.py --impl reference` (CPU only): one JSON line with impl = reference, the metric / unit of our arm, the SAME
+    config keys our N = 1 line carries, the requested steps, and an e2e object with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                        "--vocab", "20000", "--batch", "4096", "--dim", "32"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "pairs/sec" and line["unit"] == "pairs/s"
+    assert line["steps"] == 3 and line["warmup"] == 1 and line["higher_is_better"] is True and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, root)
+    import bench
+    argv, sys.argv = sys.argv, ["bench.py", "--vocab", "20000", "--batch", "4096", "--dim", "32"]
+    try:
+        ours = bench.config_single(bench.parse())
+    finally:
+        sys.argv = argv
+    assert set(line["config"]) == set(ours) and line["config"]["workload"] == ours["workload"]
